@@ -1,0 +1,35 @@
+"""Input generators re-stating the reference's QuickCheck generators (test/Gen.hs).
+
+genNiceFloat (Gen.hs:39-44): frequency 10:40:40 of 0, +everyday, -everyday;
+genEveryday (Gen.hs:130-131, 208-214): uniform on the real interval (2^-24, 2^24-1).
+Seeded (numpy Generator) so every run sees the same cases -- the reference's are unseeded.
+"""
+import numpy as np
+
+EVERYDAY_LO = np.float32(2.0 ** -24)
+EVERYDAY_HI = np.float32(2.0 ** 24 - 1)
+
+
+def gen_everyday(rng: np.random.Generator, size) -> np.ndarray:
+    return rng.uniform(float(EVERYDAY_LO), float(EVERYDAY_HI), size=size).astype(np.float32)
+
+
+def gen_nice_float(rng: np.random.Generator, size) -> np.ndarray:
+    kind = rng.choice(3, size=size, p=[10 / 90, 40 / 90, 40 / 90])
+    v = gen_everyday(rng, size)
+    v = np.where(kind == 0, np.float32(0), np.where(kind == 1, v, -v))
+    return v.astype(np.float32)
+
+
+def nice_scalar(rng) -> np.float32:
+    return gen_nice_float(rng, 1)[0]
+
+
+def gen_unit(rng: np.random.Generator, size) -> np.ndarray:
+    """U(-1,1): the large-n bench distribution."""
+    return rng.uniform(-1.0, 1.0, size=size).astype(np.float32)
+
+
+def span(n: int, inc: int, extra: int = 0) -> int:
+    """Vector length the reference's tests allocate: extra + 1 + (n-1)|inc| (Main.hs:72,122,251)."""
+    return extra + 1 + max(n - 1, 0) * abs(inc)
