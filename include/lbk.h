@@ -1,0 +1,183 @@
+/*
+ * lbk.h -- C ABI of the B200 Level-1 kernel library ("lambda-blas kernels").
+ *
+ * This is the drop-in boundary for ONE path of dlewissandy/lambda-blas: the
+ * single-precision Level-1 routines of Numerical.BLAS.Single
+ * (src/Numerical/BLAS/Single.hs:41-61).  The reference has no plugin interface of
+ * its own; the only FFI it contains is the test oracle binding of
+ * test/Foreign.hs:32-81 (`foreign import ccall "sdot_" ...`) with the marshalling
+ * helpers of test/Foreign.hs:363-396.  Each entry point below names the reference
+ * function it replaces and the Fortran binding whose role it takes.  The Haskell
+ * module a maintainer would add on top of it is hs/Numerical/BLAS/Device.hs and is
+ * described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C linkage, opaque handles, no torch / C++ types in any signature;
+ *   - every function returns an int status, LBK_OK (0) on success; results come
+ *     back through out-pointers; scalars are passed BY VALUE (unlike the Fortran
+ *     by-reference convention of test/Foreign.hs);
+ *   - all lengths, counts and increments are int64_t (Haskell `Int` is 64-bit);
+ *   - degenerate arguments follow the reference, which "does not generally guard
+ *     against invalid values" (Single.hs:32-39): they produce the reference's
+ *     sentinel results (0, -1, unchanged vector) with status LBK_OK.  Non-zero
+ *     statuses are reserved for CUDA/NCCL failures, null handles, spans that fall
+ *     outside a vector (the reference would read out of bounds) and layouts the
+ *     device path does not support (see LBK_ERR_UNSUPPORTED);
+ *   - vector routines are IN PLACE on device vectors and only ENQUEUE work on the
+ *     context's stream; routines returning a scalar synchronise that stream before
+ *     they return.  The reference's PURE results (new vectors, inputs untouched,
+ *     Util.hs:134-142) are obtained by the host layer with lbk_vec_clone + the
+ *     in-place routine, or in one pass with the *_oop ("out of place") variants;
+ *   - one context per host thread, or calls on a context serialised by the caller.
+ *     There is no CPU fallback: without a CUDA device lbk_init fails.
+ */
+#ifndef LBK_H
+#define LBK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBK_VERSION 100 /* 0.1.0 */
+
+enum lbk_status {
+    LBK_OK = 0,
+    LBK_ERR_CUDA = 1,        /* a CUDA runtime call failed; see lbk_last_error */
+    LBK_ERR_NCCL = 2,        /* an NCCL call failed */
+    LBK_ERR_ARG = 3,         /* null handle / pointer, negative length, handle of another context */
+    LBK_ERR_RANGE = 4,       /* 1+(n-1)|inc| exceeds the vector (reference: undefined behaviour) */
+    LBK_ERR_ALIAS = 5,       /* the two operands overlap in a way an in-place parallel update cannot honour */
+    LBK_ERR_UNSUPPORTED = 6, /* e.g. non-unit increment on a sharded vector */
+    LBK_ERR_NOMEM = 7
+};
+
+typedef struct lbk_ctx lbk_ctx;     /* device + stream + scratch (+ communicator) */
+typedef struct lbk_vec lbk_vec;     /* device-resident fp32 vector, or one rank's shard of one */
+typedef struct lbk_event lbk_event; /* CUDA event on the context's stream (timing) */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int lbk_version(void);
+int lbk_device_count(int *count);
+int lbk_init(int device, lbk_ctx **ctx);
+int lbk_shutdown(lbk_ctx *ctx);
+int lbk_sync(lbk_ctx *ctx);                 /* wait for everything enqueued on the context */
+const char *lbk_last_error(lbk_ctx *ctx);   /* text of the last failure ("" if none); ctx may be NULL */
+void *lbk_stream(lbk_ctx *ctx);             /* the cudaStream_t all work is enqueued on */
+int lbk_sm_count(lbk_ctx *ctx, int *sms);
+/* Select the launch shape of a routine ("sdot", "saxpy", ..., or "all"): kernel variant (vector width /
+ * unroll / cache policy, see DESIGN.md "Tuning"), threads per block and resident blocks per SM.  A
+ * value <= 0 (variant < 0) restores the default.  Elementwise results never depend on the shape;
+ * reductions are deterministic for a given shape. */
+int lbk_set_launch(lbk_ctx *ctx, const char *routine, int variant, int threads, int blocks_per_sm);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int lbk_launch_count(lbk_ctx *ctx, int64_t *launches);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink -------------------------------------- */
+/* Rank 0 makes an id and hands the 128 bytes to every rank (any transport; the host layer uses
+ * torch.distributed); then every rank calls lbk_comm_init.  After that, vectors made with
+ * lbk_vec_alloc_sharded are contiguous block shards and the reductions finish with one exchange. */
+int lbk_comm_unique_id(char id[128]);
+int lbk_comm_init(lbk_ctx *ctx, int nranks, int rank, const char id[128]);
+int lbk_comm_info(lbk_ctx *ctx, int *nranks, int *rank);
+/* Block partition of [0, global_len) used by lbk_vec_alloc_sharded: rank r owns [lo, hi). */
+int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t *lo, int64_t *hi);
+
+/* ---- device vectors (the representation added beside Numerical.BLAS.Types, Types.hs:3) ----- */
+int lbk_vec_alloc(lbk_ctx *ctx, int64_t len, lbk_vec **v);
+int lbk_vec_alloc_sharded(lbk_ctx *ctx, int64_t global_len, lbk_vec **v);
+int lbk_vec_wrap(lbk_ctx *ctx, void *device_ptr, int64_t len, lbk_vec **v); /* non-owning */
+int lbk_vec_view(const lbk_vec *v, int64_t offset, int64_t len, lbk_vec **view); /* non-owning */
+int lbk_vec_free(lbk_vec *v);
+int lbk_vec_len(const lbk_vec *v, int64_t *local_len, int64_t *global_len, int64_t *shard_offset);
+void *lbk_vec_ptr(const lbk_vec *v);
+int lbk_vec_upload(lbk_vec *v, const float *host, int64_t len);        /* host -> device, synchronous */
+int lbk_vec_download(const lbk_vec *v, float *host, int64_t len);      /* device -> host, synchronous */
+int lbk_vec_upload_async(lbk_vec *v, const float *host, int64_t len);  /* enqueue only (pin the host buffer) */
+int lbk_vec_download_async(const lbk_vec *v, float *host, int64_t len);
+int lbk_vec_clone(const lbk_vec *v, lbk_vec **out);
+/* Synthetic data, generated on the device from a counter hash of (seed, GLOBAL index), so shards of
+ * any world size hold the same logical vector: v[i] = lo + (hi-lo) * u24(splitmix64(seed, i)). */
+int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, float lo, float hi);
+int lbk_vec_fill(lbk_vec *v, float value);
+/* Pinned host memory for the transfers above. */
+int lbk_host_alloc(int64_t nfloats, float **host);
+int lbk_host_free(float *host);
+
+/* ---- timing on the context's stream ---------------------------------------------------------- */
+int lbk_event_create(lbk_ctx *ctx, lbk_event **ev);
+int lbk_event_record(lbk_event *ev);
+int lbk_event_elapsed_ms(lbk_event *start, lbk_event *stop, float *ms); /* synchronises on `stop` */
+int lbk_event_destroy(lbk_event *ev);
+
+/* ---- reductions ------------------------------------------------------------------------------ */
+/* dot / sdot, Single.hs:73-87 (Fortran role: "sdot_", test/Foreign.hs:48): sum of x[kx(i)]*y[ky(i)],
+ * kx(i) = first(n,incx) + i*incx, first(n,inc) = inc>0 ? 0 : (1-n)*inc (Single.hs:91-96);
+ * inc == 0 replicates element 0 (Util.hs:86).  n <= 0 gives 0. */
+int lbk_sdot(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out);
+/* sdsdot, Single.hs:231-262 ("sdsdot_", Foreign.hs:52): sb + sum in double, rounded once to float. */
+int lbk_sdsdot(lbk_ctx *ctx, int64_t n, float sb, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out);
+/* asum / sasum, Single.hs:155-168 ("sasum_", Foreign.hs:36): 0 when incx < 1. */
+int lbk_sasum(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, float *out);
+/* nrm2 / snrm2, Single.hs:174-204 ("snrm2_", Foreign.hs:54): 0 when n<1 or incx<1, |x[0]| when n==1;
+ * overflow/underflow-safe scaled accumulation. */
+int lbk_snrm2(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, float *out);
+/* iamax / isamax, Single.hs:211-225 ("isamax_", Foreign.hs:32): 0-based LOGICAL index of the first
+ * element of largest |x|; -1 when n<1 or incx<1; 0 when n==1.  Bit-exact, including ties and NaN
+ * (a NaN wins only at logical index 0). */
+int lbk_isamax(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, int64_t *out);
+/* Enqueue-only forms: the result is written to out_dev[0] (isamax: the int64 into the 8 bytes of
+ * out_dev[0..1]) on the stream; nothing is synchronised.  `out_dev` is a device vector. */
+int lbk_sdot_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *out_dev);
+int lbk_sasum_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *out_dev);
+int lbk_snrm2_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *out_dev);
+int lbk_isamax_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *out_dev);
+
+/* ---- elementwise (in place, enqueue only) ------------------------------------------------------ */
+/* axpy / saxpy, Single.hs:430-444 ("saxpy_", Foreign.hs:40): y[ky(i)] += a*x[kx(i)], product rounded
+ * before the add, NO a==0 shortcut. */
+int lbk_saxpy(lbk_ctx *ctx, int64_t n, float a, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy);
+/* scal / sscal, Single.hs:101-116 ("sscal_", Foreign.hs:74): x[i*incx] *= a for incx >= 1; incx <= 0
+ * follows the reference's index stream (unchanged for n>1 and incx<0; x[0]*a once otherwise). */
+int lbk_sscal(lbk_ctx *ctx, int64_t n, float a, lbk_vec *x, int64_t incx);
+/* copy / scopy, Single.hs:119-132 ("scopy_", Foreign.hs:44): y[ky(i)] = x[kx(i)]; incy==0 leaves the
+ * LAST sampled x in y[0]. */
+int lbk_scopy(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy);
+/* swap / sswap, Single.hs:135-150 ("sswap_", Foreign.hs:78). */
+int lbk_sswap(lbk_ctx *ctx, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy);
+/* rot / srot, Single.hs:408-424 ("srot_", Foreign.hs:58): x' = c*x + s*y, y' = c*y - s*x, both from
+ * the old values, each product rounded separately. */
+int lbk_srot(lbk_ctx *ctx, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, float c, float s);
+/* rotm / srotm, Single.hs:463-487 ("srotm_", Foreign.hs:66).  param is the BLAS sparam array
+ * [flag,h11,h21,h12,h22] (Foreign.hs:276-280); flag -2 is a no-op that launches nothing. */
+int lbk_srotm(lbk_ctx *ctx, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, const float param[5]);
+
+/* ---- out-of-place forms: the reference's pure results in one pass ------------------------------- */
+/* yout (same length as y) = updateElems result of Util.hs:134-142: y with the touched slots replaced,
+ * everything else copied.  yout must not overlap x or y. */
+int lbk_saxpy_oop(lbk_ctx *ctx, int64_t n, float a, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout);
+int lbk_sscal_oop(lbk_ctx *ctx, int64_t n, float a, const lbk_vec *x, int64_t incx, lbk_vec *xout);
+int lbk_scopy_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout);
+int lbk_sswap_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *xout, lbk_vec *yout);
+int lbk_srot_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float c, float s, lbk_vec *xout, lbk_vec *yout);
+int lbk_srotm_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, const float param[5], lbk_vec *xout, lbk_vec *yout);
+
+/* ---- host scalars (O(1); stay on the CPU like the reference's) ---------------------------------- */
+/* rotg / srotg, Single.hs:274-300 ("srotg_", Foreign.hs:62): out = (r, z, c, s) (Types.hs:8). */
+int lbk_srotg(float sa, float sb, float out[4]);
+/* rotmg / srotmg + checkscale, Single.hs:318-401 ("srotmg_", Foreign.hs:70).
+ * out = [flag, d1, d2, x1, h11, h12, h21, h22], flag in {-2,-1,0,1} = FLAGNEG2/FLAGNEG1/FLAG0/FLAG1
+ * (Types.hs:15-20); param (may be NULL) receives the BLAS sparam array for lbk_srotm. */
+int lbk_srotmg(float sd1, float sd2, float sx1, float sy1, float out[8], float param[5]);
+
+/* ---- host-side statement of the cross-rank combine (what the finish kernel computes) ------------- */
+/* One 32-byte record per rank, in rank order; used by the CPU tests of the multi-GPU path. */
+typedef struct lbk_record { float f[3]; uint32_t key; int64_t idx; int64_t pad; } lbk_record;
+enum lbk_reduce_kind { LBK_RED_SUM = 0, LBK_RED_NRM2 = 1, LBK_RED_IAMAX = 2 };
+int lbk_combine_records(int kind, const lbk_record *recs, int nranks, float *fout, int64_t *iout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBK_H */

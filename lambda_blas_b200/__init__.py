@@ -1,0 +1,22 @@
+"""lambda_blas_b200 -- the single-precision Level-1 path of dlewissandy/lambda-blas on NVIDIA B200.
+
+  single   : the reference's call surface (Numerical.BLAS.Single) over device vectors, pure results
+  inplace  : the raw in-place / enqueue-only forms of the C ABI
+  types    : Context, DVector, GivensRot, ModGivensRot
+  sharded  : one process per GPU; torch.distributed carries the NCCL id, NCCL carries the records
+
+The compute path is hand-written CUDA for sm_100a in liblbk.so behind the C ABI of include/lbk.h.
+Importing this package without that library raises ImportError -- there is no CPU fallback.
+"""
+from . import _ffi
+
+_ffi.lib()          # fail loudly, at import, if the CUDA library is missing
+
+from .types import Context, DVector, Event, GivensRot, ModGivensRot, FLAGNEG2, hash_fill_reference  # noqa: E402
+from . import single, inplace  # noqa: E402
+from .single import (dot, sdsdot, asum, nrm2, iamax, scal, copy, swap, axpy, rot, rotm, rotg, rotmg,  # noqa: E402,F401
+                     sdot, sasum, snrm2, isamax, sscal, scopy, sswap, saxpy, srot, srotm, srotg, srotmg)
+from ._ffi import LbkError  # noqa: E402,F401
+
+__all__ = ["Context", "DVector", "Event", "GivensRot", "ModGivensRot", "FLAGNEG2", "LbkError", "single", "inplace",
+           "hash_fill_reference"]

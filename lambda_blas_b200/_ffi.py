@@ -1,0 +1,117 @@
+"""ctypes binding of the C ABI in include/lbk.h (lambda_blas_b200/liblbk.so).
+
+This is the same set of symbols the Haskell module hs/Numerical/BLAS/Device.hs imports with
+`foreign import ccall`, in the same argument order.  There is NO fallback: if the CUDA library is
+missing or no device is present, importing / creating a context raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblbk.so")
+
+STATUS_NAMES = {0: "LBK_OK", 1: "LBK_ERR_CUDA", 2: "LBK_ERR_NCCL", 3: "LBK_ERR_ARG", 4: "LBK_ERR_RANGE",
+                5: "LBK_ERR_ALIAS", 6: "LBK_ERR_UNSUPPORTED", 7: "LBK_ERR_NOMEM"}
+
+
+class LbkError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+class Record(C.Structure):
+    """lbk_record: what one rank contributes to a sharded reduction."""
+    _fields_ = [("f", C.c_float * 3), ("key", C.c_uint32), ("idx", C.c_int64), ("pad", C.c_int64)]
+
+
+_i64, _f32, _vp, _int = C.c_int64, C.c_float, C.c_void_p, C.c_int
+_pf32, _pi64, _pvp, _pint = C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); every symbol include/lbk.h declares
+PROTOTYPES = {
+    "lbk_version": (_int, []),
+    "lbk_device_count": (_int, [_pint]),
+    "lbk_init": (_int, [_int, _pvp]),
+    "lbk_shutdown": (_int, [_vp]),
+    "lbk_sync": (_int, [_vp]),
+    "lbk_last_error": (C.c_char_p, [_vp]),
+    "lbk_stream": (_vp, [_vp]),
+    "lbk_sm_count": (_int, [_vp, _pint]),
+    "lbk_set_launch": (_int, [_vp, C.c_char_p, _int, _int, _int]),
+    "lbk_launch_count": (_int, [_vp, _pi64]),
+    "lbk_comm_unique_id": (_int, [C.c_char_p]),
+    "lbk_comm_init": (_int, [_vp, _int, _int, C.c_char_p]),
+    "lbk_comm_info": (_int, [_vp, _pint, _pint]),
+    "lbk_shard_range": (_int, [_i64, _int, _int, _pi64, _pi64]),
+    "lbk_vec_alloc": (_int, [_vp, _i64, _pvp]),
+    "lbk_vec_alloc_sharded": (_int, [_vp, _i64, _pvp]),
+    "lbk_vec_wrap": (_int, [_vp, _vp, _i64, _pvp]),
+    "lbk_vec_view": (_int, [_vp, _i64, _i64, _pvp]),
+    "lbk_vec_free": (_int, [_vp]),
+    "lbk_vec_len": (_int, [_vp, _pi64, _pi64, _pi64]),
+    "lbk_vec_ptr": (_vp, [_vp]),
+    "lbk_vec_upload": (_int, [_vp, _vp, _i64]),
+    "lbk_vec_download": (_int, [_vp, _vp, _i64]),
+    "lbk_vec_upload_async": (_int, [_vp, _vp, _i64]),
+    "lbk_vec_download_async": (_int, [_vp, _vp, _i64]),
+    "lbk_vec_clone": (_int, [_vp, _pvp]),
+    "lbk_vec_fill_hash": (_int, [_vp, C.c_uint64, _f32, _f32]),
+    "lbk_vec_fill": (_int, [_vp, _f32]),
+    "lbk_host_alloc": (_int, [_i64, C.POINTER(_pf32)]),
+    "lbk_host_free": (_int, [_pf32]),
+    "lbk_event_create": (_int, [_vp, _pvp]),
+    "lbk_event_record": (_int, [_vp]),
+    "lbk_event_elapsed_ms": (_int, [_vp, _vp, _pf32]),
+    "lbk_event_destroy": (_int, [_vp]),
+    "lbk_sdot": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pf32]),
+    "lbk_sdsdot": (_int, [_vp, _i64, _f32, _vp, _i64, _vp, _i64, _pf32]),
+    "lbk_sasum": (_int, [_vp, _i64, _vp, _i64, _pf32]),
+    "lbk_snrm2": (_int, [_vp, _i64, _vp, _i64, _pf32]),
+    "lbk_isamax": (_int, [_vp, _i64, _vp, _i64, _pi64]),
+    "lbk_sdot_async": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "lbk_sasum_async": (_int, [_vp, _i64, _vp, _i64, _vp]),
+    "lbk_snrm2_async": (_int, [_vp, _i64, _vp, _i64, _vp]),
+    "lbk_isamax_async": (_int, [_vp, _i64, _vp, _i64, _vp]),
+    "lbk_saxpy": (_int, [_vp, _i64, _f32, _vp, _i64, _vp, _i64]),
+    "lbk_sscal": (_int, [_vp, _i64, _f32, _vp, _i64]),
+    "lbk_scopy": (_int, [_vp, _i64, _vp, _i64, _vp, _i64]),
+    "lbk_sswap": (_int, [_vp, _i64, _vp, _i64, _vp, _i64]),
+    "lbk_srot": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _f32]),
+    "lbk_srotm": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pf32]),
+    "lbk_saxpy_oop": (_int, [_vp, _i64, _f32, _vp, _i64, _vp, _i64, _vp]),
+    "lbk_sscal_oop": (_int, [_vp, _i64, _f32, _vp, _i64, _vp]),
+    "lbk_scopy_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "lbk_sswap_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "lbk_srot_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _f32, _vp, _vp]),
+    "lbk_srotm_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pf32, _vp, _vp]),
+    "lbk_srotg": (_int, [_f32, _f32, _pf32]),
+    "lbk_srotmg": (_int, [_f32, _f32, _f32, _f32, _pf32, _pf32]),
+    "lbk_combine_records": (_int, [_int, C.POINTER(Record), _int, _pf32, _pi64]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load liblbk.so (built by lambda_blas_b200/csrc/Makefile or __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C lambda_blas_b200/csrc` (nvcc, sm_100a). "
+                "lambda_blas_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)      # AttributeError here = header and library out of sync
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(status: int, ctx_handle=None) -> None:
+    if status != 0:
+        msg = lib().lbk_last_error(ctx_handle)
+        raise LbkError(status, msg.decode() if msg else "")

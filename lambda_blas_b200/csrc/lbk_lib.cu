@@ -1,0 +1,941 @@
+// lbk_lib.cu -- the C ABI of include/lbk.h over the sm_100a kernels of lbk_kernels.cuh.
+//
+// Host-side responsibilities (everything the reference's index helpers decide before a loop
+// runs, src/Numerical/BLAS/Util.hs:39-142 and the guards of src/Numerical/BLAS/Single.hs):
+// sentinel results, span checks, choice of the unit-stride or the general-stride kernel,
+// alignment peeling for the 128/256-bit path, snapshots for zero output increments, launch
+// shape, and -- with a communicator -- the one exchange that ends a sharded reduction.
+#include "../../include/lbk.h"
+#include "lbk_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+using lbk::i64;
+using lbk::Record;
+using lbk::FinishArgs;
+
+static_assert(sizeof(lbk_record) == sizeof(Record), "host and device records share a layout");
+
+// ------------------------------------------------------------------------------------------------
+// launch variants: (VEC floats per access, UNROLL accesses in flight per operand, cache POLICY)
+// ------------------------------------------------------------------------------------------------
+#define LBK_VARIANTS(X) \
+    X(0, 4, 4, 1) X(1, 4, 2, 1) X(2, 4, 8, 1) X(3, 8, 2, 1) X(4, 8, 4, 1) X(5, 4, 4, 0) \
+    X(6, 8, 1, 1) X(7, 4, 1, 1) X(8, 1, 4, 1) X(9, 8, 2, 0)
+static const int kVariantVec[] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8};
+constexpr int kNumVariants = 10;
+constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
+constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
+
+enum Routine { R_SDOT, R_SDSDOT, R_SASUM, R_SNRM2, R_ISAMAX, R_SAXPY, R_SSCAL, R_SCOPY, R_SSWAP, R_SROT, R_SROTM, R_COUNT };
+static const char *kRoutineNames[R_COUNT] = {"sdot", "sdsdot", "sasum", "snrm2", "isamax", "saxpy",
+                                             "sscal", "scopy", "sswap", "srot", "srotm"};
+struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
+
+constexpr int kMaxGrid = 148 * 32 * 2;   // partial-record scratch (blocks)
+
+struct lbk_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    Record *partials = nullptr;
+    unsigned *ticket = nullptr;
+    float *snap = nullptr;            // two floats: snapshots of x[0], y[0] for zero output increments
+    void *result_host = nullptr;      // mapped pinned 64 bytes: where synchronous reductions land
+    void *result_dev = nullptr;
+    Record *rec_send = nullptr;       // this rank's record
+    Record *rec_all = nullptr;        // all ranks' records after the exchange
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    LaunchCfg cfg[R_COUNT];
+    int64_t launches = 0;
+    std::string err;
+};
+
+struct lbk_vec {
+    lbk_ctx *ctx;
+    float *ptr;
+    i64 len;          // local length
+    i64 global_len;   // == len unless sharded
+    i64 shard_off;    // global index of local element 0
+    bool owner;
+    bool sharded;
+};
+
+struct lbk_event { lbk_ctx *ctx; cudaEvent_t ev; };
+
+static thread_local std::string g_err;   // failures before a context exists
+
+static int fail(lbk_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg; else g_err = msg;
+    return code;
+}
+#define CU(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail((ctx), LBK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
+    } while (0)
+#define NC(ctx, call)                                                                              \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess)                                                                     \
+            return fail((ctx), LBK_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_));  \
+    } while (0)
+#define KERNEL_CHECK(ctx)                                                                          \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail((ctx), LBK_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+static inline i64 first_index(i64 n, i64 inc) { return inc > 0 ? 0 : (1 - n) * inc; }   // Single.hs:91-96
+static inline i64 iabs64(i64 v) { return v < 0 ? -v : v; }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbk_version(void) { return LBK_VERSION; }
+
+extern "C" int lbk_device_count(int *count)
+{
+    if (!count) return fail(nullptr, LBK_ERR_ARG, "lbk_device_count: null out pointer");
+    CU(nullptr, cudaGetDeviceCount(count));
+    return LBK_OK;
+}
+
+extern "C" int lbk_init(int device, lbk_ctx **out)
+{
+    if (!out) return fail(nullptr, LBK_ERR_ARG, "lbk_init: null out pointer");
+    *out = nullptr;
+    int count = 0;
+    CU(nullptr, cudaGetDeviceCount(&count));
+    if (count <= 0) return fail(nullptr, LBK_ERR_CUDA, "lbk_init: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= count) return fail(nullptr, LBK_ERR_ARG, "lbk_init: no such device");
+    lbk_ctx *c = new (std::nothrow) lbk_ctx();
+    if (!c) return fail(nullptr, LBK_ERR_NOMEM, "lbk_init: out of host memory");
+    c->device = device;
+    for (int r = 0; r < R_COUNT; ++r) c->cfg[r] = LaunchCfg{-1, 0, 0};
+    cudaError_t e;
+#define INIT(call) if ((e = (call)) != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e); delete c; return fail(nullptr, LBK_ERR_CUDA, m); }
+    INIT(cudaSetDevice(device));
+    INIT(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
+    INIT(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    INIT(cudaMalloc(&c->partials, sizeof(Record) * kMaxGrid));
+    INIT(cudaMalloc(&c->ticket, sizeof(unsigned)));
+    INIT(cudaMemset(c->ticket, 0, sizeof(unsigned)));
+    INIT(cudaMalloc(&c->snap, 2 * sizeof(float)));
+    INIT(cudaHostAlloc(&c->result_host, 64, cudaHostAllocMapped));
+    INIT(cudaHostGetDevicePointer(&c->result_dev, c->result_host, 0));
+    INIT(cudaMalloc(&c->rec_send, sizeof(Record)));
+    INIT(cudaMalloc(&c->rec_all, sizeof(Record) * 64));
+    INIT(cudaDeviceSynchronize());
+#undef INIT
+    *out = c;
+    return LBK_OK;
+}
+
+extern "C" int lbk_shutdown(lbk_ctx *c)
+{
+    if (!c) return LBK_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) ncclCommDestroy(c->comm);
+    cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->snap);
+    cudaFree(c->rec_send); cudaFree(c->rec_all);
+    if (c->result_host) cudaFreeHost(c->result_host);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return LBK_OK;
+}
+
+extern "C" int lbk_sync(lbk_ctx *c)
+{
+    if (!c) return fail(nullptr, LBK_ERR_ARG, "lbk_sync: null context");
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LBK_OK;
+}
+
+extern "C" const char *lbk_last_error(lbk_ctx *c) { return c ? c->err.c_str() : g_err.c_str(); }
+extern "C" void *lbk_stream(lbk_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" int lbk_sm_count(lbk_ctx *c, int *sms)
+{
+    if (!c || !sms) return fail(c, LBK_ERR_ARG, "lbk_sm_count: null argument");
+    *sms = c->sms;
+    return LBK_OK;
+}
+
+extern "C" int lbk_set_launch(lbk_ctx *c, const char *routine, int variant, int threads, int blocks_per_sm)
+{
+    if (!c || !routine) return fail(c, LBK_ERR_ARG, "lbk_set_launch: null argument");
+    if (variant >= kNumVariants) return fail(c, LBK_ERR_ARG, "lbk_set_launch: no such variant");
+    if (threads > lbk::kMaxThreads || (threads > 0 && threads % 32 != 0))
+        return fail(c, LBK_ERR_ARG, "lbk_set_launch: threads must be a multiple of 32, at most 512");
+    for (int r = 0; r < R_COUNT; ++r)
+        if (!strcmp(routine, kRoutineNames[r]) || !strcmp(routine, "all")) {
+            c->cfg[r] = LaunchCfg{variant, threads, blocks_per_sm};
+            if (strcmp(routine, "all")) return LBK_OK;
+        }
+    if (!strcmp(routine, "all")) return LBK_OK;
+    return fail(c, LBK_ERR_ARG, std::string("lbk_set_launch: unknown routine ") + routine);
+}
+
+extern "C" int lbk_launch_count(lbk_ctx *c, int64_t *launches)
+{
+    if (!c || !launches) return fail(c, LBK_ERR_ARG, "lbk_launch_count: null argument");
+    *launches = c->launches;
+    return LBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// communicator
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbk_comm_unique_id(char id[128])
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (!id) return fail(nullptr, LBK_ERR_ARG, "lbk_comm_unique_id: null buffer");
+    ncclUniqueId u;
+    NC(nullptr, ncclGetUniqueId(&u));
+    memcpy(id, &u, 128);
+    return LBK_OK;
+}
+
+extern "C" int lbk_comm_init(lbk_ctx *c, int nranks, int rank, const char id[128])
+{
+    if (!c || !id) return fail(c, LBK_ERR_ARG, "lbk_comm_init: null argument");
+    if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return fail(c, LBK_ERR_ARG, "lbk_comm_init: bad rank / world size");
+    if (c->comm) return fail(c, LBK_ERR_ARG, "lbk_comm_init: communicator already attached");
+    CU(c, cudaSetDevice(c->device));
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    NC(c, ncclCommInitRank(&c->comm, nranks, u, rank));
+    c->nranks = nranks;
+    c->rank = rank;
+    return LBK_OK;
+}
+
+extern "C" int lbk_comm_info(lbk_ctx *c, int *nranks, int *rank)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_comm_info: null context");
+    if (nranks) *nranks = c->nranks;
+    if (rank) *rank = c->rank;
+    return LBK_OK;
+}
+
+// contiguous block partition: rank r owns [r*q + min(r,rem), ...) with q = len / nranks
+extern "C" int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t *lo, int64_t *hi)
+{
+    if (global_len < 0 || nranks < 1 || rank < 0 || rank >= nranks || !lo || !hi)
+        return fail(nullptr, LBK_ERR_ARG, "lbk_shard_range: bad argument");
+    const i64 q = global_len / nranks, rem = global_len % nranks;
+    *lo = rank * q + std::min<i64>(rank, rem);
+    *hi = *lo + q + (rank < rem ? 1 : 0);
+    return LBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// vectors
+// ------------------------------------------------------------------------------------------------
+static int make_vec(lbk_ctx *c, float *ptr, i64 len, i64 glen, i64 off, bool owner, bool sharded, lbk_vec **out)
+{
+    lbk_vec *v = new (std::nothrow) lbk_vec{c, ptr, len, glen, off, owner, sharded};
+    if (!v) return fail(c, LBK_ERR_NOMEM, "out of host memory");
+    *out = v;
+    return LBK_OK;
+}
+
+extern "C" int lbk_vec_alloc(lbk_ctx *c, int64_t len, lbk_vec **out)
+{
+    if (!c || !out || len < 0) return fail(c, LBK_ERR_ARG, "lbk_vec_alloc: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    float *p = nullptr;
+    if (len > 0) {
+        cudaError_t e = cudaMalloc(&p, sizeof(float) * (size_t)len);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, LBK_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    }
+    return make_vec(c, p, len, len, 0, true, false, out);
+}
+
+extern "C" int lbk_vec_alloc_sharded(lbk_ctx *c, int64_t global_len, lbk_vec **out)
+{
+    if (!c || !out || global_len < 0) return fail(c, LBK_ERR_ARG, "lbk_vec_alloc_sharded: bad argument");
+    int64_t lo, hi;
+    lbk_shard_range(global_len, c->nranks, c->rank, &lo, &hi);
+    CU(c, cudaSetDevice(c->device));
+    float *p = nullptr;
+    if (hi > lo) {
+        cudaError_t e = cudaMalloc(&p, sizeof(float) * (size_t)(hi - lo));
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, LBK_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    }
+    return make_vec(c, p, hi - lo, global_len, lo, true, c->nranks > 1, out);
+}
+
+extern "C" int lbk_vec_wrap(lbk_ctx *c, void *device_ptr, int64_t len, lbk_vec **out)
+{
+    if (!c || !out || len < 0 || (len > 0 && !device_ptr) || ((uintptr_t)device_ptr & 3))
+        return fail(c, LBK_ERR_ARG, "lbk_vec_wrap: bad argument (null, negative or not 4-byte aligned)");
+    return make_vec(c, (float *)device_ptr, len, len, 0, false, false, out);
+}
+
+extern "C" int lbk_vec_view(const lbk_vec *v, int64_t offset, int64_t len, lbk_vec **out)
+{
+    if (!v || !out || offset < 0 || len < 0 || offset + len > v->len)
+        return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_view: window outside the vector");
+    if (v->sharded) return fail(v->ctx, LBK_ERR_UNSUPPORTED, "lbk_vec_view: views of sharded vectors are not supported");
+    return make_vec(v->ctx, v->ptr + offset, len, len, 0, false, false, out);
+}
+
+extern "C" int lbk_vec_free(lbk_vec *v)
+{
+    if (!v) return LBK_OK;
+    if (v->owner && v->ptr) {
+        cudaSetDevice(v->ctx->device);
+        cudaStreamSynchronize(v->ctx->stream);
+        cudaFree(v->ptr);
+    }
+    delete v;
+    return LBK_OK;
+}
+
+extern "C" int lbk_vec_len(const lbk_vec *v, int64_t *local_len, int64_t *global_len, int64_t *shard_offset)
+{
+    if (!v) return fail(nullptr, LBK_ERR_ARG, "lbk_vec_len: null vector");
+    if (local_len) *local_len = v->len;
+    if (global_len) *global_len = v->global_len;
+    if (shard_offset) *shard_offset = v->shard_off;
+    return LBK_OK;
+}
+
+extern "C" void *lbk_vec_ptr(const lbk_vec *v) { return v ? (void *)v->ptr : nullptr; }
+
+extern "C" int lbk_vec_upload_async(lbk_vec *v, const float *host, int64_t len)
+{
+    if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_upload: bad argument");
+    if (len) CU(v->ctx, cudaMemcpyAsync(v->ptr, host, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream));
+    return LBK_OK;
+}
+extern "C" int lbk_vec_upload(lbk_vec *v, const float *host, int64_t len)
+{
+    int s = lbk_vec_upload_async(v, host, len);
+    return s ? s : lbk_sync(v->ctx);
+}
+extern "C" int lbk_vec_download_async(const lbk_vec *v, float *host, int64_t len)
+{
+    if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_download: bad argument");
+    if (len) CU(v->ctx, cudaMemcpyAsync(host, v->ptr, sizeof(float) * (size_t)len, cudaMemcpyDeviceToHost, v->ctx->stream));
+    return LBK_OK;
+}
+extern "C" int lbk_vec_download(const lbk_vec *v, float *host, int64_t len)
+{
+    int s = lbk_vec_download_async(v, host, len);
+    return s ? s : lbk_sync(v->ctx);
+}
+
+extern "C" int lbk_vec_clone(const lbk_vec *v, lbk_vec **out)
+{
+    if (!v || !out) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_clone: null argument");
+    lbk_vec *w = nullptr;
+    int s = lbk_vec_alloc(v->ctx, v->len, &w);
+    if (s) return s;
+    w->global_len = v->global_len; w->shard_off = v->shard_off; w->sharded = v->sharded;
+    if (v->len) {
+        cudaError_t e = cudaMemcpyAsync(w->ptr, v->ptr, sizeof(float) * (size_t)v->len, cudaMemcpyDeviceToDevice, v->ctx->stream);
+        if (e != cudaSuccess) { lbk_vec_free(w); return fail(v->ctx, LBK_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e)); }
+    }
+    *out = w;
+    return LBK_OK;
+}
+
+static int stream_grid(lbk_ctx *c, i64 n, int threads) { return (int)std::max<i64>(1, std::min<i64>((n + threads - 1) / threads, (i64)c->sms * 16)); }
+
+extern "C" int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, float lo, float hi)
+{
+    if (!v) return fail(nullptr, LBK_ERR_ARG, "lbk_vec_fill_hash: null vector");
+    if (!v->len) return LBK_OK;
+    lbk_ctx *c = v->ctx;
+    CU(c, cudaSetDevice(c->device));
+    lbk::fill_hash_kernel<<<stream_grid(c, v->len, 256), 256, 0, c->stream>>>(v->ptr, v->len, v->shard_off, seed, lo, hi - lo);
+    KERNEL_CHECK(c);
+    return LBK_OK;
+}
+extern "C" int lbk_vec_fill(lbk_vec *v, float value)
+{
+    if (!v) return fail(nullptr, LBK_ERR_ARG, "lbk_vec_fill: null vector");
+    if (!v->len) return LBK_OK;
+    lbk_ctx *c = v->ctx;
+    CU(c, cudaSetDevice(c->device));
+    lbk::fill_kernel<<<stream_grid(c, v->len, 256), 256, 0, c->stream>>>(v->ptr, v->len, value);
+    KERNEL_CHECK(c);
+    return LBK_OK;
+}
+
+extern "C" int lbk_host_alloc(int64_t nfloats, float **host)
+{
+    if (!host || nfloats < 0) return fail(nullptr, LBK_ERR_ARG, "lbk_host_alloc: bad argument");
+    *host = nullptr;
+    if (nfloats == 0) return LBK_OK;
+    cudaError_t e = cudaHostAlloc((void **)host, sizeof(float) * (size_t)nfloats, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, LBK_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+    return LBK_OK;
+}
+extern "C" int lbk_host_free(float *host)
+{
+    if (host) CU(nullptr, cudaFreeHost(host));
+    return LBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// events
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbk_event_create(lbk_ctx *c, lbk_event **out)
+{
+    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_event_create: null argument");
+    lbk_event *e = new (std::nothrow) lbk_event{c, nullptr};
+    if (!e) return fail(c, LBK_ERR_NOMEM, "out of host memory");
+    cudaError_t ce = cudaEventCreate(&e->ev);
+    if (ce != cudaSuccess) { delete e; return fail(c, LBK_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(ce)); }
+    *out = e;
+    return LBK_OK;
+}
+extern "C" int lbk_event_record(lbk_event *e)
+{
+    if (!e) return fail(nullptr, LBK_ERR_ARG, "lbk_event_record: null event");
+    CU(e->ctx, cudaEventRecord(e->ev, e->ctx->stream));
+    return LBK_OK;
+}
+extern "C" int lbk_event_elapsed_ms(lbk_event *a, lbk_event *b, float *ms)
+{
+    if (!a || !b || !ms) return fail(nullptr, LBK_ERR_ARG, "lbk_event_elapsed_ms: null argument");
+    CU(b->ctx, cudaEventSynchronize(b->ev));
+    CU(b->ctx, cudaEventElapsedTime(ms, a->ev, b->ev));
+    return LBK_OK;
+}
+extern "C" int lbk_event_destroy(lbk_event *e)
+{
+    if (e) { cudaEventDestroy(e->ev); delete e; }
+    return LBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// argument checks shared by all routines
+// ------------------------------------------------------------------------------------------------
+struct Operand {
+    const lbk_vec *v;
+    i64 inc;
+    i64 n_local;   // logical elements of this call that live on this rank
+    i64 i0;        // first logical element on this rank (0 unless sharded)
+};
+
+// Validates one operand for a call over n logical elements and resolves sharding.
+static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, i64 inc, i64 n, Operand *op)
+{
+    if (!v) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
+    if (v->ctx != c) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
+    op->v = v; op->inc = inc; op->i0 = 0; op->n_local = n;
+    if (n <= 0) { op->n_local = 0; return LBK_OK; }
+    if (v->sharded) {
+        if (inc != 1) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take unit increments only");
+        if (n > v->global_len) return fail(c, LBK_ERR_RANGE, std::string(who) + ": n exceeds the vector");
+        const i64 lo = v->shard_off, hi = std::min<i64>(n, v->shard_off + v->len);
+        op->n_local = hi > lo ? hi - lo : 0;
+        op->i0 = lo;
+        return LBK_OK;
+    }
+    const i64 span = 1 + (n - 1) * iabs64(inc);
+    if (span > v->len) return fail(c, LBK_ERR_RANGE, std::string(who) + ": 1+(n-1)|inc| exceeds the vector");
+    return LBK_OK;
+}
+
+// touched byte range [lo, hi) of an operand
+static void touched(const Operand &o, const float **lo, const float **hi)
+{
+    const i64 n = o.n_local;
+    *lo = o.v->ptr;
+    *hi = o.v->ptr + (n > 0 ? 1 + (n - 1) * iabs64(o.inc) : 0);
+}
+static bool overlap(const Operand &a, const Operand &b)
+{
+    const float *al, *ah, *bl, *bh;
+    touched(a, &al, &ah); touched(b, &bl, &bh);
+    return al < bh && bl < ah;
+}
+
+static inline int misalign(const float *p, int vec) { return (int)(((uintptr_t)p >> 2) % (uintptr_t)vec); }
+
+// Picks the variant that the pointers' alignment allows and the scalar head count.
+static void resolve_alignment(int *variant, i64 *head, const float *const *ptrs, int nptr, i64 n)
+{
+    for (;;) {
+        const int vec = kVariantVec[*variant];
+        if (vec == 1) { *head = 0; return; }
+        const int m = misalign(ptrs[0], vec);
+        bool same = true;
+        for (int i = 1; i < nptr; ++i) same = same && misalign(ptrs[i], vec) == m;
+        if (same) { *head = std::min<i64>((vec - m) % vec, n); return; }
+        *variant = (vec == 8) ? kVec4Fallback : kScalarVariant;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// map launchers
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static const void *map_kernel_ptr(int variant)
+{
+    switch (variant) {
+#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::map_unit_kernel<F, VEC, UNROLL, POLICY>;
+        LBK_VARIANTS(X)
+#undef X
+    }
+    return nullptr;
+}
+static int variant_unroll(int variant)
+{
+    switch (variant) {
+#define X(ID, VEC, UNROLL, POLICY) case ID: return UNROLL;
+        LBK_VARIANTS(X)
+#undef X
+    }
+    return 1;
+}
+
+static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int threads, i64 ntiles, int *grid)
+{
+    int bps = cfg.blocks_per_sm;
+    if (bps <= 0) {
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, 0));
+        if (bps < 1) bps = 1;
+    }
+    i64 g = std::min<i64>(std::max<i64>(ntiles, 1), (i64)c->sms * bps);
+    *grid = (int)std::min<i64>(g, kMaxGrid);
+    return LBK_OK;
+}
+
+template <class F>
+static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const float *xr, const float *yr, float *xw, float *yw, i64 n, int default_variant)
+{
+    const LaunchCfg &cfg = c->cfg[rid];
+    int variant = cfg.variant >= 0 ? cfg.variant : default_variant;
+    const int threads = cfg.threads > 0 ? cfg.threads : 256;
+    const float *ptrs[4]; int np = 0;
+    if (F::RX) ptrs[np++] = xr;
+    if (F::RY) ptrs[np++] = yr;
+    if (F::WX) ptrs[np++] = xw;
+    if (F::WY) ptrs[np++] = yw;
+    i64 head = 0;
+    resolve_alignment(&variant, &head, ptrs, np, n);
+    const void *k = map_kernel_ptr<F>(variant);
+    const i64 npack = (n - head) / kVariantVec[variant];
+    const i64 per_tile = (i64)variant_unroll(variant) * threads;
+    int grid;
+    int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid);
+    if (s) return s;
+    F fc = f;
+    void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n};
+    CU(c, cudaLaunchKernel(k, dim3(grid), dim3(threads), args, 0, c->stream));
+    KERNEL_CHECK(c);
+    return LBK_OK;
+}
+
+template <class F>
+static int launch_map_strided(lbk_ctx *c, const F &f, const float *xr, float *xw, i64 incx_r, i64 incx_w, i64 kx0_r, i64 kx0_w,
+                              const float *yr, float *yw, i64 incy_r, i64 incy_w, i64 ky0_r, i64 ky0_w,
+                              i64 i_begin, i64 n, int x_last, int y_last)
+{
+    const int threads = 256;
+    const int grid = stream_grid(c, n - i_begin, threads);
+    lbk::map_strided_kernel<F><<<grid, threads, 0, c->stream>>>(f, xr, xw, incx_r, incx_w, kx0_r, kx0_w,
+                                                                 yr, yw, incy_r, incy_w, ky0_r, ky0_w, i_begin, n, x_last, y_last);
+    KERNEL_CHECK(c);
+    return LBK_OK;
+}
+
+// In-place (xw == xr, yw == yr) or out-of-place update of n logical elements.  `xo`/`yo` are the
+// destinations; a destination that differs from its source must already hold a copy of the source
+// wherever this call does not write (map_entry arranges that).
+template <class F>
+static int map_dispatch(lbk_ctx *c, int rid, const F &f, i64 n,
+                        const Operand &X, float *xw, const Operand &Y, float *yw, int default_variant)
+{
+    if (n <= 0) return LBK_OK;
+    CU(c, cudaSetDevice(c->device));
+    const bool use_x = F::RX || F::WX, use_y = F::RY || F::WY;
+    const float *xr = use_x ? X.v->ptr : nullptr;
+    const float *yr = use_y ? Y.v->ptr : nullptr;
+    const i64 incx = use_x ? X.inc : 1, incy = use_y ? Y.inc : 1;
+    const i64 nl = use_x ? X.n_local : Y.n_local;   // sharded operands agree (checked by the caller)
+    if (nl <= 0) return LBK_OK;
+    // unit stride; (-1,-1) visits the same pairs in the opposite order, which an elementwise update cannot see
+    const bool unit = (incx == 1 && incy == 1) || (use_x && use_y && incx == -1 && incy == -1) ||
+                      (!use_y && incx == 1) || (!use_x && incy == 1);
+    if (unit) return launch_map_unit<F>(c, rid, f, xr, yr, xw, yw, nl, default_variant);
+
+    i64 kx0 = first_index(nl, incx), ky0 = first_index(nl, incy);
+    i64 incx_r = incx, incx_w = incx, incy_r = incy, incy_w = incy, kx0_r = kx0, ky0_r = ky0;
+    int x_last = 0, y_last = 0;
+    if (F::WX && incx == 0) {            // n sequential writes to x[0]: the last wins, all read the original
+        x_last = 1;
+        if (F::RX) { CU(c, cudaMemcpyAsync(c->snap, xr, sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); xr = c->snap; kx0_r = 0; }
+    }
+    if (F::WY && incy == 0) {
+        y_last = 1;
+        if (F::RY) { CU(c, cudaMemcpyAsync(c->snap + 1, yr, sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); yr = c->snap + 1; ky0_r = 0; }
+    }
+    const bool only_last = (!F::WX || x_last) && (!F::WY || y_last);
+    return launch_map_strided<F>(c, f, xr, xw, incx_r, incx_w, kx0_r, kx0, yr, yw, incy_r, incy_w, ky0_r, ky0,
+                                 only_last ? nl - 1 : 0, nl, x_last, y_last);
+}
+
+// Shared front end of the elementwise routines.  xo / yo: optional out-of-place destinations.
+template <class F>
+static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
+                     const lbk_vec *x, i64 incx, const lbk_vec *y, i64 incy,
+                     lbk_vec *xo, lbk_vec *yo, int default_variant)
+{
+    if (!c) return fail(nullptr, LBK_ERR_ARG, std::string(who) + ": null context");
+    const bool use_x = F::RX || F::WX, use_y = F::RY || F::WY;
+    Operand X{}, Y{};
+    int s;
+    if (use_x && (s = check_operand(c, who, x, incx, n, &X))) return s;
+    if (use_y && (s = check_operand(c, who, y, incy, n, &Y))) return s;
+    if (use_x && use_y && (x->sharded != y->sharded || (x->sharded && (x->global_len != y->global_len))))
+        return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": operands must be sharded alike");
+    float *xw = nullptr, *yw = nullptr;
+    if (F::WX) {
+        lbk_vec *d = xo ? xo : const_cast<lbk_vec *>(x);
+        if (d->ctx != c || d->len != x->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
+        xw = d->ptr;
+    }
+    if (F::WY) {
+        lbk_vec *d = yo ? yo : const_cast<lbk_vec *>(y);
+        if (d->ctx != c || d->len != y->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
+        yw = d->ptr;
+    }
+    if (n > 0 && use_x && use_y && (F::WX || F::WY) && overlap(X, Y))
+        return fail(c, LBK_ERR_ALIAS, std::string(who) + ": x and y overlap");
+    // out of place: everything this call does not write is a copy of the source (Util.hs:134-142:
+    // unsafeUpdate_ clones the whole destination first).  Fused into the update when the update covers
+    // the vector; otherwise the remainder (unit stride) or the whole vector (strided) is copied.
+    auto prepare = [&](const Operand &O, float *w, bool writes) -> int {
+        if (!writes || w == O.v->ptr || O.v->len == 0) return LBK_OK;
+        const i64 nl = n > 0 ? O.n_local : 0;
+        const bool unit_cover = nl > 0 && (O.inc == 1 || O.inc == -1);
+        const i64 from = unit_cover ? nl : 0;
+        if (from < O.v->len)
+            CU(c, cudaMemcpyAsync(w + from, O.v->ptr + from, sizeof(float) * (size_t)(O.v->len - from), cudaMemcpyDeviceToDevice, c->stream));
+        return LBK_OK;
+    };
+    if ((s = prepare(X, xw, F::WX))) return s;
+    if ((s = prepare(Y, yw, F::WY))) return s;
+    // a strided out-of-place update reads the copy it just made (same values as the source)
+    Operand Xs = X, Ys = Y;
+    lbk_vec xtmp, ytmp;
+    const bool x_unit = use_x && (X.inc == 1 || X.inc == -1), y_unit = use_y && (Y.inc == 1 || Y.inc == -1);
+    if (F::WX && xw != x->ptr && !x_unit) { xtmp = *x; xtmp.ptr = xw; Xs.v = &xtmp; }
+    if (F::WY && yw != y->ptr && !y_unit) { ytmp = *y; ytmp.ptr = yw; Ys.v = &ytmp; }
+    return map_dispatch<F>(c, rid, f, n, Xs, xw, Ys, yw, default_variant);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce launchers
+// ------------------------------------------------------------------------------------------------
+template <class Op>
+static const void *reduce_kernel_ptr(int variant)
+{
+    switch (variant) {
+#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::reduce_unit_kernel<Op, VEC, UNROLL, POLICY>;
+        LBK_VARIANTS(X)
+#undef X
+    }
+    return nullptr;
+}
+
+// Runs the local reduction and, on a communicator with sharded operands, the exchange + finish.
+// `out` is a device-visible address that receives the float (or the int64 for isamax).
+template <class Op>
+static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &X, const Operand *Y,
+                           double sb, void *out, int default_variant)
+{
+    CU(c, cudaSetDevice(c->device));
+    const bool exchange = c->nranks > 1 && X.v->sharded;
+    const i64 nl = X.n_local;
+    const float *x = X.v->ptr, *y = Y ? Y->v->ptr : nullptr;
+    const i64 incx = X.inc, incy = Y ? Y->inc : 1;
+    FinishArgs fa;
+    fa.kind = kind;
+    fa.mode = exchange ? 1 : 0;
+    fa.n_global = n;
+    fa.sb = sb;
+    fa.out = out;
+    fa.rec_out = c->rec_send;
+    fa.x0 = (X.i0 == 0 && nl > 0) ? x : nullptr;     // logical element 0 lives at x[0] for incx >= 1
+    const i64 idx_base = X.i0;
+    const bool unit = nl > 0 && ((incx == 1 && (!Y || incy == 1)) || (Y && incx == -1 && incy == -1));
+    if (unit) {
+        const LaunchCfg &cfg = c->cfg[rid];
+        int variant = cfg.variant >= 0 ? cfg.variant : default_variant;
+        const int threads = cfg.threads > 0 ? cfg.threads : 256;
+        const float *ptrs[2] = {x, y};
+        i64 head = 0;
+        resolve_alignment(&variant, &head, ptrs, Y ? 2 : 1, nl);
+        const void *k = reduce_kernel_ptr<Op>(variant);
+        const i64 npack = (nl - head) / kVariantVec[variant];
+        const i64 per_tile = (i64)variant_unroll(variant) * threads;
+        int grid;
+        int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid);
+        if (s) return s;
+        i64 nn = nl, ib = idx_base;
+        void *args[] = {(void *)&x, (void *)&y, (void *)&head, (void *)&nn, (void *)&ib, (void *)&c->partials, (void *)&c->ticket, (void *)&fa};
+        CU(c, cudaLaunchKernel(k, dim3(grid), dim3(threads), args, 0, c->stream));
+        KERNEL_CHECK(c);
+    } else {
+        const int threads = 256;
+        const int grid = stream_grid(c, std::max<i64>(nl, 1), threads);
+        lbk::reduce_strided_kernel<Op><<<grid, threads, 0, c->stream>>>(x, incx, first_index(nl, incx), y, incy,
+                                                                          first_index(nl, incy), nl, idx_base, c->partials, c->ticket, fa);
+        KERNEL_CHECK(c);
+    }
+    if (exchange) {
+        NC(c, ncclAllGather(c->rec_send, c->rec_all, sizeof(Record), ncclChar, c->comm, c->stream));
+        fa.mode = 0;
+        lbk::finish_records_kernel<<<1, 32, 0, c->stream>>>(c->rec_all, c->nranks, fa);
+        KERNEL_CHECK(c);
+    }
+    return LBK_OK;
+}
+
+static int store_f32(lbk_ctx *c, void *out, float v)
+{
+    CU(c, cudaSetDevice(c->device));
+    lbk::store_f32_kernel<<<1, 32, 0, c->stream>>>((float *)out, v);
+    KERNEL_CHECK(c);
+    return LBK_OK;
+}
+static int store_i64(lbk_ctx *c, void *out, i64 v)
+{
+    CU(c, cudaSetDevice(c->device));
+    lbk::store_i64_kernel<<<1, 32, 0, c->stream>>>((i64 *)out, v);
+    KERNEL_CHECK(c);
+    return LBK_OK;
+}
+
+static int check_out_vec(lbk_ctx *c, const char *who, lbk_vec *o, i64 need)
+{
+    if (!o || o->ctx != c || o->len < need) return fail(c, LBK_ERR_ARG, std::string(who) + ": result vector is null, foreign or too short");
+    if ((uintptr_t)o->ptr & 7) return fail(c, LBK_ERR_ARG, std::string(who) + ": result vector must be 8-byte aligned");
+    return LBK_OK;
+}
+
+// kind: 0 sdot, 3 sdsdot
+static int dot_common(lbk_ctx *c, const char *who, int rid, int kind, i64 n, float sb, const lbk_vec *x, i64 incx,
+                      const lbk_vec *y, i64 incy, void *out_dev)
+{
+    Operand X{}, Y{};
+    int s;
+    if ((s = check_operand(c, who, x, incx, n, &X))) return s;
+    if ((s = check_operand(c, who, y, incy, n, &Y))) return s;
+    if (x->sharded != y->sharded || (x->sharded && x->global_len != y->global_len))
+        return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": operands must be sharded alike");
+    if (n <= 0) return store_f32(c, out_dev, kind == 3 ? sb : 0.f);       // Single.hs:81 (empty fold), :239
+    if (kind == 3) return reduce_dispatch<lbk::DsdotOp>(c, rid, 3, n, X, &Y, (double)sb, out_dev, 0);
+    return reduce_dispatch<lbk::DotOp>(c, rid, 0, n, X, &Y, 0.0, out_dev, 0);
+}
+
+template <class T>
+static int finish_sync(lbk_ctx *c, int s, T *out)
+{
+    if (s) return s;
+    CU(c, cudaStreamSynchronize(c->stream));
+    *out = *reinterpret_cast<volatile T *>(c->result_host);
+    return LBK_OK;
+}
+
+extern "C" int lbk_sdot(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out)
+{
+    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_sdot: null argument");
+    return finish_sync(c, dot_common(c, "lbk_sdot", R_SDOT, 0, n, 0.f, x, incx, y, incy, c->result_dev), out);
+}
+extern "C" int lbk_sdot_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *o)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_sdot_async: null context");
+    int s = check_out_vec(c, "lbk_sdot_async", o, 1);
+    return s ? s : dot_common(c, "lbk_sdot_async", R_SDOT, 0, n, 0.f, x, incx, y, incy, o->ptr);
+}
+extern "C" int lbk_sdsdot(lbk_ctx *c, int64_t n, float sb, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out)
+{
+    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_sdsdot: null argument");
+    return finish_sync(c, dot_common(c, "lbk_sdsdot", R_SDSDOT, 3, n, sb, x, incx, y, incy, c->result_dev), out);
+}
+
+// sasum (kind 0 with AsumOp), snrm2 (kind 1), isamax (kind 2): one vector, positive increments
+static int ivi_common(lbk_ctx *c, const char *who, int rid, i64 n, const lbk_vec *x, i64 incx, void *out_dev)
+{
+    if (!x) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
+    if (x->ctx != c) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
+    // the reference's guards come first: Single.hs:162 (asum), :181 (nrm2), :218 (iamax)
+    if (n < 1 || incx < 1) return rid == R_ISAMAX ? store_i64(c, out_dev, -1) : store_f32(c, out_dev, 0.f);
+    Operand X{};
+    int s;
+    if ((s = check_operand(c, who, x, incx, n, &X))) return s;
+    if (rid == R_SASUM) return reduce_dispatch<lbk::AsumOp>(c, rid, 0, n, X, nullptr, 0.0, out_dev, 0);
+    if (rid == R_SNRM2) return reduce_dispatch<lbk::Nrm2Op>(c, rid, 1, n, X, nullptr, 0.0, out_dev, 0);
+    return reduce_dispatch<lbk::IamaxOp>(c, rid, 2, n, X, nullptr, 0.0, out_dev, 0);
+}
+
+extern "C" int lbk_sasum(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, float *out)
+{
+    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_sasum: null argument");
+    return finish_sync(c, ivi_common(c, "lbk_sasum", R_SASUM, n, x, incx, c->result_dev), out);
+}
+extern "C" int lbk_snrm2(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, float *out)
+{
+    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_snrm2: null argument");
+    return finish_sync(c, ivi_common(c, "lbk_snrm2", R_SNRM2, n, x, incx, c->result_dev), out);
+}
+extern "C" int lbk_isamax(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, int64_t *out)
+{
+    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_isamax: null argument");
+    return finish_sync(c, ivi_common(c, "lbk_isamax", R_ISAMAX, n, x, incx, c->result_dev), out);
+}
+extern "C" int lbk_sasum_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_sasum_async: null context");
+    int s = check_out_vec(c, "lbk_sasum_async", o, 1);
+    return s ? s : ivi_common(c, "lbk_sasum_async", R_SASUM, n, x, incx, o->ptr);
+}
+extern "C" int lbk_snrm2_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_snrm2_async: null context");
+    int s = check_out_vec(c, "lbk_snrm2_async", o, 1);
+    return s ? s : ivi_common(c, "lbk_snrm2_async", R_SNRM2, n, x, incx, o->ptr);
+}
+extern "C" int lbk_isamax_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_isamax_async: null context");
+    int s = check_out_vec(c, "lbk_isamax_async", o, 2);
+    return s ? s : ivi_common(c, "lbk_isamax_async", R_ISAMAX, n, x, incx, o->ptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbk_saxpy(lbk_ctx *c, int64_t n, float a, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy)
+{ return map_entry(c, "lbk_saxpy", R_SAXPY, lbk::AxpyF{a}, n, x, incx, y, incy, nullptr, nullptr, 0); }
+extern "C" int lbk_saxpy_oop(lbk_ctx *c, int64_t n, float a, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout)
+{
+    if (!yout) return fail(c, LBK_ERR_ARG, "lbk_saxpy_oop: null output");
+    return map_entry(c, "lbk_saxpy_oop", R_SAXPY, lbk::AxpyF{a}, n, x, incx, y, incy, nullptr, yout, 0);
+}
+
+// Single.hs:108-111: the index stream `sampleIndices n incx` is empty for incx < 0 and n > 1, and
+// yields slot 0 (n times for incx == 0, once for n == 1), each write being x[0]*a.
+static int scal_common(lbk_ctx *c, const char *who, i64 n, float a, const lbk_vec *x, i64 incx, lbk_vec *xout)
+{
+    if (!c) return fail(nullptr, LBK_ERR_ARG, std::string(who) + ": null context");
+    if (!x) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
+    i64 n_eff = n, inc_eff = incx;
+    if (n > 0 && incx <= 0) {
+        if (incx == 0 || n == 1) { n_eff = 1; inc_eff = 1; }
+        else n_eff = 0;
+        if (x->sharded) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take unit increments only");
+    }
+    if (n_eff <= 0 && xout && xout->ptr != x->ptr) {      // nothing to scale: the pure result is a copy
+        if (xout->ctx != c || xout->len != x->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
+        if (x->len) CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, sizeof(float) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream));
+        return LBK_OK;
+    }
+    return map_entry(c, who, R_SSCAL, lbk::ScalF{a}, n_eff, x, inc_eff, nullptr, 1, xout, nullptr, 0);
+}
+extern "C" int lbk_sscal(lbk_ctx *c, int64_t n, float a, lbk_vec *x, int64_t incx)
+{ return scal_common(c, "lbk_sscal", n, a, x, incx, nullptr); }
+extern "C" int lbk_sscal_oop(lbk_ctx *c, int64_t n, float a, const lbk_vec *x, int64_t incx, lbk_vec *xout)
+{
+    if (!xout) return fail(c, LBK_ERR_ARG, "lbk_sscal_oop: null output");
+    return scal_common(c, "lbk_sscal_oop", n, a, x, incx, xout);
+}
+
+extern "C" int lbk_scopy(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy)
+{ return map_entry(c, "lbk_scopy", R_SCOPY, lbk::CopyF{}, n, x, incx, y, incy, nullptr, nullptr, 0); }
+extern "C" int lbk_scopy_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout)
+{
+    if (!yout) return fail(c, LBK_ERR_ARG, "lbk_scopy_oop: null output");
+    return map_entry(c, "lbk_scopy_oop", R_SCOPY, lbk::CopyF{}, n, x, incx, y, incy, nullptr, yout, 0);
+}
+
+extern "C" int lbk_sswap(lbk_ctx *c, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy)
+{ return map_entry(c, "lbk_sswap", R_SSWAP, lbk::SwapF{}, n, x, incx, y, incy, nullptr, nullptr, 0); }
+extern "C" int lbk_sswap_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *xout, lbk_vec *yout)
+{
+    if (!xout || !yout) return fail(c, LBK_ERR_ARG, "lbk_sswap_oop: null output");
+    return map_entry(c, "lbk_sswap_oop", R_SSWAP, lbk::SwapF{}, n, x, incx, y, incy, xout, yout, 0);
+}
+
+extern "C" int lbk_srot(lbk_ctx *c, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, float cs, float sn)
+{ return map_entry(c, "lbk_srot", R_SROT, lbk::RotF{cs, sn}, n, x, incx, y, incy, nullptr, nullptr, 0); }
+extern "C" int lbk_srot_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float cs, float sn, lbk_vec *xout, lbk_vec *yout)
+{
+    if (!xout || !yout) return fail(c, LBK_ERR_ARG, "lbk_srot_oop: null output");
+    return map_entry(c, "lbk_srot_oop", R_SROT, lbk::RotF{cs, sn}, n, x, incx, y, incy, xout, yout, 0);
+}
+
+// Single.hs:472-482; param = [flag,h11,h21,h12,h22] (test/Foreign.hs:276-280)
+static int rotm_common(lbk_ctx *c, const char *who, i64 n, const lbk_vec *x, i64 incx, const lbk_vec *y, i64 incy,
+                       const float *p, lbk_vec *xout, lbk_vec *yout)
+{
+    if (!c) return fail(nullptr, LBK_ERR_ARG, std::string(who) + ": null context");
+    if (!p) return fail(c, LBK_ERR_ARG, std::string(who) + ": null param");
+    const float flag = p[0];
+    if (flag == -2.0f) {          // FLAGNEG2: the inputs come back as they are (Single.hs:473)
+        if (xout && x && xout->ptr != x->ptr && x->len) {
+            if (xout->len != x->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
+            CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, sizeof(float) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (yout && y && yout->ptr != y->ptr && y->len) {
+            if (yout->len != y->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
+            CU(c, cudaMemcpyAsync(yout->ptr, y->ptr, sizeof(float) * (size_t)y->len, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        return LBK_OK;
+    }
+    if (flag < 0.0f) return map_entry(c, who, R_SROTM, lbk::RotmNeg1F{p[1], p[3], p[2], p[4]}, n, x, incx, y, incy, xout, yout, 0);
+    if (flag == 0.0f) return map_entry(c, who, R_SROTM, lbk::Rotm0F{p[3], p[2]}, n, x, incx, y, incy, xout, yout, 0);
+    return map_entry(c, who, R_SROTM, lbk::Rotm1F{p[1], p[4]}, n, x, incx, y, incy, xout, yout, 0);
+}
+extern "C" int lbk_srotm(lbk_ctx *c, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, const float param[5])
+{ return rotm_common(c, "lbk_srotm", n, x, incx, y, incy, param, nullptr, nullptr); }
+extern "C" int lbk_srotm_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, const float param[5], lbk_vec *xout, lbk_vec *yout)
+{
+    if (!xout || !yout) return fail(c, LBK_ERR_ARG, "lbk_srotm_oop: null output");
+    return rotm_common(c, "lbk_srotm_oop", n, x, incx, y, incy, param, xout, yout);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host statement of the cross-rank combine (tests of the multi-GPU path on CPU)
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbk_combine_records(int kind, const lbk_record *recs, int nranks, float *fout, int64_t *iout)
+{
+    if (!recs || nranks < 1) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: bad argument");
+    const Record *r = reinterpret_cast<const Record *>(recs);
+    if (kind == LBK_RED_IAMAX) {
+        if (!iout) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: null out pointer");
+        *iout = lbk::fold_ranks<lbk::IamaxOp>(r, nranks).idx;
+    } else if (kind == LBK_RED_NRM2) {
+        if (!fout) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: null out pointer");
+        Record a = lbk::fold_ranks<lbk::Nrm2Op>(r, nranks);
+        *fout = lbk::nrm2_finish(a.f[0], a.f[1], a.f[2]);
+    } else if (kind == LBK_RED_SUM) {
+        if (!fout) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: null out pointer");
+        *fout = lbk::fold_ranks<lbk::DotOp>(r, nranks).f[0];
+    } else return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: unknown kind");
+    return LBK_OK;
+}

@@ -1,0 +1,244 @@
+"""Types of the path: the device vector added beside Numerical.BLAS.Types, and the reference's ADTs.
+
+Reference: src/Numerical/BLAS/Types.hs:8 (GivensRot), :15-20 (ModGivensRot with constructors
+FLAGNEG2 | FLAGNEG1{d1,d2,x1,h11,h12,h21,h22} | FLAG0{d1,d2,x1,h12,h21} | FLAG1{d1,d2,x1,h11,h22});
+vectors in the reference are Data.Vector.Storable.Vector Float (Single.hs:67), i.e. a host buffer.
+DVector is the device-resident representation the north star adds: an opaque handle to HBM with
+explicit host transfer (to_device / from_device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import NamedTuple, Optional
+
+import numpy as np
+
+from . import _ffi
+
+
+class Context:
+    """One GPU, one stream, scratch for the reductions, and (optionally) the NCCL communicator."""
+
+    def __init__(self, device: Optional[int] = None):
+        L = _ffi.lib()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = C.c_void_p()
+        _ffi.check(L.lbk_init(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.nranks, self.rank = 1, 0
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("context is closed")
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            _ffi.lib().lbk_shutdown(self._h)
+            self._h = None
+
+    def sync(self) -> None:
+        _ffi.check(_ffi.lib().lbk_sync(self.handle), self.handle)
+
+    def sm_count(self) -> int:
+        v = C.c_int()
+        _ffi.check(_ffi.lib().lbk_sm_count(self.handle, C.byref(v)), self.handle)
+        return v.value
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        _ffi.check(_ffi.lib().lbk_launch_count(self.handle, C.byref(v)), self.handle)
+        return v.value
+
+    def set_launch(self, routine: str, variant: int = -1, threads: int = 0, blocks_per_sm: int = 0) -> None:
+        _ffi.check(_ffi.lib().lbk_set_launch(self.handle, routine.encode(), variant, threads, blocks_per_sm), self.handle)
+
+    def stream(self) -> int:
+        return int(_ffi.lib().lbk_stream(self.handle) or 0)
+
+    # ---- vectors ----
+    def alloc(self, n: int) -> "DVector":
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().lbk_vec_alloc(self.handle, n, C.byref(h)), self.handle)
+        return DVector(self, h)
+
+    def alloc_sharded(self, global_len: int) -> "DVector":
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().lbk_vec_alloc_sharded(self.handle, global_len, C.byref(h)), self.handle)
+        return DVector(self, h)
+
+    def wrap(self, device_ptr: int, n: int, keepalive=None) -> "DVector":
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().lbk_vec_wrap(self.handle, C.c_void_p(device_ptr), n, C.byref(h)), self.handle)
+        v = DVector(self, h)
+        v._keep = keepalive
+        return v
+
+    def to_device(self, host) -> "DVector":
+        a = np.ascontiguousarray(host, dtype=np.float32)
+        if a.ndim != 1:
+            raise ValueError("vectors are one-dimensional")
+        v = self.alloc(a.size)
+        if a.size:
+            _ffi.check(_ffi.lib().lbk_vec_upload(v.handle, a.ctypes.data_as(C.c_void_p), a.size), self.handle)
+        return v
+
+    # ---- events ----
+    def event(self) -> "Event":
+        return Event(self)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class Event:
+    def __init__(self, ctx: Context):
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().lbk_event_create(ctx.handle, C.byref(h)), ctx.handle)
+        self._h, self.ctx = h, ctx
+
+    def record(self) -> "Event":
+        _ffi.check(_ffi.lib().lbk_event_record(self._h), self.ctx.handle)
+        return self
+
+    def elapsed_ms(self, stop: "Event") -> float:
+        ms = C.c_float()
+        _ffi.check(_ffi.lib().lbk_event_elapsed_ms(self._h, stop._h, C.byref(ms)), self.ctx.handle)
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self._h is not None and self.ctx._h is not None:
+                _ffi.lib().lbk_event_destroy(self._h)
+        except Exception:
+            pass
+
+
+class DVector:
+    """A device-resident fp32 vector (or this rank's contiguous shard of one)."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p, parent: "Optional[DVector]" = None):
+        self.ctx, self._h, self._parent, self._keep = ctx, handle, parent, None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _lens(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _ffi.check(_ffi.lib().lbk_vec_len(self._h, C.byref(a), C.byref(b), C.byref(c)), self.ctx.handle)
+        return a.value, b.value, c.value
+
+    def __len__(self) -> int:
+        return self._lens()[0]
+
+    @property
+    def global_len(self) -> int:
+        return self._lens()[1]
+
+    @property
+    def shard_offset(self) -> int:
+        return self._lens()[2]
+
+    @property
+    def ptr(self) -> int:
+        return int(_ffi.lib().lbk_vec_ptr(self._h) or 0)
+
+    def clone(self) -> "DVector":
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().lbk_vec_clone(self._h, C.byref(h)), self.ctx.handle)
+        return DVector(self.ctx, h)
+
+    def view(self, offset: int, n: int) -> "DVector":
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().lbk_vec_view(self._h, offset, n, C.byref(h)), self.ctx.handle)
+        return DVector(self.ctx, h, parent=self)
+
+    def to_host(self) -> np.ndarray:
+        n = len(self)
+        out = np.empty(n, dtype=np.float32)
+        if n:
+            _ffi.check(_ffi.lib().lbk_vec_download(self._h, out.ctypes.data_as(C.c_void_p), n), self.ctx.handle)
+        return out
+
+    def upload(self, host) -> "DVector":
+        a = np.ascontiguousarray(host, dtype=np.float32)
+        _ffi.check(_ffi.lib().lbk_vec_upload(self._h, a.ctypes.data_as(C.c_void_p), a.size), self.ctx.handle)
+        return self
+
+    def fill_hash(self, seed: int, lo: float = -1.0, hi: float = 1.0) -> "DVector":
+        _ffi.check(_ffi.lib().lbk_vec_fill_hash(self._h, seed, lo, hi), self.ctx.handle)
+        return self
+
+    def fill(self, value: float) -> "DVector":
+        _ffi.check(_ffi.lib().lbk_vec_fill(self._h, value), self.ctx.handle)
+        return self
+
+    def __del__(self):
+        try:
+            if self._h is not None and self.ctx._h is not None:
+                _ffi.lib().lbk_vec_free(self._h)
+        except Exception:
+            pass
+        self._h = None
+
+
+def hash_fill_reference(n: int, seed: int, lo: float = -1.0, hi: float = 1.0, offset: int = 0) -> np.ndarray:
+    """numpy statement of lbk_vec_fill_hash: v[i] = lo + (hi-lo) * u24(splitmix64(seed*2^40 + offset+i))."""
+    i = (np.arange(n, dtype=np.uint64) + np.uint64(offset)) + (np.uint64(seed) << np.uint64(40))
+    with np.errstate(over="ignore"):
+        z = i + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)
+    span = np.float32(np.float32(hi) - np.float32(lo))
+    return (np.float32(lo) + span * u).astype(np.float32)
+
+
+# ---- the reference's ADTs ---------------------------------------------------------------------------
+
+class GivensRot(NamedTuple):
+    """GIVENSROT (r, z, c, s)  -- Types.hs:8"""
+    r: np.float32
+    z: np.float32
+    c: np.float32
+    s: np.float32
+
+
+@dataclass(frozen=True)
+class ModGivensRot:
+    """Types.hs:15-20.  `flag` names the constructor: -2 FLAGNEG2, -1 FLAGNEG1, 0 FLAG0, 1 FLAG1."""
+    flag: int
+    d1: np.float32 = np.float32(0)
+    d2: np.float32 = np.float32(0)
+    x1: np.float32 = np.float32(0)
+    h11: np.float32 = np.float32(0)
+    h12: np.float32 = np.float32(0)
+    h21: np.float32 = np.float32(0)
+    h22: np.float32 = np.float32(0)
+
+    @property
+    def constructor(self) -> str:
+        return {-2: "FLAGNEG2", -1: "FLAGNEG1", 0: "FLAG0", 1: "FLAG1"}[self.flag]
+
+    def sparam(self) -> np.ndarray:
+        """BLAS sparam [flag,h11,h21,h12,h22], filled the way test/Foreign.hs:276-280 pokes it."""
+        if self.flag == -2:
+            return np.array([-2, 1, 0, 0, 1], dtype=np.float32)
+        if self.flag == -1:
+            return np.array([-1, self.h11, self.h21, self.h12, self.h22], dtype=np.float32)
+        if self.flag == 0:
+            return np.array([0, 0, self.h21, self.h12, 0], dtype=np.float32)
+        return np.array([1, self.h11, 0, 0, self.h22], dtype=np.float32)
+
+
+FLAGNEG2 = ModGivensRot(-2)

@@ -1,0 +1,59 @@
+"""First-contact GPU checks: unit-stride fast path at sizes that exercise head/tail peeling, every
+launch variant, the in-place forms and the device data generator."""
+import numpy as np
+import pytest
+
+import tests.test_gpu_parity as P
+from tests.gen import gen_unit
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fill_hash_matches_numpy(blas, ctx):
+    v = ctx.alloc(100003).fill_hash(7, -1.0, 1.0)
+    P.assert_same(v.to_host(), blas.hash_fill_reference(100003, 7, -1.0, 1.0))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 31, 33, 1000, 4099, 65537, 1 << 20, (1 << 20) + 3])
+@pytest.mark.parametrize("off", [0, 1, 3, 5])
+def test_unit_paths_all_alignments(blas, ctx, oracle, n, off):
+    rng = np.random.default_rng(n * 8 + off)
+    u, v = gen_unit(rng, n + off), gen_unit(rng, n + off + 2)
+    du, dv = ctx.to_device(u).view(off, n), ctx.to_device(v).view(off + 2 if off % 2 else off, n)
+    hu, hv = du.to_host(), dv.to_host()
+    got = blas.sdot(n, du, 1, dv, 1)
+    want = oracle.sdot(n, hu, 1, hv, 1)
+    assert abs(float(got) - float(want)) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(hu.astype(np.float64) * hv)))
+    assert blas.isamax(n, du, 1) == oracle.isamax(n, hu, 1)
+    assert abs(float(blas.snrm2(n, du, 1)) - float(oracle.snrm2(n, hu, 1))) <= 2 * n * 2.0 ** -24 * float(oracle.snrm2(n, hu, 1))
+    assert abs(float(blas.sasum(n, du, 1)) - float(oracle.sasum(n, hu, 1))) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(hu)))
+    P.assert_same(blas.saxpy(n, 1.000123, du, 1, dv, 1).to_host(), oracle.saxpy(n, 1.000123, hu, 1, hv, 1))
+    xo, yo = blas.srot(n, du, 1, dv, 1, np.cos(0.3), np.sin(0.3))
+    wx, wy = oracle.srot(n, hu, 1, hv, 1, np.cos(0.3), np.sin(0.3))
+    P.assert_same(xo.to_host(), wx); P.assert_same(yo.to_host(), wy)
+
+
+@pytest.mark.parametrize("variant", range(10))
+@pytest.mark.parametrize("threads", [128, 512])
+def test_every_variant(blas, ctx, oracle, variant, threads):
+    n = 300007
+    rng = np.random.default_rng(variant)
+    u, v = gen_unit(rng, n), gen_unit(rng, n)
+    u[12345] = -3.0; u[99999] = 3.0          # tie: the first wins
+    du, dv = ctx.to_device(u), ctx.to_device(v)
+    ctx.set_launch("all", variant, threads, 0)
+    try:
+        assert blas.isamax(n, du, 1) == 12345
+        want = oracle.sdot(n, u, 1, v, 1)
+        assert abs(float(blas.sdot(n, du, 1, dv, 1)) - float(want)) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(u.astype(np.float64) * v)))
+        assert abs(float(blas.snrm2(n, du, 1)) - float(oracle.snrm2(n, u, 1))) <= 2 * n * 2.0 ** -24 * float(oracle.snrm2(n, u, 1))
+        y = dv.clone()
+        blas.inplace.saxpy_(n, 0.5, du, 1, y, 1)
+        P.assert_same(y.to_host(), oracle.saxpy(n, 0.5, u, 1, v, 1))
+        x2, y2 = du.clone(), dv.clone()
+        blas.inplace.sswap_(n, x2, 1, y2, 1)
+        P.assert_same(x2.to_host(), v); P.assert_same(y2.to_host(), u)
+        blas.inplace.sscal_(n, 3.0, x2, 1)
+        P.assert_same(x2.to_host(), oracle.sscal(n, 3.0, v, 1))
+    finally:
+        ctx.set_launch("all", -1, 0, 0)
