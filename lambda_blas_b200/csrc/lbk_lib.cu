@@ -39,6 +39,14 @@ enum Routine { R_SDOT, R_SDSDOT, R_SASUM, R_SNRM2, R_ISAMAX, R_SAXPY, R_SSCAL, R
 static const char *kRoutineNames[R_COUNT] = {"sdot", "sdsdot", "sasum", "snrm2", "isamax", "saxpy",
                                              "sscal", "scopy", "sswap", "srot", "srotm"};
 struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
+// Defaults from the n = 2^28 sweep on B200 (profiles/r01_tune_sweep.csv; tools/tune.py):
+// blocks_per_sm 0 = one resident wave (occupancy x SMs); larger values oversubscribe the SMs.
+static const LaunchCfg kDefaultCfg[R_COUNT] = {
+    /* sdot   */ {3, 512, 8},   /* sdsdot */ {3, 512, 8},   /* sasum  */ {0, 512, 0},
+    /* snrm2  */ {0, 512, 0},   /* isamax */ {2, 512, 16},  /* saxpy  */ {4, 128, 64},
+    /* sscal  */ {4, 256, 32},  /* scopy  */ {4, 256, 32},  /* sswap  */ {4, 128, 64},
+    /* srot   */ {4, 128, 64},  /* srotm  */ {4, 128, 64},
+};
 
 constexpr int kMaxGrid = 148 * 32 * 2;   // partial-record scratch (blocks)
 
@@ -125,7 +133,7 @@ extern "C" int lbk_init(int device, lbk_ctx **out)
     lbk_ctx *c = new (std::nothrow) lbk_ctx();
     if (!c) return fail(nullptr, LBK_ERR_NOMEM, "lbk_init: out of host memory");
     c->device = device;
-    for (int r = 0; r < R_COUNT; ++r) c->cfg[r] = LaunchCfg{-1, 0, 0};
+    for (int r = 0; r < R_COUNT; ++r) c->cfg[r] = kDefaultCfg[r];
     cudaError_t e;
 #define INIT(call) if ((e = (call)) != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e); delete c; return fail(nullptr, LBK_ERR_CUDA, m); }
     INIT(cudaSetDevice(device));
@@ -184,7 +192,8 @@ extern "C" int lbk_set_launch(lbk_ctx *c, const char *routine, int variant, int 
         return fail(c, LBK_ERR_ARG, "lbk_set_launch: threads must be a multiple of 32, at most 512");
     for (int r = 0; r < R_COUNT; ++r)
         if (!strcmp(routine, kRoutineNames[r]) || !strcmp(routine, "all")) {
-            c->cfg[r] = LaunchCfg{variant, threads, blocks_per_sm};
+            c->cfg[r] = LaunchCfg{variant >= 0 ? variant : kDefaultCfg[r].variant, threads > 0 ? threads : kDefaultCfg[r].threads,
+                                  (variant < 0 && threads <= 0 && blocks_per_sm <= 0) ? kDefaultCfg[r].blocks_per_sm : blocks_per_sm};
             if (strcmp(routine, "all")) return LBK_OK;
         }
     if (!strcmp(routine, "all")) return LBK_OK;

@@ -61,6 +61,18 @@ class Context:
     def stream(self) -> int:
         return int(_ffi.lib().lbk_stream(self.handle) or 0)
 
+    # ---- communicator (one process per GPU) ----
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _ffi.check(_ffi.lib().lbk_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes) -> None:
+        assert len(unique_id) == 128
+        _ffi.check(_ffi.lib().lbk_comm_init(self.handle, nranks, rank, unique_id), self.handle)
+        self.nranks, self.rank = nranks, rank
+
     # ---- vectors ----
     def alloc(self, n: int) -> "DVector":
         h = C.c_void_p()
@@ -174,6 +186,18 @@ class DVector:
         _ffi.check(_ffi.lib().lbk_vec_upload(self._h, a.ctypes.data_as(C.c_void_p), a.size), self.ctx.handle)
         return self
 
+    def upload_async(self, host: np.ndarray) -> "DVector":
+        """Enqueue host -> device (host should come from pinned_array); returns at once."""
+        assert host.dtype == np.float32 and host.flags.c_contiguous
+        _ffi.check(_ffi.lib().lbk_vec_upload_async(self._h, host.ctypes.data_as(C.c_void_p), host.size), self.ctx.handle)
+        return self
+
+    def download_async(self, out: np.ndarray) -> np.ndarray:
+        """Enqueue device -> host into `out` (pinned); valid after ctx.sync()."""
+        assert out.dtype == np.float32 and out.flags.c_contiguous
+        _ffi.check(_ffi.lib().lbk_vec_download_async(self._h, out.ctypes.data_as(C.c_void_p), out.size), self.ctx.handle)
+        return out
+
     def fill_hash(self, seed: int, lo: float = -1.0, hi: float = 1.0) -> "DVector":
         _ffi.check(_ffi.lib().lbk_vec_fill_hash(self._h, seed, lo, hi), self.ctx.handle)
         return self
@@ -189,6 +213,39 @@ class DVector:
         except Exception:
             pass
         self._h = None
+
+
+class _Pinned:
+    def __init__(self, n: int):
+        p = C.POINTER(C.c_float)()
+        _ffi.check(_ffi.lib().lbk_host_alloc(n, C.byref(p)))
+        self.p, self.n = p, n
+
+    def __del__(self):
+        try:
+            _ffi.lib().lbk_host_free(self.p)
+        except Exception:
+            pass
+
+
+def pinned_array(n: int) -> np.ndarray:
+    """A float32 numpy array over page-locked host memory (lbk_host_alloc), for async transfers."""
+    if n == 0:
+        return np.empty(0, dtype=np.float32)
+    owner = _Pinned(n)
+    arr = np.ctypeslib.as_array(owner.p, shape=(n,))
+    # keep the allocation alive as long as any view of the array is
+    out = arr.view(_PinnedArray)
+    out._owner = owner
+    return out
+
+
+class _PinnedArray(np.ndarray):
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._owner = getattr(obj, "_owner", None)
 
 
 def hash_fill_reference(n: int, seed: int, lo: float = -1.0, hi: float = 1.0, offset: int = 0) -> np.ndarray:
