@@ -73,6 +73,12 @@ int lbk_sm_count(lbk_ctx *ctx, int *sms);
 int lbk_set_launch(lbk_ctx *ctx, const char *routine, int variant, int threads, int blocks_per_sm);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int lbk_launch_count(lbk_ctx *ctx, int64_t *launches);
+/* Programmatic dependent launch (on by default): a unit-stride kernel enqueued right after a unit-stride
+ * reduction may start while that reduction's latency-bound tail (block combine, last-block fold) drains,
+ * provided its operands do not overlap the reduction's result.  Results are unaffected.  lbk_pdl_count
+ * reports how many launches took that path. */
+int lbk_set_pdl(lbk_ctx *ctx, int enabled);
+int lbk_pdl_count(lbk_ctx *ctx, int64_t *launches);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink -------------------------------------- */
 /* Rank 0 makes an id and hands the 128 bytes to every rank (any transport; the host layer uses

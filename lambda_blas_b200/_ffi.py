@@ -42,6 +42,8 @@ PROTOTYPES = {
     "lbk_sm_count": (_int, [_vp, _pint]),
     "lbk_set_launch": (_int, [_vp, C.c_char_p, _int, _int, _int]),
     "lbk_launch_count": (_int, [_vp, _pi64]),
+    "lbk_set_pdl": (_int, [_vp, _int]),
+    "lbk_pdl_count": (_int, [_vp, _pi64]),
     "lbk_comm_unique_id": (_int, [C.c_char_p]),
     "lbk_comm_init": (_int, [_vp, _int, _int, C.c_char_p]),
     "lbk_comm_info": (_int, [_vp, _pint, _pint]),

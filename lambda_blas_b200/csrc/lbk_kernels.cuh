@@ -99,6 +99,18 @@ __device__ __forceinline__ void store_pack(float *ptr, const Pack<VEC> &p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A reduction ends with a latency-bound tail (block combine,
+// fence, ticket, last-block fold: ~8 us, as much as 5% of a 4-byte-per-element kernel at n = 2^28).
+// Once a block of a reduction has issued its last load it lets the NEXT kernel of the stream start
+// (launch_dependents); that kernel streams through HBM while the tail drains and calls wait()
+// before it touches anything the tail still owns (scratch, ticket) or before it exits.  The host only
+// sets the launch attribute when the next kernel's operands do not overlap the tail's output.
+// Both instructions are no-ops in a kernel launched without the attribute.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // map functors.  (x, y) are the OLD values; the functor overwrites them with the new ones.  Every
 // product is rounded before it is added (__fmul_rn / __fadd_rn are never contracted into an FMA),
 // which is what the reference's compiled code does, so results are bit-identical to it.
@@ -230,6 +242,7 @@ map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64
             if constexpr (F::WY) yw[e] = ys;
         }
     }
+    pdl_wait();     // as a PDL secondary: do not retire before the preceding reduction has
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -292,7 +305,7 @@ constexpr float kSSml = 3.7778931862957162e+22f;     // 2^75
 
 // Op concept:  Acc, zero(), step(acc,x,y,ord), to_record(acc, ord->index map), merge(a,b)
 struct DotOp {       // Single.hs:81-82
-    static constexpr bool TWO = true, IS_IAMAX = false;
+    static constexpr bool TWO = true, IS_IAMAX = false, HAS_PACK_STEP = false;
     struct Acc { float s; };
     __device__ static __forceinline__ Acc zero() { return {0.f}; }
     __device__ static __forceinline__ void step(Acc &a, float x, float y, unsigned) { a.s = fmaf(x, y, a.s); }
@@ -302,7 +315,7 @@ struct DotOp {       // Single.hs:81-82
     { Record o = a; o.f[0] = a.f[0] + b.f[0]; return o; }
 };
 struct DsdotOp {     // Single.hs:238-262: products and sum in double (held as a double split over f[0],f[1] bits)
-    static constexpr bool TWO = true, IS_IAMAX = false;
+    static constexpr bool TWO = true, IS_IAMAX = false, HAS_PACK_STEP = false;
     struct Acc { double s; };
     __device__ static __forceinline__ Acc zero() { return {0.0}; }
     __device__ static __forceinline__ void step(Acc &a, float x, float y, unsigned) { a.s = fma((double)x, (double)y, a.s); }
@@ -316,7 +329,7 @@ struct DsdotOp {     // Single.hs:238-262: products and sum in double (held as a
     { Record o = a; put(o, get(a) + get(b)); return o; }
 };
 struct AsumOp {      // Single.hs:163
-    static constexpr bool TWO = false, IS_IAMAX = false;
+    static constexpr bool TWO = false, IS_IAMAX = false, HAS_PACK_STEP = false;
     struct Acc { float s; };
     __device__ static __forceinline__ Acc zero() { return {0.f}; }
     __device__ static __forceinline__ void step(Acc &a, float x, float, unsigned) { a.s += fabsf(x); }
@@ -326,7 +339,7 @@ struct AsumOp {      // Single.hs:163
     { Record o = a; o.f[0] = a.f[0] + b.f[0]; return o; }
 };
 struct Nrm2Op {      // Single.hs:180-199, restated as Blue's three accumulators
-    static constexpr bool TWO = false, IS_IAMAX = false;
+    static constexpr bool TWO = false, IS_IAMAX = false, HAS_PACK_STEP = true;
     struct Acc { float big, med, sml; };
     __device__ static __forceinline__ Acc zero() { return {0.f, 0.f, 0.f}; }
     __device__ static __forceinline__ void step(Acc &a, float x, float, unsigned)
@@ -335,6 +348,23 @@ struct Nrm2Op {      // Single.hs:180-199, restated as Blue's three accumulators
         if (ax > kBig) { const float t = ax * kSBig; a.big = fmaf(t, t, a.big); }
         else if (ax < kSml) { const float t = ax * kSSml; a.sml = fmaf(t, t, a.sml); }
         else a.med = fmaf(ax, ax, a.med);      // NaN lands here and propagates
+    }
+    // One vector of lanes: when every lane is mid-range (the overwhelmingly common case) the pack costs
+    // one FFMA and two FMNMX per element; a pack holding a huge, tiny or zero lane takes the exact
+    // per-lane classification.  fmaxf/fminf skip NaN lanes, and the fast path's x*x propagates them.
+    template <int VEC>
+    __device__ static __forceinline__ void step_pack(Acc &a, const Pack<VEC> &x, const Pack<VEC> &, unsigned)
+    {
+        float mx = fabsf(x.v[0]), mn = mx;
+#pragma unroll
+        for (int l = 1; l < VEC; ++l) { mx = fmaxf(mx, fabsf(x.v[l])); mn = fminf(mn, fabsf(x.v[l])); }
+        if (mx <= kBig && mn >= kSml) {
+#pragma unroll
+            for (int l = 0; l < VEC; ++l) a.med = fmaf(x.v[l], x.v[l], a.med);
+        } else {
+#pragma unroll
+            for (int l = 0; l < VEC; ++l) step(a, x.v[l], 0.f, 0u);
+        }
     }
     __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = a.big; r.f[1] = a.med; r.f[2] = a.sml; }
     __device__ static __forceinline__ void single(Record &r, float x, float, i64)
@@ -351,15 +381,31 @@ __device__ __forceinline__ unsigned amax_key(float x)
     return b > 0x7f800000u ? 0u : b;
 }
 struct IamaxOp {
-    static constexpr bool TWO = false, IS_IAMAX = true;
-    struct Acc { unsigned key; unsigned ord; };
-    __device__ static __forceinline__ Acc zero() { return {0u, 0u}; }
-    // elements reach a thread in increasing index order, so strict '>' keeps the first maximum; a
-    // thread that saw any element saw ordinal 0 first, which is what (key 0, ord 0) stands for
+    static constexpr bool TWO = false, IS_IAMAX = true, HAS_PACK_STEP = true;
+    // running maximum of |x| as a float (-1 = nothing seen yet; any |x| >= 0 beats it) and the ordinal,
+    // within this thread's element sequence, of the FIRST element that reached it
+    struct Acc { float val; unsigned ord; };
+    __device__ static __forceinline__ Acc zero() { return {-1.f, 0u}; }
     __device__ static __forceinline__ void step(Acc &a, float x, float, unsigned ord)
     {
-        const unsigned k = amax_key(x);
-        if (k > a.key) { a.key = k; a.ord = ord; }
+        const float ax = fabsf(x);
+        if (ax > a.val) { a.val = ax; a.ord = ord; }      // false for NaN: a NaN never displaces
+    }
+    // elements reach a thread in increasing index order, so strict '>' keeps the first maximum.  Per
+    // pack: one FMNMX per element (fmaxf drops NaN lanes, which is the reference's "NaN never wins");
+    // only a pack that raises the thread's maximum (O(log) times per thread) looks for the lane.
+    template <int VEC>
+    __device__ static __forceinline__ void step_pack(Acc &a, const Pack<VEC> &x, const Pack<VEC> &, unsigned ord0)
+    {
+        float m = fabsf(x.v[0]);
+#pragma unroll
+        for (int l = 1; l < VEC; ++l) m = fmaxf(m, fabsf(x.v[l]));
+        if (m > a.val) {
+            unsigned lane = 0;
+#pragma unroll
+            for (int l = VEC - 1; l >= 0; --l) if (fabsf(x.v[l]) == m) lane = l;
+            a.val = m; a.ord = ord0 + lane;
+        }
     }
     __device__ static __forceinline__ void to_record(Record &, const Acc &) {}
     __device__ static __forceinline__ void single(Record &r, float x, float, i64 idx)
@@ -439,10 +485,9 @@ __host__ __device__ __forceinline__ float nrm2_finish(float abig, float amed, fl
 }
 
 // Applies the rules that depend on logical element 0 to this rank's record (before any exchange).
-__device__ __forceinline__ void localize_record(Record &r, const FinishArgs &fa)
+__device__ __forceinline__ void localize_record(Record &r, const FinishArgs &fa, float x0)
 {
     if (fa.x0 != nullptr) {
-        const float x0 = *fa.x0;
         if (fa.kind == 2 && x0 != x0) { r.key = kNanKey; r.idx = 0; }      // NaN at index 0 stays
         if (fa.kind == 1) r.key = __float_as_uint(fabsf(x0));              // nrm2 n==1 -> |x[0]|
     }
@@ -461,10 +506,11 @@ __device__ __forceinline__ void finish_record(const Record &r, const FinishArgs 
 
 template <class Op>
 __device__ __forceinline__ void grid_finish(Record r, Record *partials, unsigned *ticket,
-                                            const FinishArgs &fa, Record *smem)
+                                            const FinishArgs &fa, Record *smem, float x0)
 {
     __shared__ bool is_last;
     r = block_combine<Op>(r, smem);
+    pdl_wait();          // the scratch below may still be in use by the preceding reduction's tail
     if (threadIdx.x == 0) {
         partials[blockIdx.x] = r;
         __threadfence();
@@ -484,9 +530,19 @@ __device__ __forceinline__ void grid_finish(Record r, Record *partials, unsigned
     }
     acc = block_combine<Op>(acc, smem);
     if (threadIdx.x == 0) {
-        localize_record(acc, fa);
+        localize_record(acc, fa, x0);
         if (fa.mode == 0) finish_record(acc, fa);
         else *fa.rec_out = acc;
+    }
+}
+
+template <class Op, int VEC>
+__device__ __forceinline__ void pack_step(typename Op::Acc &acc, const Pack<VEC> &x, const Pack<VEC> &y, unsigned ord0)
+{
+    if constexpr (Op::HAS_PACK_STEP) Op::template step_pack<VEC>(acc, x, y, ord0);
+    else {
+#pragma unroll
+        for (int l = 0; l < VEC; ++l) Op::step(acc, x.v[l], Op::TWO ? y.v[l] : 0.f, ord0 + l);
     }
 }
 
@@ -502,6 +558,7 @@ reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
     const float *bx = x + head, *by = y + head;
+    const float x0 = fa.x0 != nullptr ? *fa.x0 : 0.f;   // read now: a PDL secondary may overwrite x later
 
     typename Op::Acc acc = Op::zero();
     unsigned it = 0;
@@ -516,11 +573,7 @@ reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base
                 if constexpr (Op::TWO) load_pack<VEC, POLICY, true>(yv[u], by + e);
             }
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-#pragma unroll
-                for (int l = 0; l < VEC; ++l)
-                    Op::step(acc, xv[u].v[l], Op::TWO ? yv[u].v[l] : 0.f, it * (UNROLL * VEC) + u * VEC + l);
-            }
+            for (int u = 0; u < UNROLL; ++u) pack_step<Op, VEC>(acc, xv[u], yv[u], it * (UNROLL * VEC) + u * VEC);
         } else {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -529,25 +582,12 @@ reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base
                     const i64 e = p * VEC;
                     load_pack<VEC, POLICY, true>(xv[u], bx + e);
                     if constexpr (Op::TWO) load_pack<VEC, POLICY, true>(yv[u], by + e);
-#pragma unroll
-                    for (int l = 0; l < VEC; ++l)
-                        Op::step(acc, xv[u].v[l], Op::TWO ? yv[u].v[l] : 0.f, it * (UNROLL * VEC) + u * VEC + l);
+                    pack_step<Op, VEC>(acc, xv[u], yv[u], it * (UNROLL * VEC) + u * VEC);
                 }
             }
         }
     }
     Record r = empty_record<Op>();
-    if constexpr (Op::IS_IAMAX) {
-        if ((i64)blockIdx.x * per_tile + threadIdx.x < npack) {    // saw >= 1 element; ordinal -> global index
-            const unsigned per = UNROLL * VEC;
-            const unsigned iter = acc.ord / per, rem = acc.ord % per, u = rem / VEC, l = rem % VEC;
-            const i64 tile = (i64)blockIdx.x + (i64)iter * gridDim.x;
-            r.key = acc.key;
-            r.idx = idx_base + head + ((tile * UNROLL + u) * blockDim.x + threadIdx.x) * VEC + l;
-        }
-    } else {
-        Op::to_record(r, acc);
-    }
     if (blockIdx.x == 0) {      // scalar head and tail
         const i64 tail0 = head + npack * VEC;
         const i64 nscalar = head + (n - tail0);
@@ -556,7 +596,23 @@ reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base
             Op::single(r, x[e], Op::TWO ? y[e] : 0.f, idx_base + e);
         }
     }
-    grid_finish<Op>(r, partials, ticket, fa, smem);
+    pdl_launch_dependents();    // every load of this block has been issued and consumed
+    if constexpr (Op::IS_IAMAX) {
+        if (acc.val >= 0.f) {    // saw >= 1 non-NaN element; ordinal -> global index
+            const unsigned per = UNROLL * VEC;
+            const unsigned iter = acc.ord / per, rem = acc.ord % per, u = rem / VEC, l = rem % VEC;
+            const i64 tile = (i64)blockIdx.x + (i64)iter * gridDim.x;
+            Record v = empty_record<Op>();
+            v.key = __float_as_uint(acc.val);
+            v.idx = idx_base + head + ((tile * UNROLL + u) * blockDim.x + threadIdx.x) * VEC + l;
+            r = Op::merge(v, r);
+        }
+    } else {
+        Record v = empty_record<Op>();
+        Op::to_record(v, acc);
+        r = Op::merge(v, r);
+    }
+    grid_finish<Op>(r, partials, ticket, fa, smem, x0);
 }
 
 // reduce, any increments: logical element i at x[kx0 + i*incx] (, y[ky0 + i*incy]).
@@ -566,11 +622,12 @@ reduce_strided_kernel(const float *x, i64 incx, i64 kx0, const float *y, i64 inc
                       i64 idx_base, Record *partials, unsigned *ticket, FinishArgs fa)
 {
     __shared__ Record smem[32];
+    const float x0 = fa.x0 != nullptr ? *fa.x0 : 0.f;
     Record r = empty_record<Op>();
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         Op::single(r, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : 0.f, idx_base + i);
-    grid_finish<Op>(r, partials, ticket, fa, smem);
+    grid_finish<Op>(r, partials, ticket, fa, smem, x0);
 }
 
 // Cross-GPU finish: every rank holds all ranks' records (rank order) and folds them identically.

@@ -29,9 +29,9 @@ static_assert(sizeof(lbk_record) == sizeof(Record), "host and device records sha
 // ------------------------------------------------------------------------------------------------
 #define LBK_VARIANTS(X) \
     X(0, 4, 4, 1) X(1, 4, 2, 1) X(2, 4, 8, 1) X(3, 8, 2, 1) X(4, 8, 4, 1) X(5, 4, 4, 0) \
-    X(6, 8, 1, 1) X(7, 4, 1, 1) X(8, 1, 4, 1) X(9, 8, 2, 0)
-static const int kVariantVec[] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8};
-constexpr int kNumVariants = 10;
+    X(6, 8, 1, 1) X(7, 4, 1, 1) X(8, 1, 4, 1) X(9, 8, 2, 0) X(10, 8, 8, 1)
+static const int kVariantVec[] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8};
+constexpr int kNumVariants = 11;
 constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
 
@@ -64,7 +64,13 @@ struct lbk_ctx {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     LaunchCfg cfg[R_COUNT];
+    // Programmatic dependent launch: true while the last thing enqueued is a unit-stride reduction whose
+    // tail the next unit-stride kernel may overlap; [tail_lo, tail_hi) is what that tail still writes.
+    bool tail_open = false;
+    bool pdl_enabled = true;
+    const char *tail_lo = nullptr, *tail_hi = nullptr;
     int64_t launches = 0;
+    int64_t pdl_launches = 0;
     std::string err;
 };
 
@@ -207,6 +213,20 @@ extern "C" int lbk_launch_count(lbk_ctx *c, int64_t *launches)
     return LBK_OK;
 }
 
+extern "C" int lbk_set_pdl(lbk_ctx *c, int enabled)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_set_pdl: null context");
+    c->pdl_enabled = enabled != 0;
+    return LBK_OK;
+}
+
+extern "C" int lbk_pdl_count(lbk_ctx *c, int64_t *launches)
+{
+    if (!c || !launches) return fail(c, LBK_ERR_ARG, "lbk_pdl_count: null argument");
+    *launches = c->pdl_launches;
+    return LBK_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // communicator
 // ------------------------------------------------------------------------------------------------
@@ -331,7 +351,7 @@ extern "C" void *lbk_vec_ptr(const lbk_vec *v) { return v ? (void *)v->ptr : nul
 extern "C" int lbk_vec_upload_async(lbk_vec *v, const float *host, int64_t len)
 {
     if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_upload: bad argument");
-    if (len) CU(v->ctx, cudaMemcpyAsync(v->ptr, host, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream));
+    if (len) { v->ctx->tail_open = false; CU(v->ctx, cudaMemcpyAsync(v->ptr, host, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream)); }
     return LBK_OK;
 }
 extern "C" int lbk_vec_upload(lbk_vec *v, const float *host, int64_t len)
@@ -342,7 +362,7 @@ extern "C" int lbk_vec_upload(lbk_vec *v, const float *host, int64_t len)
 extern "C" int lbk_vec_download_async(const lbk_vec *v, float *host, int64_t len)
 {
     if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_download: bad argument");
-    if (len) CU(v->ctx, cudaMemcpyAsync(host, v->ptr, sizeof(float) * (size_t)len, cudaMemcpyDeviceToHost, v->ctx->stream));
+    if (len) { v->ctx->tail_open = false; CU(v->ctx, cudaMemcpyAsync(host, v->ptr, sizeof(float) * (size_t)len, cudaMemcpyDeviceToHost, v->ctx->stream)); }
     return LBK_OK;
 }
 extern "C" int lbk_vec_download(const lbk_vec *v, float *host, int64_t len)
@@ -359,6 +379,7 @@ extern "C" int lbk_vec_clone(const lbk_vec *v, lbk_vec **out)
     if (s) return s;
     w->global_len = v->global_len; w->shard_off = v->shard_off; w->sharded = v->sharded;
     if (v->len) {
+        v->ctx->tail_open = false;
         cudaError_t e = cudaMemcpyAsync(w->ptr, v->ptr, sizeof(float) * (size_t)v->len, cudaMemcpyDeviceToDevice, v->ctx->stream);
         if (e != cudaSuccess) { lbk_vec_free(w); return fail(v->ctx, LBK_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e)); }
     }
@@ -374,6 +395,7 @@ extern "C" int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, float lo, float hi)
     if (!v->len) return LBK_OK;
     lbk_ctx *c = v->ctx;
     CU(c, cudaSetDevice(c->device));
+    c->tail_open = false;
     lbk::fill_hash_kernel<<<stream_grid(c, v->len, 256), 256, 0, c->stream>>>(v->ptr, v->len, v->shard_off, seed, lo, hi - lo);
     KERNEL_CHECK(c);
     return LBK_OK;
@@ -384,6 +406,7 @@ extern "C" int lbk_vec_fill(lbk_vec *v, float value)
     if (!v->len) return LBK_OK;
     lbk_ctx *c = v->ctx;
     CU(c, cudaSetDevice(c->device));
+    c->tail_open = false;
     lbk::fill_kernel<<<stream_grid(c, v->len, 256), 256, 0, c->stream>>>(v->ptr, v->len, value);
     KERNEL_CHECK(c);
     return LBK_OK;
@@ -420,6 +443,7 @@ extern "C" int lbk_event_create(lbk_ctx *c, lbk_event **out)
 extern "C" int lbk_event_record(lbk_event *e)
 {
     if (!e) return fail(nullptr, LBK_ERR_ARG, "lbk_event_record: null event");
+    e->ctx->tail_open = false;
     CU(e->ctx, cudaEventRecord(e->ev, e->ctx->stream));
     return LBK_OK;
 }
@@ -531,6 +555,29 @@ static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int th
     return LBK_OK;
 }
 
+// Launches a unit-stride kernel, as a PDL secondary when the preceding reduction's tail is still open
+// and none of this kernel's operands overlaps what that tail writes.
+static int launch_stream_kernel(lbk_ctx *c, const void *k, int grid, int threads, void **args,
+                                const float *const *ptrs, const i64 *lens, int nptr)
+{
+    bool pdl = c->tail_open && c->pdl_enabled;
+    for (int i = 0; pdl && i < nptr; ++i) {
+        const char *lo = (const char *)ptrs[i], *hi = lo + 4 * lens[i];
+        if (ptrs[i] && lo < c->tail_hi && c->tail_lo < hi) pdl = false;
+    }
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = 0; lc.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+    c->tail_open = false;
+    CU(c, cudaLaunchKernelExC(&lc, k, args));
+    if (pdl) c->pdl_launches++;
+    KERNEL_CHECK(c);
+    return LBK_OK;
+}
+
 template <class F>
 static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const float *xr, const float *yr, float *xw, float *yw, i64 n, int default_variant)
 {
@@ -552,9 +599,9 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const float *xr, con
     if (s) return s;
     F fc = f;
     void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n};
-    CU(c, cudaLaunchKernel(k, dim3(grid), dim3(threads), args, 0, c->stream));
-    KERNEL_CHECK(c);
-    return LBK_OK;
+    const float *ops[4] = {xr, yr, xw, yw};
+    const i64 lens[4] = {n, n, n, n};
+    return launch_stream_kernel(c, k, grid, threads, args, ops, lens, 4);
 }
 
 template <class F>
@@ -564,6 +611,7 @@ static int launch_map_strided(lbk_ctx *c, const F &f, const float *xr, float *xw
 {
     const int threads = 256;
     const int grid = stream_grid(c, n - i_begin, threads);
+    c->tail_open = false;
     lbk::map_strided_kernel<F><<<grid, threads, 0, c->stream>>>(f, xr, xw, incx_r, incx_w, kx0_r, kx0_w,
                                                                  yr, yw, incy_r, incy_w, ky0_r, ky0_w, i_begin, n, x_last, y_last);
     KERNEL_CHECK(c);
@@ -595,11 +643,11 @@ static int map_dispatch(lbk_ctx *c, int rid, const F &f, i64 n,
     int x_last = 0, y_last = 0;
     if (F::WX && incx == 0) {            // n sequential writes to x[0]: the last wins, all read the original
         x_last = 1;
-        if (F::RX) { CU(c, cudaMemcpyAsync(c->snap, xr, sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); xr = c->snap; kx0_r = 0; }
+        if (F::RX) { c->tail_open = false; CU(c, cudaMemcpyAsync(c->snap, xr, sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); xr = c->snap; kx0_r = 0; }
     }
     if (F::WY && incy == 0) {
         y_last = 1;
-        if (F::RY) { CU(c, cudaMemcpyAsync(c->snap + 1, yr, sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); yr = c->snap + 1; ky0_r = 0; }
+        if (F::RY) { c->tail_open = false; CU(c, cudaMemcpyAsync(c->snap + 1, yr, sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); yr = c->snap + 1; ky0_r = 0; }
     }
     const bool only_last = (!F::WX || x_last) && (!F::WY || y_last);
     return launch_map_strided<F>(c, f, xr, xw, incx_r, incx_w, kx0_r, kx0, yr, yw, incy_r, incy_w, ky0_r, ky0,
@@ -641,8 +689,10 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
         const i64 nl = n > 0 ? O.n_local : 0;
         const bool unit_cover = nl > 0 && (O.inc == 1 || O.inc == -1);
         const i64 from = unit_cover ? nl : 0;
-        if (from < O.v->len)
+        if (from < O.v->len) {
+            c->tail_open = false;
             CU(c, cudaMemcpyAsync(w + from, O.v->ptr + from, sizeof(float) * (size_t)(O.v->len - from), cudaMemcpyDeviceToDevice, c->stream));
+        }
         return LBK_OK;
     };
     if ((s = prepare(X, xw, F::WX))) return s;
@@ -706,18 +756,28 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         if (s) return s;
         i64 nn = nl, ib = idx_base;
         void *args[] = {(void *)&x, (void *)&y, (void *)&head, (void *)&nn, (void *)&ib, (void *)&c->partials, (void *)&c->ticket, (void *)&fa};
-        CU(c, cudaLaunchKernel(k, dim3(grid), dim3(threads), args, 0, c->stream));
-        KERNEL_CHECK(c);
+        const float *ops[3] = {x, y, (const float *)out};
+        const i64 lens[3] = {nl, nl, 2};
+        s = launch_stream_kernel(c, k, grid, threads, args, ops, lens, 3);
+        if (s) return s;
+        if (!exchange) {            // the next unit-stride kernel may start under this kernel's tail
+            c->tail_open = true;
+            c->tail_lo = (const char *)out; c->tail_hi = c->tail_lo + 8;
+        }
     } else {
+        c->tail_open = false;
         const int threads = 256;
         const int grid = stream_grid(c, std::max<i64>(nl, 1), threads);
+        c->tail_open = false;
         lbk::reduce_strided_kernel<Op><<<grid, threads, 0, c->stream>>>(x, incx, first_index(nl, incx), y, incy,
                                                                           first_index(nl, incy), nl, idx_base, c->partials, c->ticket, fa);
         KERNEL_CHECK(c);
     }
     if (exchange) {
+        c->tail_open = false;
         NC(c, ncclAllGather(c->rec_send, c->rec_all, sizeof(Record), ncclChar, c->comm, c->stream));
         fa.mode = 0;
+        c->tail_open = false;
         lbk::finish_records_kernel<<<1, 32, 0, c->stream>>>(c->rec_all, c->nranks, fa);
         KERNEL_CHECK(c);
     }
@@ -727,6 +787,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
 static int store_f32(lbk_ctx *c, void *out, float v)
 {
     CU(c, cudaSetDevice(c->device));
+    c->tail_open = false;
     lbk::store_f32_kernel<<<1, 32, 0, c->stream>>>((float *)out, v);
     KERNEL_CHECK(c);
     return LBK_OK;
@@ -734,6 +795,7 @@ static int store_f32(lbk_ctx *c, void *out, float v)
 static int store_i64(lbk_ctx *c, void *out, i64 v)
 {
     CU(c, cudaSetDevice(c->device));
+    c->tail_open = false;
     lbk::store_i64_kernel<<<1, 32, 0, c->stream>>>((i64 *)out, v);
     KERNEL_CHECK(c);
     return LBK_OK;
@@ -861,7 +923,7 @@ static int scal_common(lbk_ctx *c, const char *who, i64 n, float a, const lbk_ve
     }
     if (n_eff <= 0 && xout && xout->ptr != x->ptr) {      // nothing to scale: the pure result is a copy
         if (xout->ctx != c || xout->len != x->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
-        if (x->len) CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, sizeof(float) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream));
+        if (x->len) { c->tail_open = false; CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, sizeof(float) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream)); }
         return LBK_OK;
     }
     return map_entry(c, who, R_SSCAL, lbk::ScalF{a}, n_eff, x, inc_eff, nullptr, 1, xout, nullptr, 0);
@@ -908,10 +970,12 @@ static int rotm_common(lbk_ctx *c, const char *who, i64 n, const lbk_vec *x, i64
     if (flag == -2.0f) {          // FLAGNEG2: the inputs come back as they are (Single.hs:473)
         if (xout && x && xout->ptr != x->ptr && x->len) {
             if (xout->len != x->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
+            c->tail_open = false;
             CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, sizeof(float) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream));
         }
         if (yout && y && yout->ptr != y->ptr && y->len) {
             if (yout->len != y->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
+            c->tail_open = false;
             CU(c, cudaMemcpyAsync(yout->ptr, y->ptr, sizeof(float) * (size_t)y->len, cudaMemcpyDeviceToDevice, c->stream));
         }
         return LBK_OK;

@@ -55,6 +55,14 @@ class Context:
         _ffi.check(_ffi.lib().lbk_launch_count(self.handle, C.byref(v)), self.handle)
         return v.value
 
+    def pdl_count(self) -> int:
+        v = C.c_int64()
+        _ffi.check(_ffi.lib().lbk_pdl_count(self.handle, C.byref(v)), self.handle)
+        return v.value
+
+    def set_pdl(self, enabled: bool) -> None:
+        _ffi.check(_ffi.lib().lbk_set_pdl(self.handle, int(enabled)), self.handle)
+
     def set_launch(self, routine: str, variant: int = -1, threads: int = 0, blocks_per_sm: int = 0) -> None:
         _ffi.check(_ffi.lib().lbk_set_launch(self.handle, routine.encode(), variant, threads, blocks_per_sm), self.handle)
 

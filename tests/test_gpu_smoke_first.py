@@ -33,7 +33,7 @@ def test_unit_paths_all_alignments(blas, ctx, oracle, n, off):
     P.assert_same(xo.to_host(), wx); P.assert_same(yo.to_host(), wy)
 
 
-@pytest.mark.parametrize("variant", range(10))
+@pytest.mark.parametrize("variant", range(11))
 @pytest.mark.parametrize("threads", [128, 512])
 def test_every_variant(blas, ctx, oracle, variant, threads):
     n = 300007
@@ -57,3 +57,33 @@ def test_every_variant(blas, ctx, oracle, variant, threads):
         P.assert_same(x2.to_host(), oracle.sscal(n, 3.0, v, 1))
     finally:
         ctx.set_launch("all", -1, 0, 0)
+
+
+def test_pdl_overlap_is_invisible(blas, ctx, oracle):
+    """Programmatic dependent launch lets the kernel after a reduction start under its tail: every result
+    must be bit-identical to the serialized order, including when the next kernel overwrites the vector
+    the reduction just read."""
+    from lambda_blas_b200 import inplace as ip
+    n = (1 << 22) + 5
+    rng = np.random.default_rng(77)
+    hx, hy = gen_unit(rng, n), gen_unit(rng, n)
+    hx[0] = np.nan                                  # isamax must still answer 0 (NaN at index 0 stays)
+    outs = {}
+    for pdl in (False, True):
+        ctx.set_pdl(pdl)
+        x, y, r = ctx.to_device(hx), ctx.to_device(hy), ctx.alloc(16)
+        before = ctx.pdl_count()
+        for it in range(6):
+            ip.sdot_async(n - 1, x.view(1, n - 1), 1, y.view(1, n - 1), 1, r.view(0, 2))
+            ip.saxpy_(n, 0.25, x, 1, y, 1)                   # writes y right after a reduction read it
+            ip.snrm2_async(n - 1, y.view(1, n - 1), 1, r.view(2, 2))
+            ip.isamax_async(n, x, 1, r.view(4, 2))
+            ip.sscal_(n, 1.5, x, 1)                           # overwrites x[0] the isamax tail depends on
+            ip.sasum_async(n - 1, x.view(1, n - 1), 1, r.view(6, 2))
+            ip.sdot_async(n - 1, x.view(1, n - 1), 1, x.view(1, n - 1), 1, r.view(8, 2))
+        outs[pdl] = (r.to_host(), x.to_host(), y.to_host(), ctx.pdl_count() - before)
+    ctx.set_pdl(True)
+    assert outs[False][3] == 0 and outs[True][3] >= 6 * 4
+    for a, b in zip(outs[False][:3], outs[True][:3]):
+        P.assert_same(a, b)
+    assert outs[True][0][4:6].view(np.int64)[0] == 0
