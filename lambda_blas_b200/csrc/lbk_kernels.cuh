@@ -41,17 +41,17 @@ template <int VEC, int POLICY, bool RO>
 __device__ __forceinline__ void load_pack(Pack<VEC> &p, const float *ptr)
 {
     if constexpr (VEC == 1) {
-        if constexpr (POLICY == 1 && RO)
+        if constexpr (POLICY >= 1 && RO)
             asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(p.v[0]) : "l"(ptr));
-        else if constexpr (POLICY == 1)
+        else if constexpr (POLICY >= 1)
             asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(p.v[0]) : "l"(ptr) : "memory");
         else
             asm volatile("ld.global.f32 %0, [%1];" : "=f"(p.v[0]) : "l"(ptr) : "memory");
     } else if constexpr (VEC == 4) {
-        if constexpr (POLICY == 1 && RO)
+        if constexpr (POLICY >= 1 && RO)
             asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                          : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]) : "l"(ptr));
-        else if constexpr (POLICY == 1)
+        else if constexpr (POLICY >= 1)
             asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                          : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]) : "l"(ptr) : "memory");
         else
@@ -59,18 +59,19 @@ __device__ __forceinline__ void load_pack(Pack<VEC> &p, const float *ptr)
                          : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]) : "l"(ptr) : "memory");
     } else {
         static_assert(VEC == 8, "VEC is 1, 4 or 8");
-        if constexpr (POLICY == 1 && RO)
-            asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]),
-                           "=f"(p.v[4]), "=f"(p.v[5]), "=f"(p.v[6]), "=f"(p.v[7]) : "l"(ptr));
-        else if constexpr (POLICY == 1)
-            asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]),
-                           "=f"(p.v[4]), "=f"(p.v[5]), "=f"(p.v[6]), "=f"(p.v[7]) : "l"(ptr) : "memory");
-        else
-            asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]),
-                           "=f"(p.v[4]), "=f"(p.v[5]), "=f"(p.v[6]), "=f"(p.v[7]) : "l"(ptr) : "memory");
+#define LBK_LD8(QUAL, CLOBBER)                                                                      \
+        asm volatile("ld.global" QUAL ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                     \
+                     : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]),                         \
+                       "=f"(p.v[4]), "=f"(p.v[5]), "=f"(p.v[6]), "=f"(p.v[7]) : "l"(ptr) CLOBBER)
+        // experimental L2 policies (256-bit accesses only): 2/3 evict-first loads, 4 256-byte L2 prefetch
+        if constexpr ((POLICY == 2 || POLICY == 3) && RO) LBK_LD8(".nc.L1::no_allocate.L2::evict_first", );
+        else if constexpr (POLICY == 2 || POLICY == 3) LBK_LD8(".L1::no_allocate.L2::evict_first", : "memory");
+        else if constexpr (POLICY == 4 && RO) LBK_LD8(".nc.L1::no_allocate.L2::256B", );
+        else if constexpr (POLICY == 4) LBK_LD8(".L1::no_allocate.L2::256B", : "memory");
+        else if constexpr (POLICY >= 1 && RO) LBK_LD8(".nc.L1::no_allocate", );
+        else if constexpr (POLICY >= 1) LBK_LD8(".L1::no_allocate", : "memory");
+        else LBK_LD8("", : "memory");
+#undef LBK_LD8
     }
 }
 
@@ -80,21 +81,22 @@ __device__ __forceinline__ void store_pack(float *ptr, const Pack<VEC> &p)
     if constexpr (VEC == 1) {
         asm volatile("st.global.f32 [%0], %1;" ::"l"(ptr), "f"(p.v[0]) : "memory");
     } else if constexpr (VEC == 4) {
-        if constexpr (POLICY == 1)
+        if constexpr (POLICY >= 1)
             asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(ptr),
                          "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]) : "memory");
         else
             asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(ptr),
                          "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]) : "memory");
     } else {
-        if constexpr (POLICY == 1)
-            asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr),
-                         "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]),
-                         "f"(p.v[4]), "f"(p.v[5]), "f"(p.v[6]), "f"(p.v[7]) : "memory");
-        else
-            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr),
-                         "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]),
-                         "f"(p.v[4]), "f"(p.v[5]), "f"(p.v[6]), "f"(p.v[7]) : "memory");
+#define LBK_ST8(QUAL)                                                                               \
+        asm volatile("st.global" QUAL ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr),         \
+                     "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]),                               \
+                     "f"(p.v[4]), "f"(p.v[5]), "f"(p.v[6]), "f"(p.v[7]) : "memory")
+        if constexpr (POLICY == 3 || POLICY == 5) LBK_ST8(".L1::no_allocate.L2::evict_first");
+        else if constexpr (POLICY == 4) LBK_ST8(".cs");
+        else if constexpr (POLICY >= 1) LBK_ST8(".L1::no_allocate");
+        else LBK_ST8("");
+#undef LBK_ST8
     }
 }
 

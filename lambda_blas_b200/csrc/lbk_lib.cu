@@ -29,9 +29,10 @@ static_assert(sizeof(lbk_record) == sizeof(Record), "host and device records sha
 // ------------------------------------------------------------------------------------------------
 #define LBK_VARIANTS(X) \
     X(0, 4, 4, 1) X(1, 4, 2, 1) X(2, 4, 8, 1) X(3, 8, 2, 1) X(4, 8, 4, 1) X(5, 4, 4, 0) \
-    X(6, 8, 1, 1) X(7, 4, 1, 1) X(8, 1, 4, 1) X(9, 8, 2, 0) X(10, 8, 8, 1)
-static const int kVariantVec[] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8};
-constexpr int kNumVariants = 11;
+    X(6, 8, 1, 1) X(7, 4, 1, 1) X(8, 1, 4, 1) X(9, 8, 2, 0) X(10, 8, 8, 1) \
+    X(11, 8, 4, 2) X(12, 8, 4, 3) X(13, 8, 4, 4) X(14, 8, 4, 5)
+static const int kVariantVec[] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8, 8, 8, 8, 8};
+constexpr int kNumVariants = 15;
 constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
 
@@ -39,11 +40,12 @@ enum Routine { R_SDOT, R_SDSDOT, R_SASUM, R_SNRM2, R_ISAMAX, R_SAXPY, R_SSCAL, R
 static const char *kRoutineNames[R_COUNT] = {"sdot", "sdsdot", "sasum", "snrm2", "isamax", "saxpy",
                                              "sscal", "scopy", "sswap", "srot", "srotm"};
 struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
-// Defaults from the n = 2^28 sweep on B200 (profiles/r01_tune_sweep.csv; tools/tune.py):
-// blocks_per_sm 0 = one resident wave (occupancy x SMs); larger values oversubscribe the SMs.
+// Defaults from the n = 2^28 sweeps on B200 (profiles/r01_tune_*.csv; tools/tune.py), reductions tuned
+// with their tails overlapped (PDL).  blocks_per_sm 0 = one resident wave (occupancy x SMs); larger
+// values oversubscribe the SMs and let the hardware block scheduler balance the load.
 static const LaunchCfg kDefaultCfg[R_COUNT] = {
-    /* sdot   */ {3, 512, 8},   /* sdsdot */ {3, 512, 8},   /* sasum  */ {0, 512, 0},
-    /* snrm2  */ {0, 512, 0},   /* isamax */ {2, 512, 16},  /* saxpy  */ {4, 128, 64},
+    /* sdot   */ {3, 512, 8},   /* sdsdot */ {3, 512, 8},   /* sasum  */ {10, 512, 0},
+    /* snrm2  */ {4, 256, 8},   /* isamax */ {0, 512, 8},   /* saxpy  */ {4, 128, 64},
     /* sscal  */ {4, 256, 32},  /* scopy  */ {4, 256, 32},  /* sswap  */ {4, 128, 64},
     /* srot   */ {4, 128, 64},  /* srotm  */ {4, 128, 64},
 };
@@ -756,9 +758,10 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         if (s) return s;
         i64 nn = nl, ib = idx_base;
         void *args[] = {(void *)&x, (void *)&y, (void *)&head, (void *)&nn, (void *)&ib, (void *)&c->partials, (void *)&c->ticket, (void *)&fa};
-        const float *ops[3] = {x, y, (const float *)out};
-        const i64 lens[3] = {nl, nl, 2};
-        s = launch_stream_kernel(c, k, grid, threads, args, ops, lens, 3);
+        // `out` is not listed: a reduction writes its result only after griddepcontrol.wait
+        const float *ops[2] = {x, y};
+        const i64 lens[2] = {nl, nl};
+        s = launch_stream_kernel(c, k, grid, threads, args, ops, lens, 2);
         if (s) return s;
         if (!exchange) {            // the next unit-stride kernel may start under this kernel's tail
             c->tail_open = true;

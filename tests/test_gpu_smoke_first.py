@@ -33,7 +33,7 @@ def test_unit_paths_all_alignments(blas, ctx, oracle, n, off):
     P.assert_same(xo.to_host(), wx); P.assert_same(yo.to_host(), wy)
 
 
-@pytest.mark.parametrize("variant", range(11))
+@pytest.mark.parametrize("variant", range(15))
 @pytest.mark.parametrize("threads", [128, 512])
 def test_every_variant(blas, ctx, oracle, variant, threads):
     n = 300007
