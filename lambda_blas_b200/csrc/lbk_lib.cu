@@ -9,7 +9,8 @@
 #include "lbk_kernels.cuh"
 
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
 #include <cstdio>
@@ -90,6 +91,41 @@ struct lbk_event { lbk_ctx *ctx; cudaEvent_t ev; };
 
 static thread_local std::string g_err;   // failures before a context exists
 
+// NCCL is bound with dlopen on first use instead of at link time: a process that also hosts PyTorch
+// must end up with ONE libnccl.so.2 (torch bundles a newer one than the system's and fails to import if
+// the older was mapped first), and single-GPU users need no NCCL at all.  RTLD_NOLOAD picks up whichever
+// copy the process already has.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { api.error = std::string("dlopen(libnccl.so.2): ") + dlerror(); return; }
+        api.handle = h;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) {
+            api.error = "libnccl.so.2 lacks a required symbol";
+            api.handle = nullptr;
+        }
+    });
+    return &api;
+}
+
 static int fail(lbk_ctx *ctx, int code, const std::string &msg)
 {
     if (ctx) ctx->err = msg; else g_err = msg;
@@ -105,7 +141,7 @@ static int fail(lbk_ctx *ctx, int code, const std::string &msg)
     do {                                                                                           \
         ncclResult_t r_ = (call);                                                                  \
         if (r_ != ncclSuccess)                                                                     \
-            return fail((ctx), LBK_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_));  \
+            return fail((ctx), LBK_ERR_NCCL, std::string(#call) + ": " + nccl_api()->GetErrorString(r_)); \
     } while (0)
 #define KERNEL_CHECK(ctx)                                                                          \
     do {                                                                                           \
@@ -166,7 +202,7 @@ extern "C" int lbk_shutdown(lbk_ctx *c)
     if (!c) return LBK_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->comm) nccl_api()->CommDestroy(c->comm);
     cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->snap);
     cudaFree(c->rec_send); cudaFree(c->rec_all);
     if (c->result_host) cudaFreeHost(c->result_host);
@@ -236,8 +272,9 @@ extern "C" int lbk_comm_unique_id(char id[128])
 {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     if (!id) return fail(nullptr, LBK_ERR_ARG, "lbk_comm_unique_id: null buffer");
+    if (!nccl_api()->handle) return fail(nullptr, LBK_ERR_NCCL, nccl_api()->error);
     ncclUniqueId u;
-    NC(nullptr, ncclGetUniqueId(&u));
+    NC(nullptr, nccl_api()->GetUniqueId(&u));
     memcpy(id, &u, 128);
     return LBK_OK;
 }
@@ -247,10 +284,11 @@ extern "C" int lbk_comm_init(lbk_ctx *c, int nranks, int rank, const char id[128
     if (!c || !id) return fail(c, LBK_ERR_ARG, "lbk_comm_init: null argument");
     if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return fail(c, LBK_ERR_ARG, "lbk_comm_init: bad rank / world size");
     if (c->comm) return fail(c, LBK_ERR_ARG, "lbk_comm_init: communicator already attached");
+    if (!nccl_api()->handle) return fail(c, LBK_ERR_NCCL, nccl_api()->error);
     CU(c, cudaSetDevice(c->device));
     ncclUniqueId u;
     memcpy(&u, id, 128);
-    NC(c, ncclCommInitRank(&c->comm, nranks, u, rank));
+    NC(c, nccl_api()->CommInitRank(&c->comm, nranks, u, rank));
     c->nranks = nranks;
     c->rank = rank;
     return LBK_OK;
@@ -778,7 +816,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
     }
     if (exchange) {
         c->tail_open = false;
-        NC(c, ncclAllGather(c->rec_send, c->rec_all, sizeof(Record), ncclChar, c->comm, c->stream));
+        NC(c, nccl_api()->AllGather(c->rec_send, c->rec_all, sizeof(Record), ncclChar, c->comm, c->stream));
         fa.mode = 0;
         c->tail_open = false;
         lbk::finish_records_kernel<<<1, 32, 0, c->stream>>>(c->rec_all, c->nranks, fa);

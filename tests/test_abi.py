@@ -1,0 +1,104 @@
+"""The C ABI library loads, exports every symbol include/lbk.h declares, and its host-only entry points
+(srotg, srotmg, shard partition, record fold) behave -- all without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.gen import nice_scalar
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "lbk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lbk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(blas):
+    from lambda_blas_b200 import _ffi
+    L = _ffi.lib()
+    names = declared_symbols()
+    assert len(names) >= 55
+    for n in names:
+        assert hasattr(L, n), f"liblbk.so does not export {n}"
+    assert sorted(_ffi.PROTOTYPES) == names, "the ctypes binding and the header disagree"
+    assert L.lbk_version() == 100
+
+
+def test_no_cpu_fallback(blas):
+    """Without a CUDA device the product refuses to run (it never routes through the oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(blas.LbkError):
+        blas.Context(0)
+    src = "".join(open(os.path.join(ROOT, "lambda_blas_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "lambda_blas_b200")) if f.endswith(".py"))
+    assert "oracle" not in src.replace("oracle binding", "").replace("test oracle", ""), "the product must not import the oracle"
+
+
+def bits(a):
+    return np.asarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_host_scalars_bit_exact(blas, oracle):      # Main.hs:31,33 (srotg, srotmg): product code, runs on the CPU
+    rng = np.random.default_rng(5)
+    seen = set()
+    for _ in range(5000):
+        a = [nice_scalar(rng) for _ in range(4)]
+        assert np.array_equal(bits(list(blas.srotg(a[0], a[1]))), bits(list(oracle.srotg(a[0], a[1]))))
+        g, w = blas.srotmg(*a), oracle.srotmg(*a)
+        seen.add(g.flag)
+        assert g.flag == w.flag
+        assert np.array_equal(bits([g.d1, g.d2, g.x1, g.h11, g.h12, g.h21, g.h22]), bits(list(w)[1:]))
+        assert np.array_equal(bits(g.sparam()), bits(w.sparam()))
+    assert seen == {-2, -1, 0, 1}
+    assert blas.srotmg(1.5, 0.75, 2.0, 0.5).constructor == "FLAG0"
+    assert list(blas.srotg(0, 0)) == [0, 0, 1, 0]          # Single.hs:281
+
+
+def test_srotmg_sparam_output(blas):
+    from lambda_blas_b200 import _ffi
+    out, par = (C.c_float * 8)(), (C.c_float * 5)()
+    assert _ffi.lib().lbk_srotmg(1.5, 0.75, 2.0, 0.5, out, par) == 0
+    assert list(par) == [0.0, 0.0, out[6], out[5], 0.0]     # [flag,h11,h21,h12,h22], Foreign.hs:279
+    assert _ffi.lib().lbk_srotmg(1.0, 0.0, 1.0, 1.0, out, par) == 0 and list(par) == [-2.0, 1.0, 0.0, 0.0, 1.0]
+
+
+@pytest.mark.parametrize("n,w", [(0, 1), (1, 4), (7, 3), (10, 8), (1 << 28, 8), ((1 << 30) + 5, 7)])
+def test_shard_partition_tiles_the_range(blas, n, w):
+    from lambda_blas_b200 import sharded
+    prev = 0
+    for r in range(w):
+        lo, hi = sharded.shard_range(n, w, r)
+        assert lo == prev and hi >= lo and hi - lo in (n // w, n // w + 1)
+        prev = hi
+    assert prev == n
+
+
+def test_record_fold(blas):
+    """What the finish kernel computes from the ranks' records, stated on the host."""
+    from lambda_blas_b200 import sharded
+    from lambda_blas_b200._ffi import Record
+
+    def rec(f=(0, 0, 0), key=0, idx=-1):
+        return Record((C.c_float * 3)(*f), key, idx, 0)
+    key = lambda v: int(np.float32(abs(v)).view(np.uint32))  # noqa: E731
+    # sum in rank order
+    assert sharded.combine_records(0, [rec((1.5,)), rec((2.25,)), rec((-0.75,))]) == 3.0
+    # isamax: larger |x| wins, ties go to the lower global index, empty shards are ignored
+    assert sharded.combine_records(2, [rec(key=key(3.0), idx=5), rec(key=key(-3.0), idx=1000), rec()]) == 5
+    assert sharded.combine_records(2, [rec(key=key(1.0), idx=5), rec(key=key(-3.0), idx=1000)]) == 1000
+    assert sharded.combine_records(2, [rec(), rec(key=0, idx=77)]) == 77
+    assert sharded.combine_records(2, [rec(key=0xFFFFFFFF, idx=0), rec(key=key(np.inf), idx=9)]) == 0   # NaN at index 0 stays
+    # nrm2: the three scaled sums add, then the Blue combine
+    got = sharded.combine_records(1, [rec((0, 9.0, 0)), rec((0, 16.0, 0))])
+    assert got == 5.0
+    big = np.float32(2.0 ** 100)
+    sb = np.float32(2.0 ** -76)
+    got = sharded.combine_records(1, [rec((float((big * sb) ** 2), 0, 0)), rec((float((big * sb) ** 2), 0, 0))])
+    assert abs(got / (float(big) * np.sqrt(2.0)) - 1) < 1e-6

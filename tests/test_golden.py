@@ -1,0 +1,121 @@
+"""Golden fixtures (tests/golden/level1_golden.json, made by tests/golden/make_golden.py).
+
+CPU: the oracle must reproduce them bit for bit (guards the checker itself).
+GPU: the CUDA path must match them -- isamax and every elementwise routine bit for bit (NaN matches NaN),
+the reductions within 2*n*eps*sum|x_i*y_i| -- including the non-finite / signed-zero / denormal cases
+the reference's own generators never produce ("spiced" input sets) and every increment sign, 0 included.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "level1_golden.json")))
+EPS = 2.0 ** -24
+
+
+def f32(u):
+    return np.array(u, dtype=np.uint32).view(np.float32)
+
+
+def same(got, want):
+    got, want = np.asarray(got, dtype=np.float32), np.asarray(want, dtype=np.float32)
+    nan = np.isnan(want)
+    return got.shape == want.shape and np.array_equal(np.isnan(got), nan) and \
+        np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan])
+
+
+def sample(v, n, inc):
+    first = 0 if inc > 0 else (1 - n) * inc
+    return np.asarray(v, dtype=np.float64)[first + np.arange(n) * inc]
+
+
+def run(impl, to_dev, to_host, case):
+    n, ix, iy = case["n"], case["incx"], case["incy"]
+    a, c, s = (f32([case[k]])[0] for k in ("a", "c", "s"))
+    x, y = f32(case["x"]), f32(case["y"])
+    dx, dy = to_dev(x), to_dev(y)
+    outs = {
+        "sdot": impl.sdot(n, dx, ix, dy, iy), "sdsdot": impl.sdsdot(n, a, dx, ix, dy, iy),
+        "sasum": impl.sasum(n, dx, ix), "snrm2": impl.snrm2(n, dx, ix), "isamax": impl.isamax(n, dx, ix),
+        "sscal": to_host(impl.sscal(n, a, dx, ix)), "scopy": to_host(impl.scopy(n, dx, ix, dy, iy)),
+        "saxpy": to_host(impl.saxpy(n, a, dx, ix, dy, iy)),
+        "sswap": [to_host(v) for v in impl.sswap(n, dx, ix, dy, iy)],
+        "srot": [to_host(v) for v in impl.srot(n, dx, ix, dy, iy, c, s)],
+    }
+    return outs, x, y
+
+
+def test_readme_example_in_golden(oracle):
+    r = G["readme_example"]
+    assert oracle.sdot(r["n"], f32(r["x"]), 1, f32(r["y"]), 1).view(np.uint32) == r["sdot"]
+
+
+def test_oracle_reproduces_golden(oracle):
+    for case in G["cases"]:
+        outs, x, y = run(oracle, lambda v: v, lambda v: v, case)
+        want = case["outs"]
+        for k in ("sdot", "sdsdot", "sasum", "snrm2"):
+            assert same([outs[k]], f32(want[k])), (k, case["n"], case["incx"], case["incy"])
+        assert outs["isamax"] == want["isamax"][0]
+        for k in ("sscal", "scopy", "saxpy"):
+            assert same(outs[k], f32(want[k])), k
+        for k in ("sswap", "srot"):
+            assert same(outs[k][0], f32(want[k][0])) and same(outs[k][1], f32(want[k][1])), k
+        flags = oracle.ModGivensRot(int(f32(case["param"])[0]))      # srotm consumes only sparam
+        p = f32(case["param"])
+        flags = oracle.ModGivensRot(int(p[0]), h11=p[1], h21=p[2], h12=p[3], h22=p[4])
+        mx, my = oracle.srotm(flags, case["n"], x, case["incx"], y, case["incy"])
+        assert same(mx, f32(want["srotm"][0])) and same(my, f32(want["srotm"][1]))
+    for s in G["scalars"]:
+        a = f32(s["args"])
+        assert same(list(oracle.srotg(a[0], a[1])), f32(s["rotg"]))
+        m = oracle.srotmg(*a)
+        assert m.flag == s["rotmg"][0] and same(list(m)[1:], f32(s["rotmg"][1:]))
+
+
+def test_product_host_scalars_match_golden(blas):
+    for s in G["scalars"]:
+        a = f32(s["args"])
+        assert same(list(blas.srotg(a[0], a[1])), f32(s["rotg"]))
+        m = blas.srotmg(*a)
+        assert m.flag == s["rotmg"][0]
+        assert same([m.d1, m.d2, m.x1, m.h11, m.h12, m.h21, m.h22], f32(s["rotmg"][1:]))
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_golden(blas, ctx):
+    import lambda_blas_b200 as lb
+    for case in G["cases"]:
+        n, ix, iy = case["n"], case["incx"], case["incy"]
+        saxpy_like_inc0 = (ix == 0 or iy == 0)
+        outs, x, y = run(blas, ctx.to_device, lambda v: v.to_host(), case)
+        want = case["outs"]
+        finite = np.all(np.isfinite(sample(x, n, ix))) and np.all(np.isfinite(sample(y, n, iy))) if n > 0 else True
+        tag = (n, ix, iy, case["spiced"])
+        assert outs["isamax"] == want["isamax"][0], tag
+        for k in ("sscal", "scopy", "saxpy"):
+            assert same(outs[k], f32(want[k])), (k,) + tag
+        for k in ("sswap", "srot"):
+            assert same(outs[k][0], f32(want[k][0])) and same(outs[k][1], f32(want[k][1])), (k,) + tag
+        p = f32(case["param"])
+        flags = lb.ModGivensRot(int(p[0]), h11=p[1], h21=p[2], h12=p[3], h22=p[4])
+        mx, my = blas.srotm(flags, n, ctx.to_device(x), ix, ctx.to_device(y), iy)
+        assert same(mx.to_host(), f32(want["srotm"][0])) and same(my.to_host(), f32(want["srotm"][1])), ("srotm",) + tag
+        if not finite:
+            continue        # reductions over Inf/NaN: covered by test_nonfinite_reductions (NaN-ness, not bits)
+        if n > 0:
+            prod = np.sum(np.abs(sample(x, n, ix) * sample(y, n, iy)))
+            assert abs(float(outs["sdot"]) - float(f32(want["sdot"])[0])) <= 2 * n * EPS * prod, ("sdot",) + tag
+            w = float(f32(want["sdsdot"])[0])
+            assert abs(float(outs["sdsdot"]) - w) <= float(np.spacing(np.float32(abs(w)))), ("sdsdot",) + tag
+        else:
+            assert same([outs["sdot"]], f32(want["sdot"])) and same([outs["sdsdot"]], f32(want["sdsdot"]))
+        ws, wn = float(f32(want["sasum"])[0]), float(f32(want["snrm2"])[0])
+        if n > 0 and ix > 0:
+            assert abs(float(outs["sasum"]) - ws) <= 2 * n * EPS * np.sum(np.abs(sample(x, n, ix))), ("sasum",) + tag
+            assert abs(float(outs["snrm2"]) - wn) <= 2 * n * EPS * wn, ("snrm2",) + tag
+        else:
+            assert float(outs["sasum"]) == ws and float(outs["snrm2"]) == wn

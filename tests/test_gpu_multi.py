@@ -1,0 +1,99 @@
+"""Sharded vectors over 2+ GPUs: one process per GPU, NCCL record exchange (run with gpurun --gpus 2).
+
+Every rank must return the same bits; the result must match the oracle on the whole (unsharded) vector:
+isamax exactly (ties and maxima at shard edges, NaN rule), sums within 2*n*eps*sum|.|, saxpy exactly.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import lambda_blas_b200 as lb
+    from lambda_blas_b200 import inplace as ip, sharded
+    from oracle import oracle
+    ctx = sharded.attach_torch_distributed(lb.Context(rank))
+    ok, notes = True, []
+    for n in [1, 2, 5, 1000, (1 << 20) + 3, 1 << 24]:
+        x, y = ctx.alloc_sharded(n).fill_hash(1), ctx.alloc_sharded(n).fill_hash(2)
+        hx, hy = lb.hash_fill_reference(n, 1), lb.hash_fill_reference(n, 2)
+        lo, hi = sharded.shard_range(n, world, rank)
+        assert len(x) == hi - lo and x.shard_offset == lo
+        # plant a tie across the shard boundary and a maximum at the last element of shard 0
+        if n >= 1000:
+            edge = sharded.shard_range(n, world, 0)[1]
+            for pos, val in ((edge - 1, 7.0), (edge, -7.0), (n - 1, 7.0)):
+                hx[pos] = val
+                if lo <= pos < hi:
+                    x.view(pos - lo, 1).upload(np.array([val], dtype=np.float32)) if world == 1 else None
+            # views of sharded vectors are refused by design: rewrite the shard through a wrapped handle
+            shard = ctx.wrap(x.ptr, len(x), keepalive=x)
+            shard.upload(hx[lo:hi])
+        prod = float(np.sum(np.abs(hx.astype(np.float64) * hy)))
+        d = lb.sdot(n, x, 1, y, 1)
+        ok &= abs(float(d) - float(oracle.sdot(n, hx, 1, hy, 1))) <= 2 * n * 2.0 ** -24 * prod
+        nr = lb.snrm2(n, x, 1)
+        ok &= abs(float(nr) - float(oracle.snrm2(n, hx, 1))) <= 2 * n * 2.0 ** -24 * float(oracle.snrm2(n, hx, 1))
+        sa = lb.sasum(n, x, 1)
+        ok &= abs(float(sa) - float(oracle.sasum(n, hx, 1))) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(hx)))
+        im = lb.isamax(n, x, 1)
+        ok &= im == oracle.isamax(n, hx, 1)
+        if n >= 5:          # n smaller than the vector: only the leading ranks take part
+            m = n - 2
+            ok &= lb.isamax(m, x, 1) == oracle.isamax(m, hx, 1)
+            ok &= abs(float(lb.sdot(m, x, 1, y, 1)) - float(oracle.sdot(m, hx, 1, hy, 1))) <= 2 * n * 2.0 ** -24 * prod
+        # every rank holds the same bits
+        t = torch.tensor([float(d), float(nr), float(sa), float(im)], dtype=torch.float64, device="cuda")
+        lo_t, hi_t = t.clone(), t.clone()
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN); dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+        ok &= bool(torch.equal(lo_t, hi_t))
+        # elementwise: no communication, shard by shard
+        ip.saxpy_(n, 1.000123, x, 1, y, 1)
+        want = oracle.saxpy(n, 1.000123, hx, 1, hy, 1)[lo:hi]
+        ok &= np.array_equal(y.to_host().view(np.uint32), want.view(np.uint32))
+        # non-unit increments on shards are refused, not silently wrong
+        try:
+            lb.sdot(max(n // 2, 1), x, 2, y, 2)
+            ok &= (world == 1)
+        except lb.LbkError as e:
+            ok &= e.status == 6
+        notes.append((n, bool(ok)))
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put((int(t.item()), notes))
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_sharded_routines_match_oracle():
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q, port = ctx.Queue(), _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    ok, notes = q.get(timeout=5)
+    assert ok == 1, notes
