@@ -156,7 +156,16 @@ def run_reference(args) -> None:
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 METRIC = "sdot+saxpy+snrm2 achieved HBM GB/s at n=2^28 per GPU (algorithmic bytes / device time)"
@@ -193,6 +202,10 @@ def run_ours(args) -> None:
     ctx = lb.Context(local)
     if world > 1:
         sharded.attach_torch_distributed(ctx)
+        if args.exchange != "auto":
+            ctx.set_fused_exchange(args.exchange == "fused")
+    exchange = ("fused: record pushed into every peer's mailbox over NVLink inside the reduction kernel" if ctx.fused_exchange()
+                else "ncclAllGather of one 32-byte record + finish kernel") if world > 1 else "none (1 rank)"
 
     n = 1 << args.log2n
     ng = n * world
@@ -343,7 +356,7 @@ def run_ours(args) -> None:
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args, world), exchange=exchange),
             "pct_of_8TBs_per_gpu": round(100 * value / world / NOMINAL_HBM_GBS, 1),
             "frac_of_measured_peak_per_gpu": round(value / world / peak, 3),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
@@ -351,7 +364,7 @@ def run_ours(args) -> None:
             "step_routines_ms": {r: round(v, 4) for r, v in per_routine_in_step.items()},
             "last_snrm2": float(step_check[0]),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.barrier()
@@ -359,6 +372,11 @@ def run_ours(args) -> None:
 
 
 def main():
+    # Libraries (NCCL's version banner, torchrun notices) may print to stdout; the contract is ONE JSON
+    # line there, so everything else goes to stderr and the line is written to the saved descriptor.
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -368,6 +386,8 @@ def main():
     ap.add_argument("--ref-log2n", type=int, default=26, help="log2 of the CPU sample length")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
+                    help="how sharded reductions end: in-kernel over NVLink peer memory, or ncclAllGather + finish kernel")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":

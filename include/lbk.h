@@ -87,6 +87,13 @@ int lbk_pdl_count(lbk_ctx *ctx, int64_t *launches);
 int lbk_comm_unique_id(char id[128]);
 int lbk_comm_init(lbk_ctx *ctx, int nranks, int rank, const char id[128]);
 int lbk_comm_info(lbk_ctx *ctx, int *nranks, int *rank);
+/* How a sharded reduction ends.  fused = 1: the reduction kernel's last block writes this rank's 32-byte
+ * record straight into every peer GPU's mailbox over NVLink (peer memory mapped with CUDA IPC at
+ * lbk_comm_init), waits for the peers' records and folds them in rank order -- compute and exchange in ONE
+ * kernel.  fused = 0: record -> ncclAllGather -> a one-thread finish kernel.  lbk_comm_init picks fused when
+ * every rank could map every mailbox; lbk_set_fused_exchange overrides it (all ranks must agree). */
+int lbk_comm_transport(lbk_ctx *ctx, int *fused);
+int lbk_set_fused_exchange(lbk_ctx *ctx, int enabled);
 /* Block partition of [0, global_len) used by lbk_vec_alloc_sharded: rank r owns [lo, hi). */
 int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t *lo, int64_t *hi);
 

@@ -47,6 +47,8 @@ PROTOTYPES = {
     "lbk_comm_unique_id": (_int, [C.c_char_p]),
     "lbk_comm_init": (_int, [_vp, _int, _int, C.c_char_p]),
     "lbk_comm_info": (_int, [_vp, _pint, _pint]),
+    "lbk_comm_transport": (_int, [_vp, _pint]),
+    "lbk_set_fused_exchange": (_int, [_vp, _int]),
     "lbk_shard_range": (_int, [_i64, _int, _int, _pi64, _pi64]),
     "lbk_vec_alloc": (_int, [_vp, _i64, _pvp]),
     "lbk_vec_alloc_sharded": (_int, [_vp, _i64, _pvp]),

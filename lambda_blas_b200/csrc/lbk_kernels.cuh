@@ -457,7 +457,10 @@ __device__ __forceinline__ Record block_combine(Record r, Record *smem)
 
 // What the last block does with the folded record.
 //   mode 0: finish on this GPU and store the scalar to `out` (float, or int64 for isamax);
-//   mode 1: store the record to `rec_out` for the cross-GPU exchange (finish_records_kernel ends it).
+//   mode 1: store the record to `rec_out`; an NCCL all-gather and finish_records_kernel end the call;
+//   mode 2: fused exchange -- push the record straight into every peer GPU's mailbox over NVLink (peer
+//           memory mapped with CUDA IPC), wait for the peers' records in this GPU's mailbox, fold them in
+//           rank order and finish, all inside this kernel.
 struct FinishArgs {
     int kind;             // lbk_reduce_kind: 0 sum, 1 nrm2, 2 iamax, 3 dsdot
     int mode;
@@ -466,7 +469,29 @@ struct FinishArgs {
     double sb;            // sdsdot's addend
     void *out;
     Record *rec_out;
+    // mode 2
+    unsigned long long *const *peers;   // device array: peers[r] = rank r's mailbox (peers[rank] is local)
+    int nranks, rank;
+    unsigned seq;                       // number of this exchange, identical on every rank, never 0
+    int *error_flag;                    // host-mapped: set to 1 if a peer's record never arrived
 };
+
+// Mailbox: two parities x kMaxRanks senders x 8 words.  Each 64-bit word carries 32 bits of record and
+// the 32-bit exchange number, so one store publishes data and "ready" together (no fence, no second
+// round trip); a word is valid once its tag equals the current exchange number.  Exchange k+2 can only
+// reuse exchange k's slots after every rank has consumed them (a rank sends k+1 only after finishing k).
+constexpr int kMaxRanks = 64;
+constexpr int kMailboxWords = 2 * kMaxRanks * 8;
+constexpr unsigned long long kExchangeTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ Record fold_by_kind(const Record *recs, int nranks, int kind);
 
 __host__ __device__ __forceinline__ float nrm2_finish(float abig, float amed, float asml)
 {
@@ -531,10 +556,45 @@ __device__ __forceinline__ void grid_finish(Record r, Record *partials, unsigned
         acc = Op::merge(acc, u.r);
     }
     acc = block_combine<Op>(acc, smem);
+    if (fa.mode != 2) {
+        if (threadIdx.x == 0) {
+            localize_record(acc, fa, x0);
+            if (fa.mode == 0) finish_record(acc, fa);
+            else *fa.rec_out = acc;
+        }
+        return;
+    }
+    // ---- fused exchange over peer memory ----
+    __shared__ Record mine;
+    __shared__ Record all[kMaxRanks];
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) { localize_record(acc, fa, x0); mine = acc; timed_out = 0; }
+    __syncthreads();
+    const unsigned par = fa.seq & 1u;
+    const unsigned *words = reinterpret_cast<const unsigned *>(&mine);
+    for (int t = threadIdx.x; t < fa.nranks * 8; t += blockDim.x) {      // push: one 8-byte store per word per peer
+        const int peer = t >> 3, w = t & 7;
+        unsigned long long *dst = fa.peers[peer] + ((par * kMaxRanks + fa.rank) << 3) + w;
+        const unsigned long long v = ((unsigned long long)fa.seq << 32) | words[w];
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+    }
+    const unsigned long long t_start = global_timer_ns();
+    for (int t = threadIdx.x; t < fa.nranks * 8; t += blockDim.x) {      // pull: poll this GPU's mailbox
+        const int src = t >> 3, w = t & 7;
+        const unsigned long long *slot = fa.peers[fa.rank] + ((par * kMaxRanks + src) << 3) + w;
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+            if ((unsigned)(v >> 32) == fa.seq) break;
+            if (global_timer_ns() - t_start > kExchangeTimeoutNs) { timed_out = 1; v = 0; break; }
+        }
+        reinterpret_cast<unsigned *>(&all[src])[w] = (unsigned)v;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        localize_record(acc, fa, x0);
-        if (fa.mode == 0) finish_record(acc, fa);
-        else *fa.rec_out = acc;
+        if (timed_out) *fa.error_flag = 1;
+        Record total = fold_by_kind(all, fa.nranks, fa.kind);
+        finish_record(total, fa);
     }
 }
 
@@ -640,15 +700,19 @@ __host__ __device__ __forceinline__ Record fold_ranks(const Record *recs, int nr
     for (int r = 1; r < nranks; ++r) acc = Op::merge(acc, recs[r]);
     return acc;
 }
+__device__ __forceinline__ Record fold_by_kind(const Record *recs, int nranks, int kind)
+{
+    Record acc;
+    if (kind == 2) acc = fold_ranks<IamaxOp>(recs, nranks);
+    else if (kind == 1) { acc = fold_ranks<Nrm2Op>(recs, nranks); acc.key = recs[0].key; }   // |x[0]| travels in rank 0's key
+    else if (kind == 3) acc = fold_ranks<DsdotOp>(recs, nranks);
+    else acc = fold_ranks<DotOp>(recs, nranks);
+    return acc;
+}
 __global__ void finish_records_kernel(const Record *recs, int nranks, FinishArgs fa)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Record acc;
-    if (fa.kind == 2) acc = fold_ranks<IamaxOp>(recs, nranks);
-    else if (fa.kind == 1) { acc = fold_ranks<Nrm2Op>(recs, nranks); acc.key = recs[0].key; }
-    else if (fa.kind == 3) acc = fold_ranks<DsdotOp>(recs, nranks);
-    else acc = fold_ranks<DotOp>(recs, nranks);
-    finish_record(acc, fa);
+    finish_record(fold_by_kind(recs, nranks, fa.kind), fa);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 using lbk::i64;
 using lbk::Record;
@@ -66,6 +67,13 @@ struct lbk_ctx {
     Record *rec_all = nullptr;        // all ranks' records after the exchange
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // fused exchange over peer memory (CUDA IPC): this rank's mailbox, the peers' mapped mailboxes
+    unsigned long long *mailbox = nullptr;
+    unsigned long long **peers_dev = nullptr;     // device copy of peer_ptrs
+    void *peer_ptrs[lbk::kMaxRanks] = {};
+    bool fused_exchange = false;
+    unsigned exchange_seq = 0;
+    int *error_flag_host = nullptr, *error_flag_dev = nullptr;   // mapped: a kernel reports an exchange timeout
     LaunchCfg cfg[R_COUNT];
     // Programmatic dependent launch: true while the last thing enqueued is a unit-stride reduction whose
     // tail the next unit-stride kernel may overlap; [tail_lo, tail_hi) is what that tail still writes.
@@ -189,6 +197,9 @@ extern "C" int lbk_init(int device, lbk_ctx **out)
     INIT(cudaMalloc(&c->snap, 2 * sizeof(float)));
     INIT(cudaHostAlloc(&c->result_host, 64, cudaHostAllocMapped));
     INIT(cudaHostGetDevicePointer(&c->result_dev, c->result_host, 0));
+    INIT(cudaHostAlloc((void **)&c->error_flag_host, sizeof(int), cudaHostAllocMapped));
+    *c->error_flag_host = 0;
+    INIT(cudaHostGetDevicePointer((void **)&c->error_flag_dev, c->error_flag_host, 0));
     INIT(cudaMalloc(&c->rec_send, sizeof(Record)));
     INIT(cudaMalloc(&c->rec_all, sizeof(Record) * 64));
     INIT(cudaDeviceSynchronize());
@@ -202,7 +213,11 @@ extern "C" int lbk_shutdown(lbk_ctx *c)
     if (!c) return LBK_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int r = 0; r < c->nranks; ++r)
+        if (r != c->rank && c->peer_ptrs[r]) cudaIpcCloseMemHandle(c->peer_ptrs[r]);
     if (c->comm) nccl_api()->CommDestroy(c->comm);
+    cudaFree(c->mailbox); cudaFree(c->peers_dev);
+    if (c->error_flag_host) cudaFreeHost(c->error_flag_host);
     cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->snap);
     cudaFree(c->rec_send); cudaFree(c->rec_all);
     if (c->result_host) cudaFreeHost(c->result_host);
@@ -211,11 +226,20 @@ extern "C" int lbk_shutdown(lbk_ctx *c)
     return LBK_OK;
 }
 
+static int check_exchange_error(lbk_ctx *c)
+{
+    if (c->error_flag_host && *reinterpret_cast<volatile int *>(c->error_flag_host)) {
+        *c->error_flag_host = 0;
+        return fail(c, LBK_ERR_NCCL, "peer exchange timed out: a rank never delivered its record (did every rank make the same call?)");
+    }
+    return LBK_OK;
+}
+
 extern "C" int lbk_sync(lbk_ctx *c)
 {
     if (!c) return fail(nullptr, LBK_ERR_ARG, "lbk_sync: null context");
     CU(c, cudaStreamSynchronize(c->stream));
-    return LBK_OK;
+    return check_exchange_error(c);
 }
 
 extern "C" const char *lbk_last_error(lbk_ctx *c) { return c ? c->err.c_str() : g_err.c_str(); }
@@ -279,6 +303,52 @@ extern "C" int lbk_comm_unique_id(char id[128])
     return LBK_OK;
 }
 
+// Maps every rank's mailbox into this process (CUDA IPC over NVLink peer access).  All ranks then agree on
+// whether the fused exchange is usable; if any rank could not map a peer, all use the NCCL all-gather.
+static int setup_fused_exchange(lbk_ctx *c)
+{
+    const int n = c->nranks;
+    struct Card { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+    Card mine;
+    memset(&mine, 0, sizeof mine);
+    Card *dev = nullptr;
+    CU(c, cudaMalloc(&c->mailbox, sizeof(unsigned long long) * lbk::kMailboxWords));
+    CU(c, cudaMemset(c->mailbox, 0, sizeof(unsigned long long) * lbk::kMailboxWords));
+    CU(c, cudaMalloc(&c->peers_dev, sizeof(void *) * lbk::kMaxRanks));
+    CU(c, cudaMalloc(&dev, sizeof(Card) * (n + 1)));
+    mine.ok = cudaIpcGetMemHandle(&mine.h, c->mailbox) == cudaSuccess ? 1 : 0;
+    cudaGetLastError();
+    std::vector<Card> cards(n);
+    // round 1: everybody's handle
+    CU(c, cudaMemcpyAsync(dev + n, &mine, sizeof(Card), cudaMemcpyHostToDevice, c->stream));
+    NC(c, nccl_api()->AllGather(dev + n, dev, sizeof(Card), ncclChar, c->comm, c->stream));
+    CU(c, cudaMemcpyAsync(cards.data(), dev, sizeof(Card) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    int ok = 1;
+    for (int r = 0; r < n; ++r) {
+        c->peer_ptrs[r] = nullptr;
+        if (!cards[r].ok) { ok = 0; continue; }
+        if (r == c->rank) { c->peer_ptrs[r] = c->mailbox; continue; }
+        if (cudaIpcOpenMemHandle(&c->peer_ptrs[r], cards[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            c->peer_ptrs[r] = nullptr;
+            ok = 0;
+        }
+    }
+    // round 2: does every rank see every mailbox?
+    mine.ok = ok;
+    CU(c, cudaMemcpyAsync(dev + n, &mine, sizeof(Card), cudaMemcpyHostToDevice, c->stream));
+    NC(c, nccl_api()->AllGather(dev + n, dev, sizeof(Card), ncclChar, c->comm, c->stream));
+    CU(c, cudaMemcpyAsync(cards.data(), dev, sizeof(Card) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < n; ++r) ok = ok && cards[r].ok;
+    CU(c, cudaMemcpy(c->peers_dev, c->peer_ptrs, sizeof(void *) * lbk::kMaxRanks, cudaMemcpyHostToDevice));
+    cudaFree(dev);
+    c->fused_exchange = ok != 0;
+    c->exchange_seq = 0;
+    return LBK_OK;
+}
+
 extern "C" int lbk_comm_init(lbk_ctx *c, int nranks, int rank, const char id[128])
 {
     if (!c || !id) return fail(c, LBK_ERR_ARG, "lbk_comm_init: null argument");
@@ -291,6 +361,21 @@ extern "C" int lbk_comm_init(lbk_ctx *c, int nranks, int rank, const char id[128
     NC(c, nccl_api()->CommInitRank(&c->comm, nranks, u, rank));
     c->nranks = nranks;
     c->rank = rank;
+    return setup_fused_exchange(c);
+}
+
+extern "C" int lbk_comm_transport(lbk_ctx *c, int *fused)
+{
+    if (!c || !fused) return fail(c, LBK_ERR_ARG, "lbk_comm_transport: null argument");
+    *fused = c->fused_exchange ? 1 : 0;
+    return LBK_OK;
+}
+
+extern "C" int lbk_set_fused_exchange(lbk_ctx *c, int enabled)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_set_fused_exchange: null context");
+    if (enabled && !c->mailbox) return fail(c, LBK_ERR_UNSUPPORTED, "lbk_set_fused_exchange: peer mailboxes were not mapped on this communicator");
+    c->fused_exchange = enabled != 0;
     return LBK_OK;
 }
 
@@ -771,9 +856,16 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
     const i64 nl = X.n_local;
     const float *x = X.v->ptr, *y = Y ? Y->v->ptr : nullptr;
     const i64 incx = X.inc, incy = Y ? Y->inc : 1;
+    const bool fused = exchange && c->fused_exchange;
     FinishArgs fa;
+    memset(&fa, 0, sizeof fa);
     fa.kind = kind;
-    fa.mode = exchange ? 1 : 0;
+    fa.mode = exchange ? (fused ? 2 : 1) : 0;
+    if (fused) {
+        if (++c->exchange_seq == 0) ++c->exchange_seq;    // tag 0 means "empty slot"
+        fa.peers = c->peers_dev; fa.nranks = c->nranks; fa.rank = c->rank; fa.seq = c->exchange_seq;
+        fa.error_flag = c->error_flag_dev;
+    }
     fa.n_global = n;
     fa.sb = sb;
     fa.out = out;
@@ -801,7 +893,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         const i64 lens[2] = {nl, nl};
         s = launch_stream_kernel(c, k, grid, threads, args, ops, lens, 2);
         if (s) return s;
-        if (!exchange) {            // the next unit-stride kernel may start under this kernel's tail
+        if (!exchange || fused) {   // the next unit-stride kernel may start under this kernel's tail
             c->tail_open = true;
             c->tail_lo = (const char *)out; c->tail_hi = c->tail_lo + 8;
         }
@@ -814,7 +906,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
                                                                           first_index(nl, incy), nl, idx_base, c->partials, c->ticket, fa);
         KERNEL_CHECK(c);
     }
-    if (exchange) {
+    if (exchange && !fused) {
         c->tail_open = false;
         NC(c, nccl_api()->AllGather(c->rec_send, c->rec_all, sizeof(Record), ncclChar, c->comm, c->stream));
         fa.mode = 0;
@@ -870,7 +962,7 @@ static int finish_sync(lbk_ctx *c, int s, T *out)
     if (s) return s;
     CU(c, cudaStreamSynchronize(c->stream));
     *out = *reinterpret_cast<volatile T *>(c->result_host);
-    return LBK_OK;
+    return check_exchange_error(c);
 }
 
 extern "C" int lbk_sdot(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out)

@@ -81,6 +81,15 @@ class Context:
         _ffi.check(_ffi.lib().lbk_comm_init(self.handle, nranks, rank, unique_id), self.handle)
         self.nranks, self.rank = nranks, rank
 
+    def fused_exchange(self) -> bool:
+        """True when sharded reductions end inside the reduction kernel over NVLink peer memory."""
+        v = C.c_int()
+        _ffi.check(_ffi.lib().lbk_comm_transport(self.handle, C.byref(v)), self.handle)
+        return bool(v.value)
+
+    def set_fused_exchange(self, enabled: bool) -> None:
+        _ffi.check(_ffi.lib().lbk_set_fused_exchange(self.handle, int(enabled)), self.handle)
+
     # ---- vectors ----
     def alloc(self, n: int) -> "DVector":
         h = C.c_void_p()

@@ -29,7 +29,9 @@ def _worker(rank, world, port, q):
     from oracle import oracle
     ctx = sharded.attach_torch_distributed(lb.Context(rank))
     ok, notes = True, []
-    for n in [1, 2, 5, 1000, (1 << 20) + 3, 1 << 24]:
+    fused_available = ctx.fused_exchange()
+    for n, fused in [(n, f) for f in ((True, False) if fused_available else (False,)) for n in [1, 2, 5, 1000, (1 << 20) + 3, 1 << 24]]:
+        ctx.set_fused_exchange(fused)
         x, y = ctx.alloc_sharded(n).fill_hash(1), ctx.alloc_sharded(n).fill_hash(2)
         hx, hy = lb.hash_fill_reference(n, 1), lb.hash_fill_reference(n, 2)
         lo, hi = sharded.shard_range(n, world, rank)
@@ -72,7 +74,8 @@ def _worker(rank, world, port, q):
             ok &= (world == 1)
         except lb.LbkError as e:
             ok &= e.status == 6
-        notes.append((n, bool(ok)))
+        notes.append((n, fused, bool(ok)))
+    notes.append(("fused_available", fused_available))
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
