@@ -1,0 +1,37 @@
+// The reference's README example (README.md:47-59) and a few more calls, through the C++ mirror.
+//   g++ -std=c++17 cpp/example.cpp -o /tmp/lb_example -Llambda_blas_b200 -llbk -Wl,-rpath,$PWD/lambda_blas_b200
+#include <cmath>
+#include <cstdio>
+
+#include "lambda_blas.hpp"
+
+using namespace lambda_blas;
+
+int main()
+{
+    try {
+        Context ctx(0);
+        DVector u(ctx, {1, 2, 3}), v(ctx, {4, 5, 6});
+        const float d = sdot(3, u, 1, v, 1);                     // README.md:57-59 prints 32.0
+        std::printf("sdot = %g\n", d);
+        DVector w = saxpy(3, 2.0f, u, 1, v, 1);                   // pure: v is untouched
+        auto hw = w.to_host(), hv = v.to_host();
+        std::printf("saxpy = [%g %g %g], v still [%g %g %g]\n", hw[0], hw[1], hw[2], hv[0], hv[1], hv[2]);
+        auto sw = sswap(2, u, -1, v, 2);
+        auto a = sw.first.to_host(), b = sw.second.to_host();
+        std::printf("sswap(2,u,-1,v,2) = [%g %g %g] [%g %g %g]\n", a[0], a[1], a[2], b[0], b[1], b[2]);
+        std::printf("snrm2 = %g isamax = %lld sasum = %g\n", snrm2(3, v, 1), (long long)isamax(3, v, 1), sasum(3, v, 1));
+        ModGivensRot m = srotmg(1.5f, 0.75f, 2.0f, 0.5f);
+        auto r = srotm(m, 3, u, 1, v, 1);
+        auto rx = r.first.to_host();
+        std::printf("srotm flag %d -> x' = [%g %g %g]\n", m.flag, rx[0], rx[1], rx[2]);
+        bool ok = d == 32.0f && hw[0] == 6 && hw[1] == 9 && hw[2] == 12 && hv[0] == 4 && isamax(3, v, 1) == 2 &&
+                  a[0] == 6 && a[1] == 4 && a[2] == 3 && b[0] == 2 && b[1] == 5 && b[2] == 1;   // x[1-i] <-> y[2i], Util.hs:118-119
+        try { sdot(5, u, 1, v, 1); ok = false; } catch (const Error &e) { ok = ok && e.status == LBK_ERR_RANGE; }
+        std::printf(ok ? "OK\n" : "MISMATCH\n");
+        return ok ? 0 : 1;
+    } catch (const Error &e) {
+        std::fprintf(stderr, "lbk error %d: %s\n", e.status, e.what());
+        return 2;
+    }
+}

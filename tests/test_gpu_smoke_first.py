@@ -87,3 +87,17 @@ def test_pdl_overlap_is_invisible(blas, ctx, oracle):
     for a, b in zip(outs[False][:3], outs[True][:3]):
         P.assert_same(a, b)
     assert outs[True][0][4:6].view(np.int64)[0] == 0
+
+
+def test_cpp_mirror_example(tmp_path):
+    """The compiled host layer (cpp/lambda_blas.hpp over the C ABI) runs the reference's README example."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "lb_example")
+    lib = os.path.join(root, "lambda_blas_b200")
+    subprocess.run(["g++", "-std=c++17", os.path.join(root, "cpp", "example.cpp"), "-o", exe, "-L" + lib, "-llbk",
+                    "-Wl,-rpath," + lib], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sdot = 32" in r.stdout and r.stdout.strip().endswith("OK")
