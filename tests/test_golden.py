@@ -105,9 +105,11 @@ def test_cuda_path_matches_golden(blas, ctx):
         mx, my = blas.srotm(flags, n, ctx.to_device(x), ix, ctx.to_device(y), iy)
         assert same(mx.to_host(), f32(want["srotm"][0])) and same(my.to_host(), f32(want["srotm"][1])), ("srotm",) + tag
         if not finite:
-            continue        # reductions over Inf/NaN: covered by test_nonfinite_reductions (NaN-ness, not bits)
+            continue        # reductions over Inf/NaN inputs: order-dependent (Inf - Inf), outside the reference's domain
         if n > 0:
             prod = np.sum(np.abs(sample(x, n, ix) * sample(y, n, iy)))
+            if prod > 1e37 or np.sum(sample(x, n, ix) ** 2) > 1e37:
+                continue    # partial sums may overflow in one summation order and not in another
             assert abs(float(outs["sdot"]) - float(f32(want["sdot"])[0])) <= 2 * n * EPS * prod, ("sdot",) + tag
             w = float(f32(want["sdsdot"])[0])
             assert abs(float(outs["sdsdot"]) - w) <= float(np.spacing(np.float32(abs(w)))), ("sdsdot",) + tag

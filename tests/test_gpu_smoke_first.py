@@ -71,7 +71,7 @@ def test_pdl_overlap_is_invisible(blas, ctx, oracle):
     outs = {}
     for pdl in (False, True):
         ctx.set_pdl(pdl)
-        x, y, r = ctx.to_device(hx), ctx.to_device(hy), ctx.alloc(16)
+        x, y, r = ctx.to_device(hx), ctx.to_device(hy), ctx.alloc(16).fill(0.0)
         before = ctx.pdl_count()
         for it in range(6):
             ip.sdot_async(n - 1, x.view(1, n - 1), 1, y.view(1, n - 1), 1, r.view(0, 2))
