@@ -182,7 +182,10 @@ struct Rotm1F {      // Single.hs:481-482   h11*x + y ; -x + h22*y
 // vector body so that xr+head (and yr/xw/yw+head: checked by the host) are VEC*4-byte aligned; they
 // and the < VEC tail are handled by the first threads of block 0.
 // ------------------------------------------------------------------------------------------------
-template <class F, int VEC, int UNROLL, int POLICY>
+//
+// REV: the (incx, incy) = (1,-1) / (-1,1) pairing -- logical element i is x[i] and y[n-1-i] -- still moves
+// whole aligned packs: the y pack for x[e..e+VEC) is y[n-e-VEC..n-e) with its lanes in reverse order.
+template <class F, int VEC, int UNROLL, int POLICY, bool REV = false>
 __global__ void __launch_bounds__(kMaxThreads)
 map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64 head, i64 n)
 {
@@ -190,8 +193,12 @@ map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64
     const i64 npack = body / VEC;
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
-    const float *bxr = xr + head, *byr = yr + head;
-    float *bxw = xw + head, *byw = yw + head;
+    const float *bxr = xr + head;
+    float *bxw = xw + head;
+    // y side: forward from y+head, or backward from one past the body's last y element
+    const float *byr = REV ? yr + (n - head) - VEC : yr + head;
+    float *byw = REV ? yw + (n - head) - VEC : yw + head;
+    constexpr int YS = REV ? -1 : 1;
 
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const i64 p0 = tile * per_tile + threadIdx.x;
@@ -201,18 +208,18 @@ map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64
             for (int u = 0; u < UNROLL; ++u) {
                 const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
                 if constexpr (F::RX) load_pack<VEC, POLICY, !F::WX>(xv[u], bxr + e);
-                if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + e);
+                if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + YS * e);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-                for (int l = 0; l < VEC; ++l) f(xv[u].v[l], yv[u].v[l]);
+                for (int l = 0; l < VEC; ++l) f(xv[u].v[l], yv[u].v[REV ? VEC - 1 - l : l]);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
                 if constexpr (F::WX) store_pack<VEC, POLICY>(bxw + e, xv[u]);
-                if constexpr (F::WY) store_pack<VEC, POLICY>(byw + e, yv[u]);
+                if constexpr (F::WY) store_pack<VEC, POLICY>(byw + YS * e, yv[u]);
             }
         } else {
 #pragma unroll
@@ -221,11 +228,11 @@ map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64
                 if (p < npack) {
                     const i64 e = p * VEC;
                     if constexpr (F::RX) load_pack<VEC, POLICY, !F::WX>(xv[u], bxr + e);
-                    if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + e);
+                    if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + YS * e);
 #pragma unroll
-                    for (int l = 0; l < VEC; ++l) f(xv[u].v[l], yv[u].v[l]);
+                    for (int l = 0; l < VEC; ++l) f(xv[u].v[l], yv[u].v[REV ? VEC - 1 - l : l]);
                     if constexpr (F::WX) store_pack<VEC, POLICY>(bxw + e, xv[u]);
-                    if constexpr (F::WY) store_pack<VEC, POLICY>(byw + e, yv[u]);
+                    if constexpr (F::WY) store_pack<VEC, POLICY>(byw + YS * e, yv[u]);
                 }
             }
         }
@@ -236,12 +243,13 @@ map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64
         const i64 nscalar = head + (n - tail0);
         for (i64 t = threadIdx.x; t < nscalar; t += blockDim.x) {
             const i64 e = t < head ? t : tail0 + (t - head);
+            const i64 ey = REV ? n - 1 - e : e;
             float xs = 0.f, ys = 0.f;
             if constexpr (F::RX) xs = xr[e];
-            if constexpr (F::RY) ys = yr[e];
+            if constexpr (F::RY) ys = yr[ey];
             f(xs, ys);
             if constexpr (F::WX) xw[e] = xs;
-            if constexpr (F::WY) yw[e] = ys;
+            if constexpr (F::WY) yw[ey] = ys;
         }
     }
     pdl_wait();     // as a PDL secondary: do not retire before the preceding reduction has
@@ -254,20 +262,42 @@ map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64
 // element 0 as the read pointer and sets *_last_only, so that only logical element n-1 (the last
 // write of the reference's sequential scatter) stores.
 // ------------------------------------------------------------------------------------------------
+constexpr int kStridedUnroll = 4;   // independent 4-byte accesses in flight per operand per thread
+
 template <class F>
 __global__ void __launch_bounds__(256)
 map_strided_kernel(F f, const float *xr, float *xw, i64 incx_r, i64 incx_w, i64 kx0_r, i64 kx0_w,
                    const float *yr, float *yw, i64 incy_r, i64 incy_w, i64 ky0_r, i64 ky0_w,
                    i64 i_begin, i64 n, int x_last_only, int y_last_only)
 {
-    const i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 i = i_begin + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float xs = 0.f, ys = 0.f;
-        if constexpr (F::RX) xs = xr[kx0_r + i * incx_r];
-        if constexpr (F::RY) ys = yr[ky0_r + i * incy_r];
-        f(xs, ys);
-        if constexpr (F::WX) { if (!x_last_only || i == n - 1) xw[kx0_w + i * incx_w] = xs; }
-        if constexpr (F::WY) { if (!y_last_only || i == n - 1) yw[ky0_w + i * incy_w] = ys; }
+    constexpr int U = kStridedUnroll;
+    const i64 per_tile = (i64)U * blockDim.x;
+    const i64 count = n - i_begin;
+    const i64 ntiles = (count + per_tile - 1) / per_tile;
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const i64 i0 = i_begin + tile * per_tile + threadIdx.x;
+        float xs[U], ys[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {            // all loads first: U independent requests per operand
+            const i64 i = i0 + (i64)u * blockDim.x;
+            xs[u] = 0.f; ys[u] = 0.f;
+            if (i < n) {      // asm volatile loads: issued here, all U before the first use
+                Pack<1> p;
+                if constexpr (F::RX) { load_pack<1, 0, !F::WX>(p, xr + kx0_r + i * incx_r); xs[u] = p.v[0]; }
+                if constexpr (F::RY) { load_pack<1, 0, !F::WY>(p, yr + ky0_r + i * incy_r); ys[u] = p.v[0]; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) asm volatile("" : "+f"(xs[u]), "+f"(ys[u]));   // keep the U loads ahead of the first use
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const i64 i = i0 + (i64)u * blockDim.x;
+            if (i < n) {
+                f(xs[u], ys[u]);
+                if constexpr (F::WX) { if (!x_last_only || i == n - 1) xw[kx0_w + i * incx_w] = xs[u]; }
+                if constexpr (F::WY) { if (!y_last_only || i == n - 1) yw[ky0_w + i * incy_w] = ys[u]; }
+            }
+        }
     }
 }
 
@@ -598,28 +628,29 @@ __device__ __forceinline__ void grid_finish(Record r, Record *partials, unsigned
     }
 }
 
-template <class Op, int VEC>
+template <class Op, int VEC, bool REV = false>
 __device__ __forceinline__ void pack_step(typename Op::Acc &acc, const Pack<VEC> &x, const Pack<VEC> &y, unsigned ord0)
 {
     if constexpr (Op::HAS_PACK_STEP) Op::template step_pack<VEC>(acc, x, y, ord0);
     else {
 #pragma unroll
-        for (int l = 0; l < VEC; ++l) Op::step(acc, x.v[l], Op::TWO ? y.v[l] : 0.f, ord0 + l);
+        for (int l = 0; l < VEC; ++l) Op::step(acc, x.v[l], Op::TWO ? y.v[REV ? VEC - 1 - l : l] : 0.f, ord0 + l);
     }
 }
 
 // reduce, unit stride.  idx_base = global logical index of element 0 of this shard (isamax).
-template <class Op, int VEC, int UNROLL, int POLICY>
+template <class Op, int VEC, int UNROLL, int POLICY, bool REV = false>
 __global__ void __launch_bounds__(kMaxThreads)
 reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base,
                    Record *partials, unsigned *ticket, FinishArgs fa)
 {
+    constexpr int YS = REV ? -1 : 1;     // REV: element i pairs x[i] with y[n-1-i] (see map_unit_kernel)
     __shared__ Record smem[32];
     const i64 body = n - head;
     const i64 npack = body / VEC;
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
-    const float *bx = x + head, *by = y + head;
+    const float *bx = x + head, *by = REV ? y + (n - head) - VEC : y + head;
     const float x0 = fa.x0 != nullptr ? *fa.x0 : 0.f;   // read now: a PDL secondary may overwrite x later
 
     typename Op::Acc acc = Op::zero();
@@ -632,10 +663,10 @@ reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base
             for (int u = 0; u < UNROLL; ++u) {
                 const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
                 load_pack<VEC, POLICY, true>(xv[u], bx + e);
-                if constexpr (Op::TWO) load_pack<VEC, POLICY, true>(yv[u], by + e);
+                if constexpr (Op::TWO) load_pack<VEC, POLICY, true>(yv[u], by + YS * e);
             }
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) pack_step<Op, VEC>(acc, xv[u], yv[u], it * (UNROLL * VEC) + u * VEC);
+            for (int u = 0; u < UNROLL; ++u) pack_step<Op, VEC, REV>(acc, xv[u], yv[u], it * (UNROLL * VEC) + u * VEC);
         } else {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -643,8 +674,8 @@ reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base
                 if (p < npack) {
                     const i64 e = p * VEC;
                     load_pack<VEC, POLICY, true>(xv[u], bx + e);
-                    if constexpr (Op::TWO) load_pack<VEC, POLICY, true>(yv[u], by + e);
-                    pack_step<Op, VEC>(acc, xv[u], yv[u], it * (UNROLL * VEC) + u * VEC);
+                    if constexpr (Op::TWO) load_pack<VEC, POLICY, true>(yv[u], by + YS * e);
+                    pack_step<Op, VEC, REV>(acc, xv[u], yv[u], it * (UNROLL * VEC) + u * VEC);
                 }
             }
         }
@@ -655,7 +686,7 @@ reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base
         const i64 nscalar = head + (n - tail0);
         for (i64 t = threadIdx.x; t < nscalar; t += blockDim.x) {
             const i64 e = t < head ? t : tail0 + (t - head);
-            Op::single(r, x[e], Op::TWO ? y[e] : 0.f, idx_base + e);
+            Op::single(r, x[e], Op::TWO ? y[REV ? n - 1 - e : e] : 0.f, idx_base + e);
         }
     }
     pdl_launch_dependents();    // every load of this block has been issued and consumed
@@ -686,9 +717,12 @@ reduce_strided_kernel(const float *x, i64 incx, i64 kx0, const float *y, i64 inc
     __shared__ Record smem[32];
     const float x0 = fa.x0 != nullptr ? *fa.x0 : 0.f;
     Record r = empty_record<Op>();
+    // a plain grid-stride loop: the compiler unrolls it four times with the loads hoisted, which measured
+    // faster than explicit tiling (ptxas interleaves predicated tile loads with their uses)
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         Op::single(r, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : 0.f, idx_base + i);
+    pdl_launch_dependents();
     grid_finish<Op>(r, partials, ticket, fa, smem, x0);
 }
 

@@ -33,7 +33,7 @@ static_assert(sizeof(lbk_record) == sizeof(Record), "host and device records sha
     X(0, 4, 4, 1) X(1, 4, 2, 1) X(2, 4, 8, 1) X(3, 8, 2, 1) X(4, 8, 4, 1) X(5, 4, 4, 0) \
     X(6, 8, 1, 1) X(7, 4, 1, 1) X(8, 1, 4, 1) X(9, 8, 2, 0) X(10, 8, 8, 1) \
     X(11, 8, 4, 2) X(12, 8, 4, 3) X(13, 8, 4, 4) X(14, 8, 4, 5)
-static const int kVariantVec[] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8, 8, 8, 8, 8};
+static const int kVariantVec[16] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8, 8, 8, 8, 8, 4};
 constexpr int kNumVariants = 15;
 constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
@@ -658,6 +658,13 @@ static const void *map_kernel_ptr(int variant)
     }
     return nullptr;
 }
+// the reversed pairing is built for two shapes only: (VEC 4, UNROLL 4) and the any-alignment scalar one
+template <class F>
+static const void *map_kernel_ptr_rev(int variant)
+{
+    return variant == kScalarVariant ? (const void *)lbk::map_unit_kernel<F, 1, 4, 1, true>
+                                     : (const void *)lbk::map_unit_kernel<F, 4, 4, 1, true>;
+}
 static int variant_unroll(int variant)
 {
     switch (variant) {
@@ -703,20 +710,44 @@ static int launch_stream_kernel(lbk_ctx *c, const void *k, int grid, int threads
     return LBK_OK;
 }
 
+// Reversed pairing: x+head and (y+n)-head must both be pack aligned; otherwise the scalar shape is used.
+static void resolve_alignment_rev(int *variant, i64 *head, const float *const *xptrs, int nx, const float *const *yptrs, int ny, i64 n)
+{
+    const int vec = 4;
+    const int m = misalign(xptrs[0], vec);
+    const i64 h = (vec - m) % vec;          // x + h is aligned; y + n - h must be too  <=>  misalign(y + n) == h
+    bool ok = h <= n;
+    for (int i = 0; i < nx; ++i) ok = ok && misalign(xptrs[i], vec) == m;
+    for (int i = 0; i < ny; ++i) ok = ok && misalign(yptrs[i] + n, vec) == (int)h;
+    if (ok) { *variant = kVec4Fallback; *head = h; }      // (VEC 4, UNROLL 4)
+    else { *variant = kScalarVariant; *head = 0; }
+}
+
 template <class F>
-static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const float *xr, const float *yr, float *xw, float *yw, i64 n, int default_variant)
+static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const float *xr, const float *yr, float *xw, float *yw, i64 n, int default_variant, bool rev = false)
 {
     const LaunchCfg &cfg = c->cfg[rid];
     int variant = cfg.variant >= 0 ? cfg.variant : default_variant;
     const int threads = cfg.threads > 0 ? cfg.threads : 256;
-    const float *ptrs[4]; int np = 0;
-    if (F::RX) ptrs[np++] = xr;
-    if (F::RY) ptrs[np++] = yr;
-    if (F::WX) ptrs[np++] = xw;
-    if (F::WY) ptrs[np++] = yw;
     i64 head = 0;
-    resolve_alignment(&variant, &head, ptrs, np, n);
-    const void *k = map_kernel_ptr<F>(variant);
+    const void *k;
+    if (rev) {
+        const float *xp[2], *yp[2]; int nx = 0, ny = 0;
+        if (F::RX) xp[nx++] = xr;
+        if (F::WX) xp[nx++] = xw;
+        if (F::RY) yp[ny++] = yr;
+        if (F::WY) yp[ny++] = yw;
+        resolve_alignment_rev(&variant, &head, xp, nx, yp, ny, n);
+        k = map_kernel_ptr_rev<F>(variant);
+    } else {
+        const float *ptrs[4]; int np = 0;
+        if (F::RX) ptrs[np++] = xr;
+        if (F::RY) ptrs[np++] = yr;
+        if (F::WX) ptrs[np++] = xw;
+        if (F::WY) ptrs[np++] = yw;
+        resolve_alignment(&variant, &head, ptrs, np, n);
+        k = map_kernel_ptr<F>(variant);
+    }
     const i64 npack = (n - head) / kVariantVec[variant];
     const i64 per_tile = (i64)variant_unroll(variant) * threads;
     int grid;
@@ -735,7 +766,7 @@ static int launch_map_strided(lbk_ctx *c, const F &f, const float *xr, float *xw
                               i64 i_begin, i64 n, int x_last, int y_last)
 {
     const int threads = 256;
-    const int grid = stream_grid(c, n - i_begin, threads);
+    const int grid = stream_grid(c, (n - i_begin + lbk::kStridedUnroll - 1) / lbk::kStridedUnroll, threads);
     c->tail_open = false;
     lbk::map_strided_kernel<F><<<grid, threads, 0, c->stream>>>(f, xr, xw, incx_r, incx_w, kx0_r, kx0_w,
                                                                  yr, yw, incy_r, incy_w, ky0_r, ky0_w, i_begin, n, x_last, y_last);
@@ -762,6 +793,9 @@ static int map_dispatch(lbk_ctx *c, int rid, const F &f, i64 n,
     const bool unit = (incx == 1 && incy == 1) || (use_x && use_y && incx == -1 && incy == -1) ||
                       (!use_y && incx == 1) || (!use_x && incy == 1);
     if (unit) return launch_map_unit<F>(c, rid, f, xr, yr, xw, yw, nl, default_variant);
+    // (1,-1) and (-1,1) pair x[k] with y[n-1-k]: the same set of pairs, handled by the reversed-lane unit kernel
+    if (use_x && use_y && ((incx == 1 && incy == -1) || (incx == -1 && incy == 1)))
+        return launch_map_unit<F>(c, rid, f, xr, yr, xw, yw, nl, default_variant, true);
 
     i64 kx0 = first_index(nl, incx), ky0 = first_index(nl, incy);
     i64 incx_r = incx, incx_w = incx, incy_r = incy, incy_w = incy, kx0_r = kx0, ky0_r = ky0;
@@ -872,15 +906,23 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
     fa.rec_out = c->rec_send;
     fa.x0 = (X.i0 == 0 && nl > 0) ? x : nullptr;     // logical element 0 lives at x[0] for incx >= 1
     const i64 idx_base = X.i0;
-    const bool unit = nl > 0 && ((incx == 1 && (!Y || incy == 1)) || (Y && incx == -1 && incy == -1));
+    const bool rev = nl > 0 && Y && ((incx == 1 && incy == -1) || (incx == -1 && incy == 1));
+    const bool unit = nl > 0 && ((incx == 1 && (!Y || incy == 1)) || (Y && incx == -1 && incy == -1) || rev);
     if (unit) {
         const LaunchCfg &cfg = c->cfg[rid];
         int variant = cfg.variant >= 0 ? cfg.variant : default_variant;
         const int threads = cfg.threads > 0 ? cfg.threads : 256;
         const float *ptrs[2] = {x, y};
         i64 head = 0;
-        resolve_alignment(&variant, &head, ptrs, Y ? 2 : 1, nl);
-        const void *k = reduce_kernel_ptr<Op>(variant);
+        const void *k;
+        if (rev) {
+            resolve_alignment_rev(&variant, &head, &x, 1, &y, 1, nl);
+            k = variant == kScalarVariant ? (const void *)lbk::reduce_unit_kernel<Op, 1, 4, 1, true>
+                                          : (const void *)lbk::reduce_unit_kernel<Op, 4, 4, 1, true>;
+        } else {
+            resolve_alignment(&variant, &head, ptrs, Y ? 2 : 1, nl);
+            k = reduce_kernel_ptr<Op>(variant);
+        }
         const i64 npack = (nl - head) / kVariantVec[variant];
         const i64 per_tile = (i64)variant_unroll(variant) * threads;
         int grid;

@@ -101,3 +101,28 @@ def test_cpp_mirror_example(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "sdot = 32" in r.stdout and r.stdout.strip().endswith("OK")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 64, 1001, 4100, (1 << 20) + 1, (1 << 20) + 2])
+@pytest.mark.parametrize("offs", [(0, 0), (1, 0), (0, 3), (2, 1), (3, 3)])
+def test_reversed_pairing_paths(blas, ctx, oracle, n, offs):
+    """(incx,incy) = (1,-1) and (-1,1): the reversed-lane vector path and its scalar fallback, all alignments."""
+    ox, oy = offs
+    rng = np.random.default_rng(n + 7 * ox + 31 * oy)
+    u, v = gen_unit(rng, n + ox), gen_unit(rng, n + oy)
+    du, dv = ctx.to_device(u).view(ox, n), ctx.to_device(v).view(oy, n)
+    hu, hv = u[ox:], v[oy:]
+    for incx, incy in ((1, -1), (-1, 1)):
+        want = oracle.sdot(n, hu, incx, hv, incy)
+        assert abs(float(blas.sdot(n, du, incx, dv, incy)) - float(want)) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(hu.astype(np.float64) * hv[::-1])))
+        assert abs(float(blas.sdsdot(n, 0.5, du, incx, dv, incy)) - float(oracle.sdsdot(n, 0.5, hu, incx, hv, incy))) <= float(np.spacing(np.float32(abs(oracle.sdsdot(n, 0.5, hu, incx, hv, incy)))))
+        P.assert_same(blas.saxpy(n, 0.75, du, incx, dv, incy).to_host(), oracle.saxpy(n, 0.75, hu, incx, hv, incy))
+        P.assert_same(blas.scopy(n, du, incx, dv, incy).to_host(), oracle.scopy(n, hu, incx, hv, incy))
+        for got, wnt in zip(blas.sswap(n, du, incx, dv, incy), oracle.sswap(n, hu, incx, hv, incy)):
+            P.assert_same(got.to_host(), wnt)
+        for got, wnt in zip(blas.srot(n, du, incx, dv, incy, 0.6, 0.8), oracle.srot(n, hu, incx, hv, incy, 0.6, 0.8)):
+            P.assert_same(got.to_host(), wnt)
+        for args in ((1.5, 0.75, 2.0, 0.5), (1.0, 2.0, 0.5, 3.0), (1e-9, 1.0, 1.0, 1.0)):
+            fl, ofl = blas.srotmg(*args), oracle.srotmg(*args)
+            for got, wnt in zip(blas.srotm(fl, n, du, incx, dv, incy), oracle.srotm(ofl, n, hu, incx, hv, incy)):
+                P.assert_same(got.to_host(), wnt)

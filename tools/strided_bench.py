@@ -1,0 +1,35 @@
+"""BASELINE.json config 4: sdot / saxpy / srot with incx, incy in {1,2,7,-1} at n = 2^26.
+Reports algorithmic GB/s (4 bytes per touched element per access; sector over-fetch is not credited)."""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lambda_blas_b200 as lb  # noqa: E402
+from lambda_blas_b200 import inplace as ip  # noqa: E402
+
+n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 26)
+incs = [1, 2, 7, -1]
+ctx = lb.Context(0)
+span = 1 + (n - 1) * 7
+x, y, out = ctx.alloc(span).fill_hash(1), ctx.alloc(span).fill_hash(2), ctx.alloc(4)
+c, s = math.cos(0.3), math.sin(0.3)
+B = {"sdot": 8, "saxpy": 12, "srot": 16}
+print("routine,incx,incy,us,GBps_algorithmic")
+for r in ("sdot", "saxpy", "srot"):
+    for incx in incs:
+        for incy in incs:
+            f = {"sdot": lambda: ip.sdot_async(n, x, incx, y, incy, out),
+                 "saxpy": lambda: ip.saxpy_(n, 1.0, x, incx, y, incy),
+                 "srot": lambda: ip.srot_(n, x, incx, y, incy, c, s)}[r]
+            for _ in range(3):
+                f()
+            e0 = ctx.event().record()
+            for _ in range(10):
+                f()
+            e1 = ctx.event().record()
+            us = e0.elapsed_ms(e1) * 100
+            print(f"{r},{incx},{incy},{us:.1f},{B[r] * n / us / 1e3:.1f}", flush=True)
+            if r != "sdot":
+                x.fill_hash(1); y.fill_hash(2)
+ctx.close()
