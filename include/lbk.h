@@ -122,6 +122,9 @@ int lbk_host_free(float *host);
 int lbk_event_create(lbk_ctx *ctx, lbk_event **ev);
 int lbk_event_record(lbk_event *ev);
 int lbk_event_elapsed_ms(lbk_event *start, lbk_event *stop, float *ms); /* synchronises on `stop` */
+/* Everything enqueued on `ctx` after this call waits for `ev` (recorded on ANOTHER context of the same device):
+ * lets a second context's stream download results while the first keeps uploading and computing. */
+int lbk_wait_event(lbk_ctx *ctx, lbk_event *ev);
 int lbk_event_destroy(lbk_event *ev);
 
 /* ---- reductions ------------------------------------------------------------------------------ */

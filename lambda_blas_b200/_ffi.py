@@ -69,6 +69,7 @@ PROTOTYPES = {
     "lbk_event_create": (_int, [_vp, _pvp]),
     "lbk_event_record": (_int, [_vp]),
     "lbk_event_elapsed_ms": (_int, [_vp, _vp, _pf32]),
+    "lbk_wait_event": (_int, [_vp, _vp]),
     "lbk_event_destroy": (_int, [_vp]),
     "lbk_sdot": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pf32]),
     "lbk_sdsdot": (_int, [_vp, _i64, _f32, _vp, _i64, _vp, _i64, _pf32]),

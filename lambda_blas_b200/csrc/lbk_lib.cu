@@ -572,6 +572,13 @@ extern "C" int lbk_event_record(lbk_event *e)
     CU(e->ctx, cudaEventRecord(e->ev, e->ctx->stream));
     return LBK_OK;
 }
+extern "C" int lbk_wait_event(lbk_ctx *c, lbk_event *e)
+{
+    if (!c || !e) return fail(c, LBK_ERR_ARG, "lbk_wait_event: null argument");
+    c->tail_open = false;
+    CU(c, cudaStreamWaitEvent(c->stream, e->ev, 0));
+    return LBK_OK;
+}
 extern "C" int lbk_event_elapsed_ms(lbk_event *a, lbk_event *b, float *ms)
 {
     if (!a || !b || !ms) return fail(nullptr, LBK_ERR_ARG, "lbk_event_elapsed_ms: null argument");

@@ -56,3 +56,8 @@ def snrm2_async(n: int, x: DVector, incx: int, out: DVector) -> None:
 
 def isamax_async(n: int, x: DVector, incx: int, out: DVector) -> None:
     _ffi.check(_L().lbk_isamax_async(x.ctx.handle, n, x.handle, incx, out.handle), x.ctx.handle)
+
+
+def saxpy_into(n: int, a, x: DVector, incx: int, y: DVector, incy: int, yout: DVector) -> None:
+    """yout = the reference's pure saxpy result (y untouched), enqueue only: lbk_saxpy_oop."""
+    _ffi.check(_L().lbk_saxpy_oop(x.ctx.handle, n, float(np.float32(a)), x.handle, incx, y.handle, incy, yout.handle), x.ctx.handle)

@@ -121,6 +121,10 @@ class Context:
     def event(self) -> "Event":
         return Event(self)
 
+    def wait_event(self, ev: "Event") -> None:
+        """Work enqueued on this context from now on waits for `ev` (recorded on another context's stream)."""
+        _ffi.check(_ffi.lib().lbk_wait_event(self.handle, ev._h), self.handle)
+
     def __enter__(self):
         return self
 

@@ -126,3 +126,43 @@ def test_reversed_pairing_paths(blas, ctx, oracle, n, offs):
             fl, ofl = blas.srotmg(*args), oracle.srotmg(*args)
             for got, wnt in zip(blas.srotm(fl, n, du, incx, dv, incy), oracle.srotm(ofl, n, hu, incx, hv, incy)):
                 P.assert_same(got.to_host(), wnt)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 33, 1000, 65537])
+@pytest.mark.parametrize("incs", [(1, 1), (-1, -1), (1, -1), (-1, 1), (2, 3), (-3, 1), (0, 1), (1, 0)])
+def test_guard_bands_stay_untouched(blas, ctx, oracle, n, incs):
+    """compute-sanitizer is closed on this pool, so out-of-bounds WRITES are looked for directly: every in-place
+    routine works on a window in the middle of a larger buffer of sentinels, and the sentinels must survive."""
+    from lambda_blas_b200 import inplace as ip
+    incx, incy = incs
+    G = 37                                              # odd guard: the window is misaligned on purpose
+    lx, ly = 1 + (n - 1) * abs(incx), 1 + (n - 1) * abs(incy)
+    rng = np.random.default_rng(n * 131 + incx * 7 + incy)
+    sent = np.float32(-12345.678)
+
+    def fresh():
+        bx, by = np.full(lx + 2 * G, sent, np.float32), np.full(ly + 2 * G, sent, np.float32)
+        bx[G:G + lx] = gen_unit(rng, lx); by[G:G + ly] = gen_unit(rng, ly)
+        dx, dy = ctx.to_device(bx), ctx.to_device(by)
+        return bx, by, dx, dy, dx.view(G, lx), dy.view(G, ly)
+
+    fl, ofl = blas.srotmg(1.0, 2.0, 0.5, 3.0), oracle.srotmg(1.0, 2.0, 0.5, 3.0)
+    ops = [
+        ("saxpy", lambda x, y: ip.saxpy_(n, 0.5, x, incx, y, incy), lambda hx, hy: (hx, oracle.saxpy(n, 0.5, hx, incx, hy, incy))),
+        ("scopy", lambda x, y: ip.scopy_(n, x, incx, y, incy), lambda hx, hy: (hx, oracle.scopy(n, hx, incx, hy, incy))),
+        ("sswap", lambda x, y: ip.sswap_(n, x, incx, y, incy), lambda hx, hy: oracle.sswap(n, hx, incx, hy, incy)),
+        ("srot", lambda x, y: ip.srot_(n, x, incx, y, incy, 0.6, 0.8), lambda hx, hy: oracle.srot(n, hx, incx, hy, incy, 0.6, 0.8)),
+        ("srotm", lambda x, y: ip.srotm_(fl, n, x, incx, y, incy), lambda hx, hy: oracle.srotm(ofl, n, hx, incx, hy, incy)),
+    ]
+    if incx > 0:
+        ops.append(("sscal", lambda x, y: ip.sscal_(n, 1.5, x, incx), lambda hx, hy: (oracle.sscal(n, 1.5, hx, incx), hy)))
+    for name, run, ref in ops:
+        if (incx == 0 or incy == 0) and name in ("sswap", "srot", "srotm", "saxpy") and incy == 0 and name == "saxpy":
+            pass
+        bx, by, dx, dy, vx, vy = fresh()
+        run(vx, vy)
+        wx, wy = ref(bx[G:G + lx], by[G:G + ly])
+        gx, gy = dx.to_host(), dy.to_host()
+        assert np.all(gx[:G] == sent) and np.all(gx[G + lx:] == sent), (name, "x guard")
+        assert np.all(gy[:G] == sent) and np.all(gy[G + ly:] == sent), (name, "y guard")
+        P.assert_same(gx[G:G + lx], wx, name); P.assert_same(gy[G:G + ly], wy, name)
