@@ -100,10 +100,21 @@ PROTOTYPES = {
 _lib = None
 
 
+def _try_build() -> None:
+    """A checkout without the built library (it is git-ignored): compile it in tree if nvcc is here.
+    This is the build step of __graft_entry__.build(), not a fallback -- without nvcc the import fails."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") and shutil.which("make"):
+        subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-s"], check=False)
+
+
 def lib() -> C.CDLL:
     """Load liblbk.so (built by lambda_blas_b200/csrc/Makefile or __graft_entry__.build())."""
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            _try_build()
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `make -C lambda_blas_b200/csrc` (nvcc, sm_100a). "
