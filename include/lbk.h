@@ -97,26 +97,34 @@ int lbk_set_fused_exchange(lbk_ctx *ctx, int enabled);
 /* Block partition of [0, global_len) used by lbk_vec_alloc_sharded: rank r owns [lo, hi). */
 int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t *lo, int64_t *hi);
 
-/* ---- device vectors (the representation added beside Numerical.BLAS.Types, Types.hs:3) ----- */
+/* ---- device vectors (the representation added beside Numerical.BLAS.Types, Types.hs:3) -----
+ * The reference's routines are polymorphic with Float and Double instances (sdot/ddot, ..., Single.hs:83-87);
+ * a device vector is single precision unless made by an *_f64 constructor.  The s* routines take single-,
+ * the d* routines double-precision vectors (LBK_ERR_ARG otherwise).  Lengths are in ELEMENTS. */
 int lbk_vec_alloc(lbk_ctx *ctx, int64_t len, lbk_vec **v);
+int lbk_vec_alloc_f64(lbk_ctx *ctx, int64_t len, lbk_vec **v);
 int lbk_vec_alloc_sharded(lbk_ctx *ctx, int64_t global_len, lbk_vec **v);
-int lbk_vec_wrap(lbk_ctx *ctx, void *device_ptr, int64_t len, lbk_vec **v); /* non-owning */
+int lbk_vec_alloc_sharded_f64(lbk_ctx *ctx, int64_t global_len, lbk_vec **v);
+int lbk_vec_wrap(lbk_ctx *ctx, void *device_ptr, int64_t len, lbk_vec **v);     /* non-owning */
+int lbk_vec_wrap_f64(lbk_ctx *ctx, void *device_ptr, int64_t len, lbk_vec **v);
 int lbk_vec_view(const lbk_vec *v, int64_t offset, int64_t len, lbk_vec **view); /* non-owning */
 int lbk_vec_free(lbk_vec *v);
 int lbk_vec_len(const lbk_vec *v, int64_t *local_len, int64_t *global_len, int64_t *shard_offset);
+int lbk_vec_elem_size(const lbk_vec *v);                                        /* 4 or 8 */
 void *lbk_vec_ptr(const lbk_vec *v);
-int lbk_vec_upload(lbk_vec *v, const float *host, int64_t len);        /* host -> device, synchronous */
-int lbk_vec_download(const lbk_vec *v, float *host, int64_t len);      /* device -> host, synchronous */
-int lbk_vec_upload_async(lbk_vec *v, const float *host, int64_t len);  /* enqueue only (pin the host buffer) */
-int lbk_vec_download_async(const lbk_vec *v, float *host, int64_t len);
+int lbk_vec_upload(lbk_vec *v, const void *host, int64_t len);        /* host -> device, synchronous */
+int lbk_vec_download(const lbk_vec *v, void *host, int64_t len);      /* device -> host, synchronous */
+int lbk_vec_upload_async(lbk_vec *v, const void *host, int64_t len);  /* enqueue only (pin the host buffer) */
+int lbk_vec_download_async(const lbk_vec *v, void *host, int64_t len);
 int lbk_vec_clone(const lbk_vec *v, lbk_vec **out);
 /* Synthetic data, generated on the device from a counter hash of (seed, GLOBAL index), so shards of
- * any world size hold the same logical vector: v[i] = lo + (hi-lo) * u24(splitmix64(seed, i)). */
-int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, float lo, float hi);
-int lbk_vec_fill(lbk_vec *v, float value);
+ * any world size hold the same logical vector: v[i] = lo + (hi-lo) * u24(splitmix64(seed, i)), computed in the
+ * vector's own precision. */
+int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, double lo, double hi);
+int lbk_vec_fill(lbk_vec *v, double value);
 /* Pinned host memory for the transfers above. */
-int lbk_host_alloc(int64_t nfloats, float **host);
-int lbk_host_free(float *host);
+int lbk_host_alloc(int64_t nbytes, void **host);
+int lbk_host_free(void *host);
 
 /* ---- timing on the context's stream ---------------------------------------------------------- */
 int lbk_event_create(lbk_ctx *ctx, lbk_event **ev);
@@ -128,70 +136,93 @@ int lbk_wait_event(lbk_ctx *ctx, lbk_event *ev);
 int lbk_event_destroy(lbk_event *ev);
 
 /* ---- reductions ------------------------------------------------------------------------------ */
-/* dot / sdot, Single.hs:73-87 (Fortran role: "sdot_", test/Foreign.hs:48): sum of x[kx(i)]*y[ky(i)],
- * kx(i) = first(n,incx) + i*incx, first(n,inc) = inc>0 ? 0 : (1-n)*inc (Single.hs:91-96);
+/* dot / sdot / ddot, Single.hs:73-87 (Fortran role: "sdot_"/"ddot_", test/Foreign.hs:48,50): sum of
+ * x[kx(i)]*y[ky(i)], kx(i) = first(n,incx) + i*incx, first(n,inc) = inc>0 ? 0 : (1-n)*inc (Single.hs:91-96);
  * inc == 0 replicates element 0 (Util.hs:86).  n <= 0 gives 0. */
 int lbk_sdot(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out);
+int lbk_ddot(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, double *out);
 /* sdsdot, Single.hs:231-262 ("sdsdot_", Foreign.hs:52): sb + sum in double, rounded once to float. */
 int lbk_sdsdot(lbk_ctx *ctx, int64_t n, float sb, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out);
-/* asum / sasum, Single.hs:155-168 ("sasum_", Foreign.hs:36): 0 when incx < 1. */
+/* asum / sasum / dasum, Single.hs:155-168 ("sasum_"/"dasum_", Foreign.hs:36,38): 0 when incx < 1. */
 int lbk_sasum(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, float *out);
-/* nrm2 / snrm2, Single.hs:174-204 ("snrm2_", Foreign.hs:54): 0 when n<1 or incx<1, |x[0]| when n==1;
- * overflow/underflow-safe scaled accumulation. */
+int lbk_dasum(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, double *out);
+/* nrm2 / snrm2 / dnrm2, Single.hs:174-204 ("snrm2_"/"dnrm2_", Foreign.hs:54,56): 0 when n<1 or incx<1,
+ * |x[0]| when n==1; overflow/underflow-safe scaled accumulation. */
 int lbk_snrm2(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, float *out);
-/* iamax / isamax, Single.hs:211-225 ("isamax_", Foreign.hs:32): 0-based LOGICAL index of the first
- * element of largest |x|; -1 when n<1 or incx<1; 0 when n==1.  Bit-exact, including ties and NaN
+int lbk_dnrm2(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, double *out);
+/* iamax / isamax / idamax, Single.hs:211-225 ("isamax_"/"idamax_", Foreign.hs:32,34): 0-based LOGICAL index
+ * of the first element of largest |x|; -1 when n<1 or incx<1; 0 when n==1.  Bit-exact, including ties and NaN
  * (a NaN wins only at logical index 0). */
 int lbk_isamax(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, int64_t *out);
-/* Enqueue-only forms: the result is written to out_dev[0] (isamax: the int64 into the 8 bytes of
- * out_dev[0..1]) on the stream; nothing is synchronised.  `out_dev` is a device vector. */
+int lbk_idamax(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, int64_t *out);
+/* Enqueue-only forms: the result is written to out_dev[0] (i?amax: the int64 into the first 8 bytes) on the
+ * stream; nothing is synchronised.  `out_dev` is a device vector of the routine's precision. */
 int lbk_sdot_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *out_dev);
 int lbk_sasum_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *out_dev);
 int lbk_snrm2_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *out_dev);
 int lbk_isamax_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *out_dev);
+int lbk_ddot_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *out_dev);
+int lbk_dasum_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *out_dev);
+int lbk_dnrm2_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *out_dev);
+int lbk_idamax_async(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *out_dev);
 
 /* ---- elementwise (in place, enqueue only) ------------------------------------------------------ */
-/* axpy / saxpy, Single.hs:430-444 ("saxpy_", Foreign.hs:40): y[ky(i)] += a*x[kx(i)], product rounded
+/* axpy, Single.hs:430-444 ("saxpy_"/"daxpy_", Foreign.hs:40,42): y[ky(i)] += a*x[kx(i)], product rounded
  * before the add, NO a==0 shortcut. */
 int lbk_saxpy(lbk_ctx *ctx, int64_t n, float a, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy);
-/* scal / sscal, Single.hs:101-116 ("sscal_", Foreign.hs:74): x[i*incx] *= a for incx >= 1; incx <= 0
+int lbk_daxpy(lbk_ctx *ctx, int64_t n, double a, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy);
+/* scal, Single.hs:101-116 ("sscal_"/"dscal_", Foreign.hs:74,76): x[i*incx] *= a for incx >= 1; incx <= 0
  * follows the reference's index stream (unchanged for n>1 and incx<0; x[0]*a once otherwise). */
 int lbk_sscal(lbk_ctx *ctx, int64_t n, float a, lbk_vec *x, int64_t incx);
-/* copy / scopy, Single.hs:119-132 ("scopy_", Foreign.hs:44): y[ky(i)] = x[kx(i)]; incy==0 leaves the
+int lbk_dscal(lbk_ctx *ctx, int64_t n, double a, lbk_vec *x, int64_t incx);
+/* copy, Single.hs:119-132 ("scopy_"/"dcopy_", Foreign.hs:44,46): y[ky(i)] = x[kx(i)]; incy==0 leaves the
  * LAST sampled x in y[0]. */
 int lbk_scopy(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy);
-/* swap / sswap, Single.hs:135-150 ("sswap_", Foreign.hs:78). */
+int lbk_dcopy(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy);
+/* swap, Single.hs:135-150 ("sswap_"/"dswap_", Foreign.hs:78,80). */
 int lbk_sswap(lbk_ctx *ctx, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy);
-/* rot / srot, Single.hs:408-424 ("srot_", Foreign.hs:58): x' = c*x + s*y, y' = c*y - s*x, both from
+int lbk_dswap(lbk_ctx *ctx, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy);
+/* rot, Single.hs:408-424 ("srot_"/"drot_", Foreign.hs:58,60): x' = c*x + s*y, y' = c*y - s*x, both from
  * the old values, each product rounded separately. */
 int lbk_srot(lbk_ctx *ctx, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, float c, float s);
-/* rotm / srotm, Single.hs:463-487 ("srotm_", Foreign.hs:66).  param is the BLAS sparam array
+int lbk_drot(lbk_ctx *ctx, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, double c, double s);
+/* rotm, Single.hs:463-487 ("srotm_"/"drotm_", Foreign.hs:66,68).  param is the BLAS sparam array
  * [flag,h11,h21,h12,h22] (Foreign.hs:276-280); flag -2 is a no-op that launches nothing. */
 int lbk_srotm(lbk_ctx *ctx, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, const float param[5]);
+int lbk_drotm(lbk_ctx *ctx, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, const double param[5]);
 
 /* ---- out-of-place forms: the reference's pure results in one pass ------------------------------- */
 /* yout (same length as y) = updateElems result of Util.hs:134-142: y with the touched slots replaced,
- * everything else copied.  yout must not overlap x or y. */
+ * everything else copied.  Outputs must not overlap the inputs. */
 int lbk_saxpy_oop(lbk_ctx *ctx, int64_t n, float a, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout);
 int lbk_sscal_oop(lbk_ctx *ctx, int64_t n, float a, const lbk_vec *x, int64_t incx, lbk_vec *xout);
 int lbk_scopy_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout);
 int lbk_sswap_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *xout, lbk_vec *yout);
 int lbk_srot_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float c, float s, lbk_vec *xout, lbk_vec *yout);
 int lbk_srotm_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, const float param[5], lbk_vec *xout, lbk_vec *yout);
+int lbk_daxpy_oop(lbk_ctx *ctx, int64_t n, double a, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout);
+int lbk_dscal_oop(lbk_ctx *ctx, int64_t n, double a, const lbk_vec *x, int64_t incx, lbk_vec *xout);
+int lbk_dcopy_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout);
+int lbk_dswap_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *xout, lbk_vec *yout);
+int lbk_drot_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, double c, double s, lbk_vec *xout, lbk_vec *yout);
+int lbk_drotm_oop(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, const double param[5], lbk_vec *xout, lbk_vec *yout);
 
 /* ---- host scalars (O(1); stay on the CPU like the reference's) ---------------------------------- */
-/* rotg / srotg, Single.hs:274-300 ("srotg_", Foreign.hs:62): out = (r, z, c, s) (Types.hs:8). */
+/* rotg, Single.hs:274-300 ("srotg_"/"drotg_", Foreign.hs:62,64): out = (r, z, c, s) (Types.hs:8). */
 int lbk_srotg(float sa, float sb, float out[4]);
-/* rotmg / srotmg + checkscale, Single.hs:318-401 ("srotmg_", Foreign.hs:70).
+int lbk_drotg(double sa, double sb, double out[4]);
+/* rotmg + checkscale, Single.hs:318-401 ("srotmg_"/"drotmg_", Foreign.hs:70,72).
  * out = [flag, d1, d2, x1, h11, h12, h21, h22], flag in {-2,-1,0,1} = FLAGNEG2/FLAGNEG1/FLAG0/FLAG1
- * (Types.hs:15-20); param (may be NULL) receives the BLAS sparam array for lbk_srotm. */
+ * (Types.hs:15-20); param (may be NULL) receives the BLAS sparam array for lbk_?rotm. */
 int lbk_srotmg(float sd1, float sd2, float sx1, float sy1, float out[8], float param[5]);
+int lbk_drotmg(double sd1, double sd2, double sx1, double sy1, double out[8], double param[5]);
 
 /* ---- host-side statement of the cross-rank combine (what the finish kernel computes) ------------- */
-/* One 32-byte record per rank, in rank order; used by the CPU tests of the multi-GPU path. */
-typedef struct lbk_record { float f[3]; uint32_t key; int64_t idx; int64_t pad; } lbk_record;
+/* One 48-byte record per rank, in rank order; used by the CPU tests of the multi-GPU path.  f[0..2] are
+ * partial sums held in double (float partials are exact in them); key/idx the i?amax candidate. */
+typedef struct lbk_record { double f[3]; uint64_t key; int64_t idx; int64_t pad; } lbk_record;
 enum lbk_reduce_kind { LBK_RED_SUM = 0, LBK_RED_NRM2 = 1, LBK_RED_IAMAX = 2 };
-int lbk_combine_records(int kind, const lbk_record *recs, int nranks, float *fout, int64_t *iout);
+int lbk_combine_records(int kind, int is_f64, const lbk_record *recs, int nranks, double *fout, int64_t *iout);
 
 #ifdef __cplusplus
 }

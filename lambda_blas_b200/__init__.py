@@ -15,7 +15,8 @@ _ffi.lib()          # fail loudly, at import, if the CUDA library is missing
 from .types import Context, DVector, Event, GivensRot, ModGivensRot, FLAGNEG2, hash_fill_reference, pinned_array  # noqa: E402
 from . import single, inplace  # noqa: E402
 from .single import (dot, sdsdot, asum, nrm2, iamax, scal, copy, swap, axpy, rot, rotm, rotg, rotmg,  # noqa: E402,F401
-                     sdot, sasum, snrm2, isamax, sscal, scopy, sswap, saxpy, srot, srotm, srotg, srotmg)
+                     sdot, sasum, snrm2, isamax, sscal, scopy, sswap, saxpy, srot, srotm, srotg, srotmg,
+                     ddot, dasum, dnrm2, idamax, dscal, dcopy, dswap, daxpy, drot, drotm, drotg, drotmg)
 from ._ffi import LbkError  # noqa: E402,F401
 
 __all__ = ["Context", "DVector", "Event", "GivensRot", "ModGivensRot", "FLAGNEG2", "LbkError", "single", "inplace",

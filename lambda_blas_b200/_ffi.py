@@ -23,12 +23,12 @@ class LbkError(RuntimeError):
 
 
 class Record(C.Structure):
-    """lbk_record: what one rank contributes to a sharded reduction."""
-    _fields_ = [("f", C.c_float * 3), ("key", C.c_uint32), ("idx", C.c_int64), ("pad", C.c_int64)]
+    """lbk_record: what one rank contributes to a sharded reduction (48 bytes)."""
+    _fields_ = [("f", C.c_double * 3), ("key", C.c_uint64), ("idx", C.c_int64), ("pad", C.c_int64)]
 
 
-_i64, _f32, _vp, _int = C.c_int64, C.c_float, C.c_void_p, C.c_int
-_pf32, _pi64, _pvp, _pint = C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int)
+_i64, _f32, _f64, _vp, _int = C.c_int64, C.c_float, C.c_double, C.c_void_p, C.c_int
+_pf32, _pf64, _pi64, _pvp, _pint = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int)
 
 # name -> (restype, argtypes); every symbol include/lbk.h declares
 PROTOTYPES = {
@@ -51,51 +51,61 @@ PROTOTYPES = {
     "lbk_set_fused_exchange": (_int, [_vp, _int]),
     "lbk_shard_range": (_int, [_i64, _int, _int, _pi64, _pi64]),
     "lbk_vec_alloc": (_int, [_vp, _i64, _pvp]),
+    "lbk_vec_alloc_f64": (_int, [_vp, _i64, _pvp]),
     "lbk_vec_alloc_sharded": (_int, [_vp, _i64, _pvp]),
+    "lbk_vec_alloc_sharded_f64": (_int, [_vp, _i64, _pvp]),
     "lbk_vec_wrap": (_int, [_vp, _vp, _i64, _pvp]),
+    "lbk_vec_wrap_f64": (_int, [_vp, _vp, _i64, _pvp]),
     "lbk_vec_view": (_int, [_vp, _i64, _i64, _pvp]),
     "lbk_vec_free": (_int, [_vp]),
     "lbk_vec_len": (_int, [_vp, _pi64, _pi64, _pi64]),
+    "lbk_vec_elem_size": (_int, [_vp]),
     "lbk_vec_ptr": (_vp, [_vp]),
     "lbk_vec_upload": (_int, [_vp, _vp, _i64]),
     "lbk_vec_download": (_int, [_vp, _vp, _i64]),
     "lbk_vec_upload_async": (_int, [_vp, _vp, _i64]),
     "lbk_vec_download_async": (_int, [_vp, _vp, _i64]),
     "lbk_vec_clone": (_int, [_vp, _pvp]),
-    "lbk_vec_fill_hash": (_int, [_vp, C.c_uint64, _f32, _f32]),
-    "lbk_vec_fill": (_int, [_vp, _f32]),
-    "lbk_host_alloc": (_int, [_i64, C.POINTER(_pf32)]),
-    "lbk_host_free": (_int, [_pf32]),
+    "lbk_vec_fill_hash": (_int, [_vp, C.c_uint64, _f64, _f64]),
+    "lbk_vec_fill": (_int, [_vp, _f64]),
+    "lbk_host_alloc": (_int, [_i64, _pvp]),
+    "lbk_host_free": (_int, [_vp]),
     "lbk_event_create": (_int, [_vp, _pvp]),
     "lbk_event_record": (_int, [_vp]),
     "lbk_event_elapsed_ms": (_int, [_vp, _vp, _pf32]),
     "lbk_wait_event": (_int, [_vp, _vp]),
     "lbk_event_destroy": (_int, [_vp]),
-    "lbk_sdot": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pf32]),
     "lbk_sdsdot": (_int, [_vp, _i64, _f32, _vp, _i64, _vp, _i64, _pf32]),
-    "lbk_sasum": (_int, [_vp, _i64, _vp, _i64, _pf32]),
-    "lbk_snrm2": (_int, [_vp, _i64, _vp, _i64, _pf32]),
-    "lbk_isamax": (_int, [_vp, _i64, _vp, _i64, _pi64]),
-    "lbk_sdot_async": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp]),
-    "lbk_sasum_async": (_int, [_vp, _i64, _vp, _i64, _vp]),
-    "lbk_snrm2_async": (_int, [_vp, _i64, _vp, _i64, _vp]),
-    "lbk_isamax_async": (_int, [_vp, _i64, _vp, _i64, _vp]),
-    "lbk_saxpy": (_int, [_vp, _i64, _f32, _vp, _i64, _vp, _i64]),
-    "lbk_sscal": (_int, [_vp, _i64, _f32, _vp, _i64]),
-    "lbk_scopy": (_int, [_vp, _i64, _vp, _i64, _vp, _i64]),
-    "lbk_sswap": (_int, [_vp, _i64, _vp, _i64, _vp, _i64]),
-    "lbk_srot": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _f32]),
-    "lbk_srotm": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pf32]),
-    "lbk_saxpy_oop": (_int, [_vp, _i64, _f32, _vp, _i64, _vp, _i64, _vp]),
-    "lbk_sscal_oop": (_int, [_vp, _i64, _f32, _vp, _i64, _vp]),
-    "lbk_scopy_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp]),
-    "lbk_sswap_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
-    "lbk_srot_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _f32, _f32, _vp, _vp]),
-    "lbk_srotm_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pf32, _vp, _vp]),
     "lbk_srotg": (_int, [_f32, _f32, _pf32]),
+    "lbk_drotg": (_int, [_f64, _f64, _pf64]),
     "lbk_srotmg": (_int, [_f32, _f32, _f32, _f32, _pf32, _pf32]),
-    "lbk_combine_records": (_int, [_int, C.POINTER(Record), _int, _pf32, _pi64]),
+    "lbk_drotmg": (_int, [_f64, _f64, _f64, _f64, _pf64, _pf64]),
+    "lbk_combine_records": (_int, [_int, _int, C.POINTER(Record), _int, _pf64, _pi64]),
 }
+# the Float and Double instances of every vector routine: same shapes, s/d prefix, float/double scalars
+for _p, _fx, _pfx, _ip in (("s", _f32, _pf32, "is"), ("d", _f64, _pf64, "id")):
+    PROTOTYPES.update({
+        f"lbk_{_p}dot": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pfx]),
+        f"lbk_{_p}asum": (_int, [_vp, _i64, _vp, _i64, _pfx]),
+        f"lbk_{_p}nrm2": (_int, [_vp, _i64, _vp, _i64, _pfx]),
+        f"lbk_{_ip}amax": (_int, [_vp, _i64, _vp, _i64, _pi64]),
+        f"lbk_{_p}dot_async": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+        f"lbk_{_p}asum_async": (_int, [_vp, _i64, _vp, _i64, _vp]),
+        f"lbk_{_p}nrm2_async": (_int, [_vp, _i64, _vp, _i64, _vp]),
+        f"lbk_{_ip}amax_async": (_int, [_vp, _i64, _vp, _i64, _vp]),
+        f"lbk_{_p}axpy": (_int, [_vp, _i64, _fx, _vp, _i64, _vp, _i64]),
+        f"lbk_{_p}scal": (_int, [_vp, _i64, _fx, _vp, _i64]),
+        f"lbk_{_p}copy": (_int, [_vp, _i64, _vp, _i64, _vp, _i64]),
+        f"lbk_{_p}swap": (_int, [_vp, _i64, _vp, _i64, _vp, _i64]),
+        f"lbk_{_p}rot": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _fx, _fx]),
+        f"lbk_{_p}rotm": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pfx]),
+        f"lbk_{_p}axpy_oop": (_int, [_vp, _i64, _fx, _vp, _i64, _vp, _i64, _vp]),
+        f"lbk_{_p}scal_oop": (_int, [_vp, _i64, _fx, _vp, _i64, _vp]),
+        f"lbk_{_p}copy_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+        f"lbk_{_p}swap_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
+        f"lbk_{_p}rot_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _fx, _fx, _vp, _vp]),
+        f"lbk_{_p}rotm_oop": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _pfx, _vp, _vp]),
+    })
 
 _lib = None
 

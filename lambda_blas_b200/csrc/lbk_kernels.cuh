@@ -5,15 +5,19 @@
 // two shapes, both bounded by HBM bandwidth (O(1) flop per 4..16 bytes, no data reuse, hence no
 // shared-memory staging and no tensor cores):
 //
-//   map     x[kx(i)], y[ky(i)]  ->  x[kx(i)], y[ky(i)]          saxpy sscal scopy sswap srot srotm
-//   reduce  x[kx(i)] (, y[ky(i)]) -> one record                 sdot sdsdot sasum snrm2 isamax
+//   map     x[kx(i)], y[ky(i)]  ->  x[kx(i)], y[ky(i)]          axpy scal copy swap rot rotm
+//   reduce  x[kx(i)] (, y[ky(i)]) -> one record                 dot sdsdot asum nrm2 iamax
 //
 // and each shape has two kernels:
-//   *_unit     incx == incy == 1 : 128- or 256-bit coalesced global loads/stores (LDG.E.128 /
-//              LDG.E.256 on sm_100a), UNROLL independent vectors in flight per thread per operand,
-//              a persistent grid-stride loop over tiles with the grid sized to the resident wave;
-//   *_strided  any increments (negative, zero, non-unit): one logical element per thread, 64-bit
-//              index arithmetic, kx(i) = first(n,inc) + i*inc (Single.hs:91-96).
+//   *_unit     |incx| == |incy| == 1 : 128- or 256-bit coalesced global accesses (LDG.E.128 /
+//              LDG.E.256 on sm_100a), UNROLL independent packs in flight per thread per operand,
+//              a grid-stride loop over tiles; opposite signs pair x[i] with y[n-1-i] and still move
+//              whole aligned packs (reversed lanes);
+//   *_strided  any increments (negative, zero, non-unit): scalar accesses, 64-bit index
+//              arithmetic, kx(i) = first(n,inc) + i*inc (Single.hs:91-96).
+//
+// The reference's routines are polymorphic (`dot :: Num a => ...`, Single.hs:73) with Float and
+// Double instances (sdot/ddot, ...); every kernel here is a template on the element type T.
 //
 // Reductions are deterministic for a given launch shape: per-thread accumulation in a fixed
 // order, warp shuffle tree, fixed-order block combine, one record per block, and the last block
@@ -26,78 +30,126 @@
 namespace lbk {
 
 typedef long long i64;
+typedef unsigned long long u64;
 
 constexpr int kMaxThreads = 512;        // launch bound of every streaming kernel
-constexpr unsigned kNanKey = 0xFFFFFFFFu;
+constexpr u64 kNanKey = ~0ull;
 
 // ------------------------------------------------------------------------------------------------
-// 128/256-bit global memory access
+// element-type helpers: one IEEE operation each, never contracted (the library is built with
+// -fmad=false and these are the *_rn intrinsics), so elementwise results are bit-identical to the
+// reference's compiled code; fma_() is used only where a fused multiply-add is wanted.
 // ------------------------------------------------------------------------------------------------
-template <int VEC> struct alignas(VEC * 4) Pack { float v[VEC]; };
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+__host__ __device__ __forceinline__ float abs_(float a) { return fabsf(a); }
+__host__ __device__ __forceinline__ double abs_(double a) { return fabs(a); }
+__device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+// bit pattern of |x| as an integer: monotone in |x| for non-NaN values
+__device__ __forceinline__ u64 abs_bits(float x) { return (u64)(__float_as_uint(x) & 0x7fffffffu); }
+__device__ __forceinline__ u64 abs_bits(double x) { return (u64)__double_as_longlong(x) & 0x7fffffffffffffffull; }
+template <class T> __device__ __forceinline__ T from_abs_bits(u64 b);
+template <> __device__ __forceinline__ float from_abs_bits<float>(u64 b) { return __uint_as_float((unsigned)b); }
+template <> __device__ __forceinline__ double from_abs_bits<double>(u64 b) { return __longlong_as_double((i64)b); }
 
-// POLICY 0: default caching.  POLICY 1: streaming -- do not allocate in L1 (each byte is touched
-// once), read-only operands through the non-coherent path.
+// ------------------------------------------------------------------------------------------------
+// 128/256-bit global memory access.  A Pack is VEC elements = 4/8 (scalar), 16 or 32 bytes.
+// POLICY 0: default caching.  POLICY >= 1: streaming -- do not allocate in L1 (each byte is touched
+// once), read-only operands through the non-coherent path.  POLICY 2..5 add L2 hints on 256-bit
+// accesses (2/3: evict-first loads, 3/5: evict-first stores, 4: 256-byte L2 prefetch + st.cs); they were
+// measured to make no difference (profiles/r01_tune_l2policy_writers.csv) and exist for tools/tune.py.
+// ------------------------------------------------------------------------------------------------
+template <class T, int VEC> struct alignas(VEC * sizeof(T)) Pack { T v[VEC]; };
+
+// qualifier class of a load: 0 plain, 1/2 no_allocate (read-only / read-write), 3/4 + L2::evict_first,
+// 5/6 + L2::256B (the last four only on 32-byte accesses)
+#define LBK_LDQ(POLICY, RO, WIDE)                                                                   \
+    ((POLICY) == 0 ? 0 : ((WIDE) && ((POLICY) == 2 || (POLICY) == 3)) ? ((RO) ? 3 : 4)              \
+                   : ((WIDE) && (POLICY) == 4) ? ((RO) ? 5 : 6) : ((RO) ? 1 : 2))
+
+// the qualifier has to be a string literal inside the asm, so the shapes are spelled out by macro
+#define LBK_LD_F32x1(Q) asm volatile("ld.global" Q ".f32 %0, [%1];" : "=f"(p.v[0]) : "l"(ptr) : "memory")
+#define LBK_LD_F32x4(Q) asm volatile("ld.global" Q ".v4.f32 {%0,%1,%2,%3}, [%4];"                   \
+                                     : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]) : "l"(ptr) : "memory")
+#define LBK_LD_F32x8(Q) asm volatile("ld.global" Q ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"       \
+                                     : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]),        \
+                                       "=f"(p.v[4]), "=f"(p.v[5]), "=f"(p.v[6]), "=f"(p.v[7]) : "l"(ptr) : "memory")
+#define LBK_LD_F64x1(Q) asm volatile("ld.global" Q ".f64 %0, [%1];" : "=d"(p.v[0]) : "l"(ptr) : "memory")
+#define LBK_LD_F64x2(Q) asm volatile("ld.global" Q ".v2.f64 {%0,%1}, [%2];" : "=d"(p.v[0]), "=d"(p.v[1]) : "l"(ptr) : "memory")
+#define LBK_LD_F64x4(Q) asm volatile("ld.global" Q ".v4.f64 {%0,%1,%2,%3}, [%4];"                   \
+                                     : "=d"(p.v[0]), "=d"(p.v[1]), "=d"(p.v[2]), "=d"(p.v[3]) : "l"(ptr) : "memory")
+#define LBK_LD_DISPATCH(SHAPE)                                                                      \
+    do {                                                                                            \
+        constexpr int q = LBK_LDQ(POLICY, RO, sizeof(T) * VEC == 32);                               \
+        if constexpr (q == 0) SHAPE("");                                                            \
+        else if constexpr (q == 1) SHAPE(".nc.L1::no_allocate");                                    \
+        else if constexpr (q == 2) SHAPE(".L1::no_allocate");                                       \
+        else if constexpr (q == 3) SHAPE(".nc.L1::no_allocate.L2::evict_first");                    \
+        else if constexpr (q == 4) SHAPE(".L1::no_allocate.L2::evict_first");                       \
+        else if constexpr (q == 5) SHAPE(".nc.L1::no_allocate.L2::256B");                           \
+        else SHAPE(".L1::no_allocate.L2::256B");                                                    \
+    } while (0)
+
 template <int VEC, int POLICY, bool RO>
-__device__ __forceinline__ void load_pack(Pack<VEC> &p, const float *ptr)
+__device__ __forceinline__ void load_pack(Pack<float, VEC> &p, const float *ptr)
 {
-    if constexpr (VEC == 1) {
-        if constexpr (POLICY >= 1 && RO)
-            asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(p.v[0]) : "l"(ptr));
-        else if constexpr (POLICY >= 1)
-            asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(p.v[0]) : "l"(ptr) : "memory");
-        else
-            asm volatile("ld.global.f32 %0, [%1];" : "=f"(p.v[0]) : "l"(ptr) : "memory");
-    } else if constexpr (VEC == 4) {
-        if constexpr (POLICY >= 1 && RO)
-            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                         : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]) : "l"(ptr));
-        else if constexpr (POLICY >= 1)
-            asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                         : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]) : "l"(ptr) : "memory");
-        else
-            asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
-                         : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]) : "l"(ptr) : "memory");
-    } else {
-        static_assert(VEC == 8, "VEC is 1, 4 or 8");
-#define LBK_LD8(QUAL, CLOBBER)                                                                      \
-        asm volatile("ld.global" QUAL ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                     \
-                     : "=f"(p.v[0]), "=f"(p.v[1]), "=f"(p.v[2]), "=f"(p.v[3]),                         \
-                       "=f"(p.v[4]), "=f"(p.v[5]), "=f"(p.v[6]), "=f"(p.v[7]) : "l"(ptr) CLOBBER)
-        // experimental L2 policies (256-bit accesses only): 2/3 evict-first loads, 4 256-byte L2 prefetch
-        if constexpr ((POLICY == 2 || POLICY == 3) && RO) LBK_LD8(".nc.L1::no_allocate.L2::evict_first", );
-        else if constexpr (POLICY == 2 || POLICY == 3) LBK_LD8(".L1::no_allocate.L2::evict_first", : "memory");
-        else if constexpr (POLICY == 4 && RO) LBK_LD8(".nc.L1::no_allocate.L2::256B", );
-        else if constexpr (POLICY == 4) LBK_LD8(".L1::no_allocate.L2::256B", : "memory");
-        else if constexpr (POLICY >= 1 && RO) LBK_LD8(".nc.L1::no_allocate", );
-        else if constexpr (POLICY >= 1) LBK_LD8(".L1::no_allocate", : "memory");
-        else LBK_LD8("", : "memory");
-#undef LBK_LD8
-    }
+    using T = float;
+    if constexpr (VEC == 1) LBK_LD_DISPATCH(LBK_LD_F32x1);
+    else if constexpr (VEC == 4) LBK_LD_DISPATCH(LBK_LD_F32x4);
+    else { static_assert(VEC == 8, "float packs hold 1, 4 or 8 elements"); LBK_LD_DISPATCH(LBK_LD_F32x8); }
+}
+template <int VEC, int POLICY, bool RO>
+__device__ __forceinline__ void load_pack(Pack<double, VEC> &p, const double *ptr)
+{
+    using T = double;
+    if constexpr (VEC == 1) LBK_LD_DISPATCH(LBK_LD_F64x1);
+    else if constexpr (VEC == 2) LBK_LD_DISPATCH(LBK_LD_F64x2);
+    else { static_assert(VEC == 4, "double packs hold 1, 2 or 4 elements"); LBK_LD_DISPATCH(LBK_LD_F64x4); }
 }
 
+#define LBK_ST_F32x1(Q) asm volatile("st.global" Q ".f32 [%0], %1;" ::"l"(ptr), "f"(p.v[0]) : "memory")
+#define LBK_ST_F32x4(Q) asm volatile("st.global" Q ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(ptr),       \
+                                     "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]) : "memory")
+#define LBK_ST_F32x8(Q) asm volatile("st.global" Q ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), \
+                                     "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]),              \
+                                     "f"(p.v[4]), "f"(p.v[5]), "f"(p.v[6]), "f"(p.v[7]) : "memory")
+#define LBK_ST_F64x1(Q) asm volatile("st.global" Q ".f64 [%0], %1;" ::"l"(ptr), "d"(p.v[0]) : "memory")
+#define LBK_ST_F64x2(Q) asm volatile("st.global" Q ".v2.f64 [%0], {%1,%2};" ::"l"(ptr), "d"(p.v[0]), "d"(p.v[1]) : "memory")
+#define LBK_ST_F64x4(Q) asm volatile("st.global" Q ".v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr),       \
+                                     "d"(p.v[0]), "d"(p.v[1]), "d"(p.v[2]), "d"(p.v[3]) : "memory")
+#define LBK_ST_DISPATCH(SHAPE)                                                                      \
+    do {                                                                                            \
+        constexpr bool wide = sizeof(T) * VEC == 32;                                                \
+        if constexpr (POLICY == 0 || sizeof(T) * VEC <= 8) SHAPE("");                               \
+        else if constexpr (wide && (POLICY == 3 || POLICY == 5)) SHAPE(".L1::no_allocate.L2::evict_first"); \
+        else if constexpr (wide && POLICY == 4) SHAPE(".cs");                                       \
+        else SHAPE(".L1::no_allocate");                                                             \
+    } while (0)
+
 template <int VEC, int POLICY>
-__device__ __forceinline__ void store_pack(float *ptr, const Pack<VEC> &p)
+__device__ __forceinline__ void store_pack(float *ptr, const Pack<float, VEC> &p)
 {
-    if constexpr (VEC == 1) {
-        asm volatile("st.global.f32 [%0], %1;" ::"l"(ptr), "f"(p.v[0]) : "memory");
-    } else if constexpr (VEC == 4) {
-        if constexpr (POLICY >= 1)
-            asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(ptr),
-                         "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]) : "memory");
-        else
-            asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(ptr),
-                         "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]) : "memory");
-    } else {
-#define LBK_ST8(QUAL)                                                                               \
-        asm volatile("st.global" QUAL ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr),         \
-                     "f"(p.v[0]), "f"(p.v[1]), "f"(p.v[2]), "f"(p.v[3]),                               \
-                     "f"(p.v[4]), "f"(p.v[5]), "f"(p.v[6]), "f"(p.v[7]) : "memory")
-        if constexpr (POLICY == 3 || POLICY == 5) LBK_ST8(".L1::no_allocate.L2::evict_first");
-        else if constexpr (POLICY == 4) LBK_ST8(".cs");
-        else if constexpr (POLICY >= 1) LBK_ST8(".L1::no_allocate");
-        else LBK_ST8("");
-#undef LBK_ST8
-    }
+    using T = float;
+    if constexpr (VEC == 1) LBK_ST_DISPATCH(LBK_ST_F32x1);
+    else if constexpr (VEC == 4) LBK_ST_DISPATCH(LBK_ST_F32x4);
+    else LBK_ST_DISPATCH(LBK_ST_F32x8);
+}
+template <int VEC, int POLICY>
+__device__ __forceinline__ void store_pack(double *ptr, const Pack<double, VEC> &p)
+{
+    using T = double;
+    if constexpr (VEC == 1) LBK_ST_DISPATCH(LBK_ST_F64x1);
+    else if constexpr (VEC == 2) LBK_ST_DISPATCH(LBK_ST_F64x2);
+    else LBK_ST_DISPATCH(LBK_ST_F64x4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -113,65 +165,71 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// map functors.  (x, y) are the OLD values; the functor overwrites them with the new ones.  Every
-// product is rounded before it is added (__fmul_rn / __fadd_rn are never contracted into an FMA),
-// which is what the reference's compiled code does, so results are bit-identical to it.
+// map functors.  (x, y) are the OLD values; the functor overwrites them with the new ones.
 // ------------------------------------------------------------------------------------------------
-struct AxpyF {   // Single.hs:439   y + a*x
-    float a;
+template <class T> struct AxpyF {   // Single.hs:439   y + a*x
+    using Scalar = T;
+    T a;
     static constexpr bool RX = true, RY = true, WX = false, WY = true;
-    __device__ __forceinline__ void operator()(float &x, float &y) const { y = __fadd_rn(y, __fmul_rn(a, x)); }
+    __device__ __forceinline__ void operator()(T &x, T &y) const { y = add_rn(y, mul_rn(a, x)); }
 };
-struct ScalF {   // Single.hs:110   x*a
-    float a;
+template <class T> struct ScalF {   // Single.hs:110   x*a
+    using Scalar = T;
+    T a;
     static constexpr bool RX = true, RY = false, WX = true, WY = false;
-    __device__ __forceinline__ void operator()(float &x, float &) const { x = __fmul_rn(x, a); }
+    __device__ __forceinline__ void operator()(T &x, T &) const { x = mul_rn(x, a); }
 };
-struct CopyF {   // Single.hs:127   \_ x -> x
+template <class T> struct CopyF {   // Single.hs:127   \_ x -> x
+    using Scalar = T;
     static constexpr bool RX = true, RY = false, WX = false, WY = true;
-    __device__ __forceinline__ void operator()(float &x, float &y) const { y = x; }
+    __device__ __forceinline__ void operator()(T &x, T &y) const { y = x; }
 };
-struct SwapF {   // Single.hs:143-145
+template <class T> struct SwapF {   // Single.hs:143-145
+    using Scalar = T;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
-    __device__ __forceinline__ void operator()(float &x, float &y) const { float t = x; x = y; y = t; }
+    __device__ __forceinline__ void operator()(T &x, T &y) const { T t = x; x = y; y = t; }
 };
-struct RotF {    // Single.hs:418-419   c*x + s*y ; c*y - s*x
-    float c, s;
+template <class T> struct RotF {    // Single.hs:418-419   c*x + s*y ; c*y - s*x
+    using Scalar = T;
+    T c, s;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
-    __device__ __forceinline__ void operator()(float &x, float &y) const
+    __device__ __forceinline__ void operator()(T &x, T &y) const
     {
-        float nx = __fadd_rn(__fmul_rn(c, x), __fmul_rn(s, y));
-        float ny = __fsub_rn(__fmul_rn(c, y), __fmul_rn(s, x));
+        T nx = add_rn(mul_rn(c, x), mul_rn(s, y));
+        T ny = sub_rn(mul_rn(c, y), mul_rn(s, x));
         x = nx; y = ny;
     }
 };
-struct RotmNeg1F {   // Single.hs:475-476   h11*x + h12*y ; h21*x + h22*y
-    float h11, h12, h21, h22;
+template <class T> struct RotmNeg1F {   // Single.hs:475-476   h11*x + h12*y ; h21*x + h22*y
+    using Scalar = T;
+    T h11, h12, h21, h22;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
-    __device__ __forceinline__ void operator()(float &x, float &y) const
+    __device__ __forceinline__ void operator()(T &x, T &y) const
     {
-        float nx = __fadd_rn(__fmul_rn(h11, x), __fmul_rn(h12, y));
-        float ny = __fadd_rn(__fmul_rn(h21, x), __fmul_rn(h22, y));
+        T nx = add_rn(mul_rn(h11, x), mul_rn(h12, y));
+        T ny = add_rn(mul_rn(h21, x), mul_rn(h22, y));
         x = nx; y = ny;
     }
 };
-struct Rotm0F {      // Single.hs:478-479   x + h12*y ; h21*x + y
-    float h12, h21;
+template <class T> struct Rotm0F {      // Single.hs:478-479   x + h12*y ; h21*x + y
+    using Scalar = T;
+    T h12, h21;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
-    __device__ __forceinline__ void operator()(float &x, float &y) const
+    __device__ __forceinline__ void operator()(T &x, T &y) const
     {
-        float nx = __fadd_rn(x, __fmul_rn(h12, y));
-        float ny = __fadd_rn(__fmul_rn(h21, x), y);
+        T nx = add_rn(x, mul_rn(h12, y));
+        T ny = add_rn(mul_rn(h21, x), y);
         x = nx; y = ny;
     }
 };
-struct Rotm1F {      // Single.hs:481-482   h11*x + y ; -x + h22*y
-    float h11, h22;
+template <class T> struct Rotm1F {      // Single.hs:481-482   h11*x + y ; -x + h22*y
+    using Scalar = T;
+    T h11, h22;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
-    __device__ __forceinline__ void operator()(float &x, float &y) const
+    __device__ __forceinline__ void operator()(T &x, T &y) const
     {
-        float nx = __fadd_rn(__fmul_rn(h11, x), y);
-        float ny = __fadd_rn(-x, __fmul_rn(h22, y));
+        T nx = add_rn(mul_rn(h11, x), y);
+        T ny = add_rn(-x, mul_rn(h22, y));
         x = nx; y = ny;
     }
 };
@@ -179,30 +237,32 @@ struct Rotm1F {      // Single.hs:481-482   h11*x + y ; -x + h22*y
 // ------------------------------------------------------------------------------------------------
 // map, unit stride.  Reads come from (xr, yr), writes go to (xw, yw); in place when they are equal,
 // out of place (the reference's pure result) when they differ.  `head` scalar elements precede the
-// vector body so that xr+head (and yr/xw/yw+head: checked by the host) are VEC*4-byte aligned; they
-// and the < VEC tail are handled by the first threads of block 0.
-// ------------------------------------------------------------------------------------------------
+// pack body so that xr+head (and yr/xw/yw+head: checked by the host) are pack aligned; they and the
+// < VEC tail are handled by the first threads of block 0.
 //
 // REV: the (incx, incy) = (1,-1) / (-1,1) pairing -- logical element i is x[i] and y[n-1-i] -- still moves
 // whole aligned packs: the y pack for x[e..e+VEC) is y[n-e-VEC..n-e) with its lanes in reverse order.
+// ------------------------------------------------------------------------------------------------
 template <class F, int VEC, int UNROLL, int POLICY, bool REV = false>
 __global__ void __launch_bounds__(kMaxThreads)
-map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64 head, i64 n)
+map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr, typename F::Scalar *xw,
+                typename F::Scalar *yw, i64 head, i64 n)
 {
+    using T = typename F::Scalar;
     const i64 body = n - head;
     const i64 npack = body / VEC;
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
-    const float *bxr = xr + head;
-    float *bxw = xw + head;
+    const T *bxr = xr + head;
+    T *bxw = xw + head;
     // y side: forward from y+head, or backward from one past the body's last y element
-    const float *byr = REV ? yr + (n - head) - VEC : yr + head;
-    float *byw = REV ? yw + (n - head) - VEC : yw + head;
+    const T *byr = REV ? yr + (n - head) - VEC : yr + head;
+    T *byw = REV ? yw + (n - head) - VEC : yw + head;
     constexpr int YS = REV ? -1 : 1;
 
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const i64 p0 = tile * per_tile + threadIdx.x;
-        Pack<VEC> xv[UNROLL], yv[UNROLL];
+        Pack<T, VEC> xv[UNROLL], yv[UNROLL];
         if (p0 + (i64)(UNROLL - 1) * blockDim.x < npack) {   // whole tile in range for this thread
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -244,7 +304,7 @@ map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64
         for (i64 t = threadIdx.x; t < nscalar; t += blockDim.x) {
             const i64 e = t < head ? t : tail0 + (t - head);
             const i64 ey = REV ? n - 1 - e : e;
-            float xs = 0.f, ys = 0.f;
+            T xs = 0, ys = 0;
             if constexpr (F::RX) xs = xr[e];
             if constexpr (F::RY) ys = yr[ey];
             f(xs, ys);
@@ -262,33 +322,32 @@ map_unit_kernel(F f, const float *xr, const float *yr, float *xw, float *yw, i64
 // element 0 as the read pointer and sets *_last_only, so that only logical element n-1 (the last
 // write of the reference's sequential scatter) stores.
 // ------------------------------------------------------------------------------------------------
-constexpr int kStridedUnroll = 4;   // independent 4-byte accesses in flight per operand per thread
+constexpr int kStridedUnroll = 4;   // independent scalar accesses in flight per operand per thread
 
 template <class F>
 __global__ void __launch_bounds__(256)
-map_strided_kernel(F f, const float *xr, float *xw, i64 incx_r, i64 incx_w, i64 kx0_r, i64 kx0_w,
-                   const float *yr, float *yw, i64 incy_r, i64 incy_w, i64 ky0_r, i64 ky0_w,
+map_strided_kernel(F f, const typename F::Scalar *xr, typename F::Scalar *xw, i64 incx_r, i64 incx_w, i64 kx0_r, i64 kx0_w,
+                   const typename F::Scalar *yr, typename F::Scalar *yw, i64 incy_r, i64 incy_w, i64 ky0_r, i64 ky0_w,
                    i64 i_begin, i64 n, int x_last_only, int y_last_only)
 {
+    using T = typename F::Scalar;
     constexpr int U = kStridedUnroll;
     const i64 per_tile = (i64)U * blockDim.x;
     const i64 count = n - i_begin;
     const i64 ntiles = (count + per_tile - 1) / per_tile;
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const i64 i0 = i_begin + tile * per_tile + threadIdx.x;
-        float xs[U], ys[U];
+        T xs[U], ys[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {            // all loads first: U independent requests per operand
             const i64 i = i0 + (i64)u * blockDim.x;
-            xs[u] = 0.f; ys[u] = 0.f;
-            if (i < n) {      // asm volatile loads: issued here, all U before the first use
-                Pack<1> p;
+            xs[u] = 0; ys[u] = 0;
+            if (i < n) {
+                Pack<T, 1> p;
                 if constexpr (F::RX) { load_pack<1, 0, !F::WX>(p, xr + kx0_r + i * incx_r); xs[u] = p.v[0]; }
                 if constexpr (F::RY) { load_pack<1, 0, !F::WY>(p, yr + ky0_r + i * incy_r); ys[u] = p.v[0]; }
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) asm volatile("" : "+f"(xs[u]), "+f"(ys[u]));   // keep the U loads ahead of the first use
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const i64 i = i0 + (i64)u * blockDim.x;
@@ -305,14 +364,16 @@ map_strided_kernel(F f, const float *xr, float *xw, i64 incx_r, i64 incx_w, i64 
 // reductions
 // ------------------------------------------------------------------------------------------------
 // The record a block (and, across GPUs, a rank) contributes.  Layout shared with the host
-// (lbk_record in include/lbk.h): f[0..2] sums, key/idx the isamax candidate.
+// (lbk_record in include/lbk.h): f[0..2] partial sums (held in double, so float partials are exact),
+// key/idx the iamax candidate.
 struct Record {
-    float f[3];
-    unsigned key;
+    double f[3];
+    u64 key;
     i64 idx;
     i64 pad;
 };
-static_assert(sizeof(Record) == 32, "Record is 32 bytes");
+static_assert(sizeof(Record) == 48, "Record is 48 bytes");
+constexpr int kRecordWords = sizeof(Record) / 4;
 
 __device__ __forceinline__ Record shfl_xor_record(const Record &r, int mask)
 {
@@ -326,123 +387,138 @@ __device__ __forceinline__ Record shfl_xor_record(const Record &r, int mask)
     return o;
 }
 
-// Blue's scaled accumulation (as in LAPACK 3.10 snrm2, thresholds tightened so that 2^36 mid-range
-// squares cannot overflow binary32): |x| > kBig is accumulated as (x*kSBig)^2, |x| < kSml as
-// (x*kSSml)^2, everything else as x^2.  All three are plain sums, so the cross-block and
-// cross-GPU combine is addition.
-constexpr float kBig = 70368744177664.0f;            // 2^46
-constexpr float kSml = 1.0842021724855044e-19f;      // 2^-63
-constexpr float kSBig = 1.3234889800848443e-23f;     // 2^-76
-constexpr float kSSml = 3.7778931862957162e+22f;     // 2^75
+// Blue's scaled accumulation (as in LAPACK 3.10 *nrm2): |x| > big is accumulated as (x*sbig)^2,
+// |x| < sml as (x*ssml)^2, everything else as x^2.  All three are plain sums, so the cross-block and
+// cross-GPU combine is addition.  The float thresholds are tightened so that 2^36 mid-range squares
+// cannot overflow binary32; the double ones are LAPACK's.
+template <class T> struct Blue;
+template <> struct Blue<float> {
+    static constexpr float big = 70368744177664.0f;            // 2^46
+    static constexpr float sml = 1.0842021724855044e-19f;      // 2^-63
+    static constexpr float sbig = 1.3234889800848443e-23f;     // 2^-76
+    static constexpr float ssml = 3.7778931862957162e+22f;     // 2^75
+};
+template <> struct Blue<double> {
+    static constexpr double big = 1.9979190722022350e+146;     // 2^486
+    static constexpr double sml = 1.4916681462400413e-154;     // 2^-511
+    static constexpr double sbig = 1.1113793747425387e-162;    // 2^-538
+    static constexpr double ssml = 4.4989137945431964e+161;    // 2^537
+};
 
-// Op concept:  Acc, zero(), step(acc,x,y,ord), to_record(acc, ord->index map), merge(a,b)
-struct DotOp {       // Single.hs:81-82
+// Op concept:  Scalar, Acc, zero(), step(acc,x,y,ord) [or step_pack], to_record, single, merge
+template <class T> struct DotOp {       // Single.hs:81-82
+    using Scalar = T;
     static constexpr bool TWO = true, IS_IAMAX = false, HAS_PACK_STEP = false;
-    struct Acc { float s; };
-    __device__ static __forceinline__ Acc zero() { return {0.f}; }
-    __device__ static __forceinline__ void step(Acc &a, float x, float y, unsigned) { a.s = fmaf(x, y, a.s); }
-    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = a.s; }
-    __device__ static __forceinline__ void single(Record &r, float x, float y, i64) { r.f[0] = fmaf(x, y, r.f[0]); }
+    struct Acc { T s; };
+    __device__ static __forceinline__ Acc zero() { return {0}; }
+    __device__ static __forceinline__ void step(Acc &a, T x, T y, unsigned) { a.s = fma_(x, y, a.s); }
+    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = (double)a.s; }
+    __device__ static __forceinline__ void single(Record &r, T x, T y, i64) { r.f[0] = fma((double)x, (double)y, r.f[0]); }
     __host__ __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
     { Record o = a; o.f[0] = a.f[0] + b.f[0]; return o; }
 };
-struct DsdotOp {     // Single.hs:238-262: products and sum in double (held as a double split over f[0],f[1] bits)
+struct DsdotOp {     // Single.hs:238-262: float inputs, products and sum in double
+    using Scalar = float;
     static constexpr bool TWO = true, IS_IAMAX = false, HAS_PACK_STEP = false;
     struct Acc { double s; };
     __device__ static __forceinline__ Acc zero() { return {0.0}; }
     __device__ static __forceinline__ void step(Acc &a, float x, float y, unsigned) { a.s = fma((double)x, (double)y, a.s); }
-    __device__ static __forceinline__ double get(const Record &r)
-    { return __hiloint2double(__float_as_int(r.f[1]), __float_as_int(r.f[0])); }
-    __device__ static __forceinline__ void put(Record &r, double d)
-    { r.f[0] = __int_as_float(__double2loint(d)); r.f[1] = __int_as_float(__double2hiint(d)); }
-    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { put(r, a.s); }
-    __device__ static __forceinline__ void single(Record &r, float x, float y, i64) { put(r, fma((double)x, (double)y, get(r))); }
-    __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
-    { Record o = a; put(o, get(a) + get(b)); return o; }
-};
-struct AsumOp {      // Single.hs:163
-    static constexpr bool TWO = false, IS_IAMAX = false, HAS_PACK_STEP = false;
-    struct Acc { float s; };
-    __device__ static __forceinline__ Acc zero() { return {0.f}; }
-    __device__ static __forceinline__ void step(Acc &a, float x, float, unsigned) { a.s += fabsf(x); }
     __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = a.s; }
-    __device__ static __forceinline__ void single(Record &r, float x, float, i64) { r.f[0] += fabsf(x); }
+    __device__ static __forceinline__ void single(Record &r, float x, float y, i64) { r.f[0] = fma((double)x, (double)y, r.f[0]); }
     __host__ __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
     { Record o = a; o.f[0] = a.f[0] + b.f[0]; return o; }
 };
-struct Nrm2Op {      // Single.hs:180-199, restated as Blue's three accumulators
+template <class T> struct AsumOp {      // Single.hs:163
+    using Scalar = T;
+    static constexpr bool TWO = false, IS_IAMAX = false, HAS_PACK_STEP = false;
+    struct Acc { T s; };
+    __device__ static __forceinline__ Acc zero() { return {0}; }
+    __device__ static __forceinline__ void step(Acc &a, T x, T, unsigned) { a.s += abs_(x); }
+    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = (double)a.s; }
+    __device__ static __forceinline__ void single(Record &r, T x, T, i64) { r.f[0] += (double)abs_(x); }
+    __host__ __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
+    { Record o = a; o.f[0] = a.f[0] + b.f[0]; return o; }
+};
+template <class T> struct Nrm2Op {      // Single.hs:180-199, restated as Blue's three accumulators
+    using Scalar = T;
     static constexpr bool TWO = false, IS_IAMAX = false, HAS_PACK_STEP = true;
-    struct Acc { float big, med, sml; };
-    __device__ static __forceinline__ Acc zero() { return {0.f, 0.f, 0.f}; }
-    __device__ static __forceinline__ void step(Acc &a, float x, float, unsigned)
+    struct Acc { T big, med, sml; };
+    __device__ static __forceinline__ Acc zero() { return {0, 0, 0}; }
+    __device__ static __forceinline__ void step(Acc &a, T x, T, unsigned)
     {
-        const float ax = fabsf(x);
-        if (ax > kBig) { const float t = ax * kSBig; a.big = fmaf(t, t, a.big); }
-        else if (ax < kSml) { const float t = ax * kSSml; a.sml = fmaf(t, t, a.sml); }
-        else a.med = fmaf(ax, ax, a.med);      // NaN lands here and propagates
+        const T ax = abs_(x);
+        if (ax > Blue<T>::big) { const T t = ax * Blue<T>::sbig; a.big = fma_(t, t, a.big); }
+        else if (ax < Blue<T>::sml) { const T t = ax * Blue<T>::ssml; a.sml = fma_(t, t, a.sml); }
+        else a.med = fma_(ax, ax, a.med);      // NaN lands here and propagates
     }
-    // One vector of lanes: when every lane is mid-range (the overwhelmingly common case) the pack costs
-    // one FFMA and two FMNMX per element; a pack holding a huge, tiny or zero lane takes the exact
-    // per-lane classification.  fmaxf/fminf skip NaN lanes, and the fast path's x*x propagates them.
+    // One pack of lanes: when every lane is mid-range (the overwhelmingly common case) the pack costs
+    // one FMA and two min/max per element; a pack holding a huge, tiny or zero lane takes the exact
+    // per-lane classification.  max_/min_ skip NaN lanes, and the fast path's x*x propagates them.
     template <int VEC>
-    __device__ static __forceinline__ void step_pack(Acc &a, const Pack<VEC> &x, const Pack<VEC> &, unsigned)
+    __device__ static __forceinline__ void step_pack(Acc &a, const Pack<T, VEC> &x, const Pack<T, VEC> &, unsigned)
     {
-        float mx = fabsf(x.v[0]), mn = mx;
+        T mx = abs_(x.v[0]), mn = mx;
 #pragma unroll
-        for (int l = 1; l < VEC; ++l) { mx = fmaxf(mx, fabsf(x.v[l])); mn = fminf(mn, fabsf(x.v[l])); }
-        if (mx <= kBig && mn >= kSml) {
+        for (int l = 1; l < VEC; ++l) { mx = max_(mx, abs_(x.v[l])); mn = min_(mn, abs_(x.v[l])); }
+        if (mx <= Blue<T>::big && mn >= Blue<T>::sml) {
 #pragma unroll
-            for (int l = 0; l < VEC; ++l) a.med = fmaf(x.v[l], x.v[l], a.med);
+            for (int l = 0; l < VEC; ++l) a.med = fma_(x.v[l], x.v[l], a.med);
         } else {
 #pragma unroll
-            for (int l = 0; l < VEC; ++l) step(a, x.v[l], 0.f, 0u);
+            for (int l = 0; l < VEC; ++l) step(a, x.v[l], T(0), 0u);
         }
     }
-    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = a.big; r.f[1] = a.med; r.f[2] = a.sml; }
-    __device__ static __forceinline__ void single(Record &r, float x, float, i64)
-    { Acc a = {r.f[0], r.f[1], r.f[2]}; step(a, x, 0.f, 0u); to_record(r, a); }
+    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = (double)a.big; r.f[1] = (double)a.med; r.f[2] = (double)a.sml; }
+    __device__ static __forceinline__ void single(Record &r, T x, T, i64)
+    {   // the strided / scalar path classifies in T and accumulates in the record's doubles
+        const T ax = abs_(x);
+        if (ax > Blue<T>::big) { const double t = (double)(ax * Blue<T>::sbig); r.f[0] = fma(t, t, r.f[0]); }
+        else if (ax < Blue<T>::sml) { const double t = (double)(ax * Blue<T>::ssml); r.f[2] = fma(t, t, r.f[2]); }
+        else { const double t = (double)ax; r.f[1] = fma(t, t, r.f[1]); }
+    }
     __host__ __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
     { Record o = a; o.f[0] = a.f[0] + b.f[0]; o.f[1] = a.f[1] + b.f[1]; o.f[2] = a.f[2] + b.f[2]; return o; }
 };
-// isamax (Single.hs:217-220).  key = bit pattern of |x| (monotone for non-NaN), NaN -> 0 so that it
+// iamax (Single.hs:217-220).  key = bit pattern of |x| (monotone for non-NaN), NaN -> 0 so that it
 // can never displace an earlier element (`|best| < |NaN|` is false in the reference's fold); the
 // "NaN at logical index 0 is never displaced" half of the rule is applied once, at the finish.
-__device__ __forceinline__ unsigned amax_key(float x)
+template <class T> __device__ __forceinline__ u64 amax_key(T x)
 {
-    const unsigned b = __float_as_uint(x) & 0x7fffffffu;
-    return b > 0x7f800000u ? 0u : b;
+    const u64 b = abs_bits(x);
+    return (x != x) ? 0ull : b;
 }
-struct IamaxOp {
+template <class T> struct IamaxOp {
+    using Scalar = T;
     static constexpr bool TWO = false, IS_IAMAX = true, HAS_PACK_STEP = true;
-    // running maximum of |x| as a float (-1 = nothing seen yet; any |x| >= 0 beats it) and the ordinal,
-    // within this thread's element sequence, of the FIRST element that reached it
-    struct Acc { float val; unsigned ord; };
-    __device__ static __forceinline__ Acc zero() { return {-1.f, 0u}; }
-    __device__ static __forceinline__ void step(Acc &a, float x, float, unsigned ord)
+    // running maximum of |x| (-1 = nothing seen yet; any |x| >= 0 beats it) and the ordinal, within this
+    // thread's element sequence, of the FIRST element that reached it
+    struct Acc { T val; unsigned ord; };
+    __device__ static __forceinline__ Acc zero() { return {T(-1), 0u}; }
+    __device__ static __forceinline__ void step(Acc &a, T x, T, unsigned ord)
     {
-        const float ax = fabsf(x);
+        const T ax = abs_(x);
         if (ax > a.val) { a.val = ax; a.ord = ord; }      // false for NaN: a NaN never displaces
     }
     // elements reach a thread in increasing index order, so strict '>' keeps the first maximum.  Per
-    // pack: one FMNMX per element (fmaxf drops NaN lanes, which is the reference's "NaN never wins");
+    // pack: one max per element (max_ drops NaN lanes, which is the reference's "NaN never wins");
     // only a pack that raises the thread's maximum (O(log) times per thread) looks for the lane.
     template <int VEC>
-    __device__ static __forceinline__ void step_pack(Acc &a, const Pack<VEC> &x, const Pack<VEC> &, unsigned ord0)
+    __device__ static __forceinline__ void step_pack(Acc &a, const Pack<T, VEC> &x, const Pack<T, VEC> &, unsigned ord0)
     {
-        float m = fabsf(x.v[0]);
+        T m = abs_(x.v[0]);
 #pragma unroll
-        for (int l = 1; l < VEC; ++l) m = fmaxf(m, fabsf(x.v[l]));
+        for (int l = 1; l < VEC; ++l) m = max_(m, abs_(x.v[l]));
         if (m > a.val) {
             unsigned lane = 0;
 #pragma unroll
-            for (int l = VEC - 1; l >= 0; --l) if (fabsf(x.v[l]) == m) lane = l;
+            for (int l = VEC - 1; l >= 0; --l) if (abs_(x.v[l]) == m) lane = l;
             a.val = m; a.ord = ord0 + lane;
         }
     }
     __device__ static __forceinline__ void to_record(Record &, const Acc &) {}
-    __device__ static __forceinline__ void single(Record &r, float x, float, i64 idx)
+    __device__ static __forceinline__ void single(Record &r, T x, T, i64 idx)
     {
-        const unsigned k = amax_key(x);
+        const u64 k = amax_key(x);
         if (r.idx < 0 || k > r.key || (k == r.key && idx < r.idx)) { r.key = k; r.idx = idx; }
     }
     // larger key wins; on a tie the lower index; idx < 0 means "no candidate"
@@ -455,12 +531,11 @@ struct IamaxOp {
     }
 };
 
-template <class Op>
-__device__ __forceinline__ Record empty_record()
+__host__ __device__ __forceinline__ Record empty_record()
 {
     Record r;
-    r.f[0] = r.f[1] = r.f[2] = 0.f;
-    r.key = 0u;
+    r.f[0] = r.f[1] = r.f[2] = 0.0;
+    r.key = 0ull;
     r.idx = -1;
     r.pad = 0;
     return r;
@@ -478,7 +553,7 @@ __device__ __forceinline__ Record block_combine(Record r, Record *smem)
     if (lane == 0) smem[warp] = r;
     __syncthreads();
     if (warp == 0) {
-        r = lane < nwarps ? smem[lane] : empty_record<Op>();
+        r = lane < nwarps ? smem[lane] : empty_record();
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) r = Op::merge(r, shfl_xor_record(r, m));
     }
@@ -486,84 +561,115 @@ __device__ __forceinline__ Record block_combine(Record r, Record *smem)
 }
 
 // What the last block does with the folded record.
-//   mode 0: finish on this GPU and store the scalar to `out` (float, or int64 for isamax);
+//   mode 0: finish on this GPU and store the scalar to `out` (T, or int64 for iamax);
 //   mode 1: store the record to `rec_out`; an NCCL all-gather and finish_records_kernel end the call;
 //   mode 2: fused exchange -- push the record straight into every peer GPU's mailbox over NVLink (peer
 //           memory mapped with CUDA IPC), wait for the peers' records in this GPU's mailbox, fold them in
 //           rank order and finish, all inside this kernel.
 struct FinishArgs {
-    int kind;             // lbk_reduce_kind: 0 sum, 1 nrm2, 2 iamax, 3 dsdot
+    int kind;             // 0 sum, 1 nrm2, 2 iamax, 3 dsdot
     int mode;
-    const float *x0;      // logical element 0 if this rank owns it (isamax NaN rule, nrm2 n==1), else null
+    int is_f64;           // element type of the vectors (and of the scalar result)
+    const void *x0;       // logical element 0 if this rank owns it (iamax NaN rule, nrm2 n==1), else null
     i64 n_global;
     double sb;            // sdsdot's addend
     void *out;
     Record *rec_out;
     // mode 2
-    unsigned long long *const *peers;   // device array: peers[r] = rank r's mailbox (peers[rank] is local)
+    u64 *const *peers;    // device array: peers[r] = rank r's mailbox (peers[rank] is local)
     int nranks, rank;
-    unsigned seq;                       // number of this exchange, identical on every rank, never 0
-    int *error_flag;                    // host-mapped: set to 1 if a peer's record never arrived
+    unsigned seq;         // number of this exchange, identical on every rank, never 0
+    int *error_flag;      // host-mapped: set to 1 if a peer's record never arrived
 };
 
-// Mailbox: two parities x kMaxRanks senders x 8 words.  Each 64-bit word carries 32 bits of record and
-// the 32-bit exchange number, so one store publishes data and "ready" together (no fence, no second
-// round trip); a word is valid once its tag equals the current exchange number.  Exchange k+2 can only
-// reuse exchange k's slots after every rank has consumed them (a rank sends k+1 only after finishing k).
+// Mailbox: two parities x kMaxRanks senders x kMailboxSlot words.  Each 64-bit word carries 32 bits of
+// record and the 32-bit exchange number, so one store publishes data and "ready" together (no fence, no
+// second round trip); a word is valid once its tag equals the current exchange number.  Exchange k+2 can
+// only reuse exchange k's slots after every rank has consumed them (a rank sends k+1 only after finishing k).
 constexpr int kMaxRanks = 64;
-constexpr int kMailboxWords = 2 * kMaxRanks * 8;
-constexpr unsigned long long kExchangeTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;
+constexpr int kMailboxSlot = 16;                               // words reserved per sender (>= kRecordWords)
+constexpr int kMailboxWords = 2 * kMaxRanks * kMailboxSlot;
+constexpr u64 kExchangeTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;
+static_assert(kRecordWords <= kMailboxSlot, "a record fits its mailbox slot");
 
-__device__ __forceinline__ unsigned long long global_timer_ns()
+__device__ __forceinline__ u64 global_timer_ns()
 {
-    unsigned long long t;
+    u64 t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
 
-__device__ __forceinline__ Record fold_by_kind(const Record *recs, int nranks, int kind);
-
-__host__ __device__ __forceinline__ float nrm2_finish(float abig, float amed, float asml)
+// scale * sqrt(sumsq) of Blue's combine, in double for both element types (SB, SS: the type's scalings)
+__host__ __device__ __forceinline__ double nrm2_finish(double abig, double amed, double asml, double SB, double SS)
 {
-    float scl, sumsq;
-    if (abig > 0.f) {
-        if (amed > 0.f || amed != amed) abig += (amed * kSBig) * kSBig;
-        scl = 1.f / kSBig; sumsq = abig;
-    } else if (asml > 0.f) {
-        if (amed > 0.f || amed != amed) {
-            const float m = sqrtf(amed), s = sqrtf(asml) / kSSml;
-            const float ymin = fminf(m, s), ymax = fmaxf(m, s);
-            const float q = ymin / ymax;
-            scl = 1.f; sumsq = (ymax * ymax) * (1.f + q * q);
+    double scl, sumsq;
+    if (abig > 0.0) {
+        if (amed > 0.0 || amed != amed) abig += (amed * SB) * SB;
+        scl = 1.0 / SB; sumsq = abig;
+    } else if (asml > 0.0) {
+        if (amed > 0.0 || amed != amed) {
+            const double m = sqrt(amed), s = sqrt(asml) / SS;
+            const double ymin = m < s ? m : s, ymax = m < s ? s : m;
+            const double q = ymin / ymax;
+            scl = 1.0; sumsq = (ymax * ymax) * (1.0 + q * q);
             if (amed != amed) sumsq = amed;
-        } else { scl = 1.f / kSSml; sumsq = asml; }
-    } else { scl = 1.f; sumsq = amed; }
-    return scl * sqrtf(sumsq);
+        } else { scl = 1.0 / SS; sumsq = asml; }
+    } else { scl = 1.0; sumsq = amed; }
+    return scl * sqrt(sumsq);
 }
 
 // Applies the rules that depend on logical element 0 to this rank's record (before any exchange).
-__device__ __forceinline__ void localize_record(Record &r, const FinishArgs &fa, float x0)
+// x0_bits / x0_nan describe element 0, read at kernel start (a PDL secondary may overwrite x later).
+__device__ __forceinline__ void localize_record(Record &r, const FinishArgs &fa, u64 x0_bits, bool x0_nan)
 {
     if (fa.x0 != nullptr) {
-        if (fa.kind == 2 && x0 != x0) { r.key = kNanKey; r.idx = 0; }      // NaN at index 0 stays
-        if (fa.kind == 1) r.key = __float_as_uint(fabsf(x0));              // nrm2 n==1 -> |x[0]|
+        if (fa.kind == 2 && x0_nan) { r.key = kNanKey; r.idx = 0; }      // NaN at index 0 stays
+        if (fa.kind == 1) r.key = x0_bits;                                // nrm2 n==1 -> |x[0]|
     }
+}
+
+__device__ __forceinline__ void store_result(const FinishArgs &fa, double v)
+{
+    if (fa.is_f64) *reinterpret_cast<double *>(fa.out) = v;
+    else *reinterpret_cast<float *>(fa.out) = (float)v;
 }
 
 __device__ __forceinline__ void finish_record(const Record &r, const FinishArgs &fa)
 {
-    if (fa.kind == 2) { *reinterpret_cast<i64 *>(fa.out) = r.idx; }
-    else if (fa.kind == 1) {
-        *reinterpret_cast<float *>(fa.out) =
-            fa.n_global == 1 ? __uint_as_float(r.key) : nrm2_finish(r.f[0], r.f[1], r.f[2]);
+    if (fa.kind == 2) { *reinterpret_cast<i64 *>(fa.out) = r.idx; return; }
+    if (fa.kind == 1) {
+        if (fa.n_global == 1) {           // |x[0]| exactly, Single.hs:182
+            if (fa.is_f64) *reinterpret_cast<double *>(fa.out) = from_abs_bits<double>(r.key);
+            else *reinterpret_cast<float *>(fa.out) = from_abs_bits<float>(r.key);
+            return;
+        }
+        store_result(fa, fa.is_f64 ? nrm2_finish(r.f[0], r.f[1], r.f[2], (double)Blue<double>::sbig, (double)Blue<double>::ssml)
+                                   : nrm2_finish(r.f[0], r.f[1], r.f[2], (double)Blue<float>::sbig, (double)Blue<float>::ssml));
+        return;
     }
-    else if (fa.kind == 3) { *reinterpret_cast<float *>(fa.out) = (float)(fa.sb + DsdotOp::get(r)); }
-    else { *reinterpret_cast<float *>(fa.out) = r.f[0]; }
+    store_result(fa, fa.kind == 3 ? fa.sb + r.f[0] : r.f[0]);
+}
+
+// Cross-GPU fold: every rank holds all ranks' records (rank order) and folds them identically.
+template <class Op>
+__host__ __device__ __forceinline__ Record fold_ranks(const Record *recs, int nranks)
+{
+    Record acc = recs[0];
+    for (int r = 1; r < nranks; ++r) acc = Op::merge(acc, recs[r]);
+    return acc;
+}
+__host__ __device__ __forceinline__ Record fold_by_kind(const Record *recs, int nranks, int kind)
+{
+    Record acc;
+    if (kind == 2) acc = fold_ranks<IamaxOp<float>>(recs, nranks);          // the merges do not depend on T
+    else if (kind == 1) { acc = fold_ranks<Nrm2Op<float>>(recs, nranks); acc.key = recs[0].key; }   // |x[0]| travels in rank 0's key
+    else acc = fold_ranks<DotOp<float>>(recs, nranks);
+    return acc;
 }
 
 template <class Op>
 __device__ __forceinline__ void grid_finish(Record r, Record *partials, unsigned *ticket,
-                                            const FinishArgs &fa, Record *smem, float x0)
+                                            const FinishArgs &fa, Record *smem, u64 x0_bits, bool x0_nan)
 {
     __shared__ bool is_last;
     r = block_combine<Op>(r, smem);
@@ -577,18 +683,18 @@ __device__ __forceinline__ void grid_finish(Record r, Record *partials, unsigned
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    Record acc = empty_record<Op>();
+    Record acc = empty_record();
     for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
         // other blocks' records: read through L2 (L1 is not coherent across SMs)
-        union { int4 q[2]; Record r; } u;
-        u.q[0] = __ldcg(reinterpret_cast<const int4 *>(&partials[b]));
-        u.q[1] = __ldcg(reinterpret_cast<const int4 *>(&partials[b]) + 1);
+        union { int4 q[3]; Record r; } u;
+        const int4 *src = reinterpret_cast<const int4 *>(&partials[b]);
+        u.q[0] = __ldcg(src); u.q[1] = __ldcg(src + 1); u.q[2] = __ldcg(src + 2);
         acc = Op::merge(acc, u.r);
     }
     acc = block_combine<Op>(acc, smem);
     if (fa.mode != 2) {
         if (threadIdx.x == 0) {
-            localize_record(acc, fa, x0);
+            localize_record(acc, fa, x0_bits, x0_nan);
             if (fa.mode == 0) finish_record(acc, fa);
             else *fa.rec_out = acc;
         }
@@ -598,21 +704,21 @@ __device__ __forceinline__ void grid_finish(Record r, Record *partials, unsigned
     __shared__ Record mine;
     __shared__ Record all[kMaxRanks];
     __shared__ int timed_out;
-    if (threadIdx.x == 0) { localize_record(acc, fa, x0); mine = acc; timed_out = 0; }
+    if (threadIdx.x == 0) { localize_record(acc, fa, x0_bits, x0_nan); mine = acc; timed_out = 0; }
     __syncthreads();
     const unsigned par = fa.seq & 1u;
     const unsigned *words = reinterpret_cast<const unsigned *>(&mine);
-    for (int t = threadIdx.x; t < fa.nranks * 8; t += blockDim.x) {      // push: one 8-byte store per word per peer
-        const int peer = t >> 3, w = t & 7;
-        unsigned long long *dst = fa.peers[peer] + ((par * kMaxRanks + fa.rank) << 3) + w;
-        const unsigned long long v = ((unsigned long long)fa.seq << 32) | words[w];
+    for (int t = threadIdx.x; t < fa.nranks * kRecordWords; t += blockDim.x) {   // push: one 8-byte store per word per peer
+        const int peer = t / kRecordWords, w = t % kRecordWords;
+        u64 *dst = fa.peers[peer] + (par * kMaxRanks + fa.rank) * kMailboxSlot + w;
+        const u64 v = ((u64)fa.seq << 32) | words[w];
         asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
     }
-    const unsigned long long t_start = global_timer_ns();
-    for (int t = threadIdx.x; t < fa.nranks * 8; t += blockDim.x) {      // pull: poll this GPU's mailbox
-        const int src = t >> 3, w = t & 7;
-        const unsigned long long *slot = fa.peers[fa.rank] + ((par * kMaxRanks + src) << 3) + w;
-        unsigned long long v;
+    const u64 t_start = global_timer_ns();
+    for (int t = threadIdx.x; t < fa.nranks * kRecordWords; t += blockDim.x) {   // pull: poll this GPU's mailbox
+        const int src = t / kRecordWords, w = t % kRecordWords;
+        const u64 *slot = fa.peers[fa.rank] + (par * kMaxRanks + src) * kMailboxSlot + w;
+        u64 v;
         for (;;) {
             asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
             if ((unsigned)(v >> 32) == fa.seq) break;
@@ -623,41 +729,53 @@ __device__ __forceinline__ void grid_finish(Record r, Record *partials, unsigned
     __syncthreads();
     if (threadIdx.x == 0) {
         if (timed_out) *fa.error_flag = 1;
-        Record total = fold_by_kind(all, fa.nranks, fa.kind);
-        finish_record(total, fa);
+        finish_record(fold_by_kind(all, fa.nranks, fa.kind), fa);
     }
 }
 
 template <class Op, int VEC, bool REV = false>
-__device__ __forceinline__ void pack_step(typename Op::Acc &acc, const Pack<VEC> &x, const Pack<VEC> &y, unsigned ord0)
+__device__ __forceinline__ void pack_step(typename Op::Acc &acc, const Pack<typename Op::Scalar, VEC> &x,
+                                          const Pack<typename Op::Scalar, VEC> &y, unsigned ord0)
 {
+    using T = typename Op::Scalar;
     if constexpr (Op::HAS_PACK_STEP) Op::template step_pack<VEC>(acc, x, y, ord0);
     else {
 #pragma unroll
-        for (int l = 0; l < VEC; ++l) Op::step(acc, x.v[l], Op::TWO ? y.v[REV ? VEC - 1 - l : l] : 0.f, ord0 + l);
+        for (int l = 0; l < VEC; ++l) Op::step(acc, x.v[l], Op::TWO ? y.v[REV ? VEC - 1 - l : l] : T(0), ord0 + l);
     }
 }
 
-// reduce, unit stride.  idx_base = global logical index of element 0 of this shard (isamax).
+template <class T> __device__ __forceinline__ void read_x0(const FinishArgs &fa, u64 &bits, bool &is_nan)
+{
+    bits = 0; is_nan = false;
+    if (fa.x0 != nullptr) {
+        const T v = *reinterpret_cast<const T *>(fa.x0);
+        bits = abs_bits(v); is_nan = (v != v);
+    }
+}
+
+// reduce, unit stride.  idx_base = global logical index of element 0 of this shard (iamax).
 template <class Op, int VEC, int UNROLL, int POLICY, bool REV = false>
 __global__ void __launch_bounds__(kMaxThreads)
-reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base,
+reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i64 head, i64 n, i64 idx_base,
                    Record *partials, unsigned *ticket, FinishArgs fa)
 {
+    using T = typename Op::Scalar;
     constexpr int YS = REV ? -1 : 1;     // REV: element i pairs x[i] with y[n-1-i] (see map_unit_kernel)
     __shared__ Record smem[32];
     const i64 body = n - head;
     const i64 npack = body / VEC;
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
-    const float *bx = x + head, *by = REV ? y + (n - head) - VEC : y + head;
-    const float x0 = fa.x0 != nullptr ? *fa.x0 : 0.f;   // read now: a PDL secondary may overwrite x later
+    const T *bx = x + head, *by = REV ? y + (n - head) - VEC : y + head;
+    u64 x0_bits; bool x0_nan;
+    read_x0<T>(fa, x0_bits, x0_nan);     // read now: a PDL secondary may overwrite x later
 
     typename Op::Acc acc = Op::zero();
     unsigned it = 0;
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const i64 p0 = tile * per_tile + threadIdx.x;
-        Pack<VEC> xv[UNROLL], yv[UNROLL];
+        Pack<T, VEC> xv[UNROLL], yv[UNROLL];
         if (p0 + (i64)(UNROLL - 1) * blockDim.x < npack) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -680,69 +798,54 @@ reduce_unit_kernel(const float *x, const float *y, i64 head, i64 n, i64 idx_base
             }
         }
     }
-    Record r = empty_record<Op>();
+    Record r = empty_record();
     if (blockIdx.x == 0) {      // scalar head and tail
         const i64 tail0 = head + npack * VEC;
         const i64 nscalar = head + (n - tail0);
         for (i64 t = threadIdx.x; t < nscalar; t += blockDim.x) {
             const i64 e = t < head ? t : tail0 + (t - head);
-            Op::single(r, x[e], Op::TWO ? y[REV ? n - 1 - e : e] : 0.f, idx_base + e);
+            Op::single(r, x[e], Op::TWO ? y[REV ? n - 1 - e : e] : T(0), idx_base + e);
         }
     }
     pdl_launch_dependents();    // every load of this block has been issued and consumed
     if constexpr (Op::IS_IAMAX) {
-        if (acc.val >= 0.f) {    // saw >= 1 non-NaN element; ordinal -> global index
+        if (acc.val >= T(0)) {    // saw >= 1 non-NaN element; ordinal -> global index
             const unsigned per = UNROLL * VEC;
             const unsigned iter = acc.ord / per, rem = acc.ord % per, u = rem / VEC, l = rem % VEC;
             const i64 tile = (i64)blockIdx.x + (i64)iter * gridDim.x;
-            Record v = empty_record<Op>();
-            v.key = __float_as_uint(acc.val);
+            Record v = empty_record();
+            v.key = abs_bits(acc.val);
             v.idx = idx_base + head + ((tile * UNROLL + u) * blockDim.x + threadIdx.x) * VEC + l;
             r = Op::merge(v, r);
         }
     } else {
-        Record v = empty_record<Op>();
+        Record v = empty_record();
         Op::to_record(v, acc);
         r = Op::merge(v, r);
     }
-    grid_finish<Op>(r, partials, ticket, fa, smem, x0);
+    grid_finish<Op>(r, partials, ticket, fa, smem, x0_bits, x0_nan);
 }
 
 // reduce, any increments: logical element i at x[kx0 + i*incx] (, y[ky0 + i*incy]).
 template <class Op>
 __global__ void __launch_bounds__(256)
-reduce_strided_kernel(const float *x, i64 incx, i64 kx0, const float *y, i64 incy, i64 ky0, i64 n,
+reduce_strided_kernel(const typename Op::Scalar *x, i64 incx, i64 kx0, const typename Op::Scalar *y, i64 incy, i64 ky0, i64 n,
                       i64 idx_base, Record *partials, unsigned *ticket, FinishArgs fa)
 {
+    using T = typename Op::Scalar;
     __shared__ Record smem[32];
-    const float x0 = fa.x0 != nullptr ? *fa.x0 : 0.f;
-    Record r = empty_record<Op>();
+    u64 x0_bits; bool x0_nan;
+    read_x0<T>(fa, x0_bits, x0_nan);
+    Record r = empty_record();
     // a plain grid-stride loop: the compiler unrolls it four times with the loads hoisted, which measured
     // faster than explicit tiling (ptxas interleaves predicated tile loads with their uses)
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        Op::single(r, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : 0.f, idx_base + i);
+        Op::single(r, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : T(0), idx_base + i);
     pdl_launch_dependents();
-    grid_finish<Op>(r, partials, ticket, fa, smem, x0);
+    grid_finish<Op>(r, partials, ticket, fa, smem, x0_bits, x0_nan);
 }
 
-// Cross-GPU finish: every rank holds all ranks' records (rank order) and folds them identically.
-template <class Op>
-__host__ __device__ __forceinline__ Record fold_ranks(const Record *recs, int nranks)
-{
-    Record acc = recs[0];
-    for (int r = 1; r < nranks; ++r) acc = Op::merge(acc, recs[r]);
-    return acc;
-}
-__device__ __forceinline__ Record fold_by_kind(const Record *recs, int nranks, int kind)
-{
-    Record acc;
-    if (kind == 2) acc = fold_ranks<IamaxOp>(recs, nranks);
-    else if (kind == 1) { acc = fold_ranks<Nrm2Op>(recs, nranks); acc.key = recs[0].key; }   // |x[0]| travels in rank 0's key
-    else if (kind == 3) acc = fold_ranks<DsdotOp>(recs, nranks);
-    else acc = fold_ranks<DotOp>(recs, nranks);
-    return acc;
-}
 __global__ void finish_records_kernel(const Record *recs, int nranks, FinishArgs fa)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -752,28 +855,29 @@ __global__ void finish_records_kernel(const Record *recs, int nranks, FinishArgs
 // ------------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------------
-__global__ void store_f32_kernel(float *out, float v) { if (threadIdx.x == 0 && blockIdx.x == 0) *out = v; }
-__global__ void store_i64_kernel(i64 *out, i64 v) { if (threadIdx.x == 0 && blockIdx.x == 0) *out = v; }
+template <class T> __global__ void store_scalar_kernel(T *out, T v) { if (threadIdx.x == 0 && blockIdx.x == 0) *out = v; }
 
-__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z)
+__host__ __device__ __forceinline__ u64 splitmix64(u64 z)
 {
     z += 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
-// v[i] = lo + span * u,  u = top 24 bits of splitmix64(seed * 2^40 + global_i) scaled by 2^-24
+// v[i] = lo + span * u,  u = top 24 bits of splitmix64(seed * 2^40 + global_i) scaled by 2^-24, in T arithmetic
+template <class T>
 __global__ void __launch_bounds__(256)
-fill_hash_kernel(float *v, i64 n, i64 idx_base, unsigned long long seed, float lo, float span)
+fill_hash_kernel(T *v, i64 n, i64 idx_base, u64 seed, T lo, T span)
 {
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned long long h = splitmix64((seed << 40) + (unsigned long long)(idx_base + i));
-        const float u = (float)(h >> 40) * 5.9604644775390625e-8f;   // exact: 24 bits * 2^-24
-        v[i] = __fadd_rn(lo, __fmul_rn(span, u));
+        const u64 h = splitmix64((seed << 40) + (u64)(idx_base + i));
+        const T u = (T)(h >> 40) * (T)5.9604644775390625e-8;   // exact: 24 bits * 2^-24
+        v[i] = add_rn(lo, mul_rn(span, u));
     }
 }
-__global__ void __launch_bounds__(256) fill_kernel(float *v, i64 n, float value)
+template <class T>
+__global__ void __launch_bounds__(256) fill_kernel(T *v, i64 n, T value)
 {
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = value;

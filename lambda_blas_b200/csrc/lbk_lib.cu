@@ -27,7 +27,8 @@ using lbk::FinishArgs;
 static_assert(sizeof(lbk_record) == sizeof(Record), "host and device records share a layout");
 
 // ------------------------------------------------------------------------------------------------
-// launch variants: (VEC floats per access, UNROLL accesses in flight per operand, cache POLICY)
+// launch variants: (VEC floats per access = 4/16/32 bytes, UNROLL accesses in flight per operand, cache POLICY);
+// for double vectors the same variant moves the same bytes (VEC/2 elements)
 // ------------------------------------------------------------------------------------------------
 #define LBK_VARIANTS(X) \
     X(0, 4, 4, 1) X(1, 4, 2, 1) X(2, 4, 8, 1) X(3, 8, 2, 1) X(4, 8, 4, 1) X(5, 4, 4, 0) \
@@ -38,18 +39,18 @@ constexpr int kNumVariants = 15;
 constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
 
-enum Routine { R_SDOT, R_SDSDOT, R_SASUM, R_SNRM2, R_ISAMAX, R_SAXPY, R_SSCAL, R_SCOPY, R_SSWAP, R_SROT, R_SROTM, R_COUNT };
-static const char *kRoutineNames[R_COUNT] = {"sdot", "sdsdot", "sasum", "snrm2", "isamax", "saxpy",
-                                             "sscal", "scopy", "sswap", "srot", "srotm"};
+// launch shapes are per routine and shared by the Float and Double instances (they are in bytes per access)
+enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_COUNT };
+static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm"};
 struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
 // Defaults from the n = 2^28 sweeps on B200 (profiles/r01_tune_*.csv; tools/tune.py), reductions tuned
 // with their tails overlapped (PDL).  blocks_per_sm 0 = one resident wave (occupancy x SMs); larger
 // values oversubscribe the SMs and let the hardware block scheduler balance the load.
 static const LaunchCfg kDefaultCfg[R_COUNT] = {
-    /* sdot   */ {3, 512, 8},   /* sdsdot */ {3, 512, 8},   /* sasum  */ {10, 512, 0},
-    /* snrm2  */ {4, 256, 8},   /* isamax */ {0, 512, 8},   /* saxpy  */ {4, 128, 64},
-    /* sscal  */ {4, 256, 32},  /* scopy  */ {4, 256, 32},  /* sswap  */ {4, 128, 64},
-    /* srot   */ {4, 128, 64},  /* srotm  */ {4, 128, 64},
+    /* dot  */ {3, 512, 8},   /* sdsdot */ {3, 512, 8},   /* asum */ {10, 512, 0},
+    /* nrm2 */ {4, 256, 8},   /* iamax  */ {0, 512, 8},   /* axpy */ {4, 128, 64},
+    /* scal */ {4, 256, 32},  /* copy   */ {4, 256, 32},  /* swap */ {4, 128, 64},
+    /* rot  */ {4, 128, 64},  /* rotm   */ {4, 128, 64},
 };
 
 constexpr int kMaxGrid = 148 * 32 * 2;   // partial-record scratch (blocks)
@@ -60,7 +61,7 @@ struct lbk_ctx {
     cudaStream_t stream = nullptr;
     Record *partials = nullptr;
     unsigned *ticket = nullptr;
-    float *snap = nullptr;            // two floats: snapshots of x[0], y[0] for zero output increments
+    double *snap = nullptr;           // two slots: snapshots of x[0], y[0] for zero output increments
     void *result_host = nullptr;      // mapped pinned 64 bytes: where synchronous reductions land
     void *result_dev = nullptr;
     Record *rec_send = nullptr;       // this rank's record
@@ -87,13 +88,15 @@ struct lbk_ctx {
 
 struct lbk_vec {
     lbk_ctx *ctx;
-    float *ptr;
-    i64 len;          // local length
+    char *ptr;
+    i64 len;          // local length, in elements
     i64 global_len;   // == len unless sharded
     i64 shard_off;    // global index of local element 0
     bool owner;
     bool sharded;
+    int dtype;        // 0: float (Vector Float), 1: double (Vector Double)
 };
+static inline int esz(int dtype) { return dtype ? 8 : 4; }
 
 struct lbk_event { lbk_ctx *ctx; cudaEvent_t ev; };
 
@@ -194,7 +197,7 @@ extern "C" int lbk_init(int device, lbk_ctx **out)
     INIT(cudaMalloc(&c->partials, sizeof(Record) * kMaxGrid));
     INIT(cudaMalloc(&c->ticket, sizeof(unsigned)));
     INIT(cudaMemset(c->ticket, 0, sizeof(unsigned)));
-    INIT(cudaMalloc(&c->snap, 2 * sizeof(float)));
+    INIT(cudaMalloc(&c->snap, 2 * sizeof(double)));
     INIT(cudaHostAlloc(&c->result_host, 64, cudaHostAllocMapped));
     INIT(cudaHostGetDevicePointer(&c->result_dev, c->result_host, 0));
     INIT(cudaHostAlloc((void **)&c->error_flag_host, sizeof(int), cudaHostAllocMapped));
@@ -258,6 +261,13 @@ extern "C" int lbk_set_launch(lbk_ctx *c, const char *routine, int variant, int 
     if (variant >= kNumVariants) return fail(c, LBK_ERR_ARG, "lbk_set_launch: no such variant");
     if (threads > lbk::kMaxThreads || (threads > 0 && threads % 32 != 0))
         return fail(c, LBK_ERR_ARG, "lbk_set_launch: threads must be a multiple of 32, at most 512");
+    // the BLAS spellings name the same shapes: sdot/ddot -> dot, isamax/idamax -> iamax, ...
+    std::string name(routine);
+    if (name != "sdsdot" && name != "all") {
+        if (name.size() > 2 && name[0] == 'i' && (name[1] == 's' || name[1] == 'd')) name = "i" + name.substr(2);
+        else if (name.size() > 1 && (name[0] == 's' || name[0] == 'd') && name != "scal" && name != "swap" && name != "dot") name = name.substr(1);
+    }
+    routine = name.c_str();
     for (int r = 0; r < R_COUNT; ++r)
         if (!strcmp(routine, kRoutineNames[r]) || !strcmp(routine, "all")) {
             c->cfg[r] = LaunchCfg{variant >= 0 ? variant : kDefaultCfg[r].variant, threads > 0 ? threads : kDefaultCfg[r].threads,
@@ -401,53 +411,56 @@ extern "C" int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t
 // ------------------------------------------------------------------------------------------------
 // vectors
 // ------------------------------------------------------------------------------------------------
-static int make_vec(lbk_ctx *c, float *ptr, i64 len, i64 glen, i64 off, bool owner, bool sharded, lbk_vec **out)
+static int make_vec(lbk_ctx *c, void *ptr, i64 len, i64 glen, i64 off, bool owner, bool sharded, int dtype, lbk_vec **out)
 {
-    lbk_vec *v = new (std::nothrow) lbk_vec{c, ptr, len, glen, off, owner, sharded};
+    lbk_vec *v = new (std::nothrow) lbk_vec{c, (char *)ptr, len, glen, off, owner, sharded, dtype};
     if (!v) return fail(c, LBK_ERR_NOMEM, "out of host memory");
     *out = v;
     return LBK_OK;
 }
 
-extern "C" int lbk_vec_alloc(lbk_ctx *c, int64_t len, lbk_vec **out)
+static int alloc_common(lbk_ctx *c, const char *who, i64 len, i64 glen, i64 off, bool sharded, int dtype, lbk_vec **out)
 {
-    if (!c || !out || len < 0) return fail(c, LBK_ERR_ARG, "lbk_vec_alloc: bad argument");
     CU(c, cudaSetDevice(c->device));
-    float *p = nullptr;
+    void *p = nullptr;
     if (len > 0) {
-        cudaError_t e = cudaMalloc(&p, sizeof(float) * (size_t)len);
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, LBK_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+        cudaError_t e = cudaMalloc(&p, (size_t)esz(dtype) * (size_t)len);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, LBK_ERR_NOMEM, std::string(who) + ": cudaMalloc: " + cudaGetErrorString(e)); }
     }
-    return make_vec(c, p, len, len, 0, true, false, out);
+    return make_vec(c, p, len, glen, off, true, sharded, dtype, out);
 }
 
-extern "C" int lbk_vec_alloc_sharded(lbk_ctx *c, int64_t global_len, lbk_vec **out)
+static int vec_alloc(lbk_ctx *c, int64_t len, int dtype, lbk_vec **out)
+{
+    if (!c || !out || len < 0) return fail(c, LBK_ERR_ARG, "lbk_vec_alloc: bad argument");
+    return alloc_common(c, "lbk_vec_alloc", len, len, 0, false, dtype, out);
+}
+static int vec_alloc_sharded(lbk_ctx *c, int64_t global_len, int dtype, lbk_vec **out)
 {
     if (!c || !out || global_len < 0) return fail(c, LBK_ERR_ARG, "lbk_vec_alloc_sharded: bad argument");
     int64_t lo, hi;
     lbk_shard_range(global_len, c->nranks, c->rank, &lo, &hi);
-    CU(c, cudaSetDevice(c->device));
-    float *p = nullptr;
-    if (hi > lo) {
-        cudaError_t e = cudaMalloc(&p, sizeof(float) * (size_t)(hi - lo));
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, LBK_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
-    }
-    return make_vec(c, p, hi - lo, global_len, lo, true, c->nranks > 1, out);
+    return alloc_common(c, "lbk_vec_alloc_sharded", hi - lo, global_len, lo, c->nranks > 1, dtype, out);
 }
-
-extern "C" int lbk_vec_wrap(lbk_ctx *c, void *device_ptr, int64_t len, lbk_vec **out)
+static int vec_wrap(lbk_ctx *c, void *device_ptr, int64_t len, int dtype, lbk_vec **out)
 {
-    if (!c || !out || len < 0 || (len > 0 && !device_ptr) || ((uintptr_t)device_ptr & 3))
-        return fail(c, LBK_ERR_ARG, "lbk_vec_wrap: bad argument (null, negative or not 4-byte aligned)");
-    return make_vec(c, (float *)device_ptr, len, len, 0, false, false, out);
+    if (!c || !out || len < 0 || (len > 0 && !device_ptr) || ((uintptr_t)device_ptr & (uintptr_t)(esz(dtype) - 1)))
+        return fail(c, LBK_ERR_ARG, "lbk_vec_wrap: bad argument (null, negative or not element aligned)");
+    return make_vec(c, device_ptr, len, len, 0, false, false, dtype, out);
 }
+extern "C" int lbk_vec_alloc(lbk_ctx *c, int64_t len, lbk_vec **out) { return vec_alloc(c, len, 0, out); }
+extern "C" int lbk_vec_alloc_f64(lbk_ctx *c, int64_t len, lbk_vec **out) { return vec_alloc(c, len, 1, out); }
+extern "C" int lbk_vec_alloc_sharded(lbk_ctx *c, int64_t glen, lbk_vec **out) { return vec_alloc_sharded(c, glen, 0, out); }
+extern "C" int lbk_vec_alloc_sharded_f64(lbk_ctx *c, int64_t glen, lbk_vec **out) { return vec_alloc_sharded(c, glen, 1, out); }
+extern "C" int lbk_vec_wrap(lbk_ctx *c, void *p, int64_t len, lbk_vec **out) { return vec_wrap(c, p, len, 0, out); }
+extern "C" int lbk_vec_wrap_f64(lbk_ctx *c, void *p, int64_t len, lbk_vec **out) { return vec_wrap(c, p, len, 1, out); }
 
 extern "C" int lbk_vec_view(const lbk_vec *v, int64_t offset, int64_t len, lbk_vec **out)
 {
     if (!v || !out || offset < 0 || len < 0 || offset + len > v->len)
         return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_view: window outside the vector");
     if (v->sharded) return fail(v->ctx, LBK_ERR_UNSUPPORTED, "lbk_vec_view: views of sharded vectors are not supported");
-    return make_vec(v->ctx, v->ptr + offset, len, len, 0, false, false, out);
+    return make_vec(v->ctx, v->ptr + offset * esz(v->dtype), len, len, 0, false, false, v->dtype, out);
 }
 
 extern "C" int lbk_vec_free(lbk_vec *v)
@@ -470,27 +483,27 @@ extern "C" int lbk_vec_len(const lbk_vec *v, int64_t *local_len, int64_t *global
     if (shard_offset) *shard_offset = v->shard_off;
     return LBK_OK;
 }
-
+extern "C" int lbk_vec_elem_size(const lbk_vec *v) { return v ? esz(v->dtype) : 0; }
 extern "C" void *lbk_vec_ptr(const lbk_vec *v) { return v ? (void *)v->ptr : nullptr; }
 
-extern "C" int lbk_vec_upload_async(lbk_vec *v, const float *host, int64_t len)
+extern "C" int lbk_vec_upload_async(lbk_vec *v, const void *host, int64_t len)
 {
     if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_upload: bad argument");
-    if (len) { v->ctx->tail_open = false; CU(v->ctx, cudaMemcpyAsync(v->ptr, host, sizeof(float) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream)); }
+    if (len) { v->ctx->tail_open = false; CU(v->ctx, cudaMemcpyAsync(v->ptr, host, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream)); }
     return LBK_OK;
 }
-extern "C" int lbk_vec_upload(lbk_vec *v, const float *host, int64_t len)
+extern "C" int lbk_vec_upload(lbk_vec *v, const void *host, int64_t len)
 {
     int s = lbk_vec_upload_async(v, host, len);
     return s ? s : lbk_sync(v->ctx);
 }
-extern "C" int lbk_vec_download_async(const lbk_vec *v, float *host, int64_t len)
+extern "C" int lbk_vec_download_async(const lbk_vec *v, void *host, int64_t len)
 {
     if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_download: bad argument");
-    if (len) { v->ctx->tail_open = false; CU(v->ctx, cudaMemcpyAsync(host, v->ptr, sizeof(float) * (size_t)len, cudaMemcpyDeviceToHost, v->ctx->stream)); }
+    if (len) { v->ctx->tail_open = false; CU(v->ctx, cudaMemcpyAsync(host, v->ptr, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyDeviceToHost, v->ctx->stream)); }
     return LBK_OK;
 }
-extern "C" int lbk_vec_download(const lbk_vec *v, float *host, int64_t len)
+extern "C" int lbk_vec_download(const lbk_vec *v, void *host, int64_t len)
 {
     int s = lbk_vec_download_async(v, host, len);
     return s ? s : lbk_sync(v->ctx);
@@ -500,12 +513,12 @@ extern "C" int lbk_vec_clone(const lbk_vec *v, lbk_vec **out)
 {
     if (!v || !out) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_clone: null argument");
     lbk_vec *w = nullptr;
-    int s = lbk_vec_alloc(v->ctx, v->len, &w);
+    int s = vec_alloc(v->ctx, v->len, v->dtype, &w);
     if (s) return s;
     w->global_len = v->global_len; w->shard_off = v->shard_off; w->sharded = v->sharded;
     if (v->len) {
         v->ctx->tail_open = false;
-        cudaError_t e = cudaMemcpyAsync(w->ptr, v->ptr, sizeof(float) * (size_t)v->len, cudaMemcpyDeviceToDevice, v->ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(w->ptr, v->ptr, (size_t)esz(v->dtype) * (size_t)v->len, cudaMemcpyDeviceToDevice, v->ctx->stream);
         if (e != cudaSuccess) { lbk_vec_free(w); return fail(v->ctx, LBK_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e)); }
     }
     *out = w;
@@ -514,39 +527,43 @@ extern "C" int lbk_vec_clone(const lbk_vec *v, lbk_vec **out)
 
 static int stream_grid(lbk_ctx *c, i64 n, int threads) { return (int)std::max<i64>(1, std::min<i64>((n + threads - 1) / threads, (i64)c->sms * 16)); }
 
-extern "C" int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, float lo, float hi)
+extern "C" int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, double lo, double hi)
 {
     if (!v) return fail(nullptr, LBK_ERR_ARG, "lbk_vec_fill_hash: null vector");
     if (!v->len) return LBK_OK;
     lbk_ctx *c = v->ctx;
     CU(c, cudaSetDevice(c->device));
     c->tail_open = false;
-    lbk::fill_hash_kernel<<<stream_grid(c, v->len, 256), 256, 0, c->stream>>>(v->ptr, v->len, v->shard_off, seed, lo, hi - lo);
+    const int grid = stream_grid(c, v->len, 256);
+    if (v->dtype) lbk::fill_hash_kernel<double><<<grid, 256, 0, c->stream>>>((double *)v->ptr, v->len, v->shard_off, seed, lo, hi - lo);
+    else lbk::fill_hash_kernel<float><<<grid, 256, 0, c->stream>>>((float *)v->ptr, v->len, v->shard_off, seed, (float)lo, (float)hi - (float)lo);
     KERNEL_CHECK(c);
     return LBK_OK;
 }
-extern "C" int lbk_vec_fill(lbk_vec *v, float value)
+extern "C" int lbk_vec_fill(lbk_vec *v, double value)
 {
     if (!v) return fail(nullptr, LBK_ERR_ARG, "lbk_vec_fill: null vector");
     if (!v->len) return LBK_OK;
     lbk_ctx *c = v->ctx;
     CU(c, cudaSetDevice(c->device));
     c->tail_open = false;
-    lbk::fill_kernel<<<stream_grid(c, v->len, 256), 256, 0, c->stream>>>(v->ptr, v->len, value);
+    const int grid = stream_grid(c, v->len, 256);
+    if (v->dtype) lbk::fill_kernel<double><<<grid, 256, 0, c->stream>>>((double *)v->ptr, v->len, value);
+    else lbk::fill_kernel<float><<<grid, 256, 0, c->stream>>>((float *)v->ptr, v->len, (float)value);
     KERNEL_CHECK(c);
     return LBK_OK;
 }
 
-extern "C" int lbk_host_alloc(int64_t nfloats, float **host)
+extern "C" int lbk_host_alloc(int64_t nbytes, void **host)
 {
-    if (!host || nfloats < 0) return fail(nullptr, LBK_ERR_ARG, "lbk_host_alloc: bad argument");
+    if (!host || nbytes < 0) return fail(nullptr, LBK_ERR_ARG, "lbk_host_alloc: bad argument");
     *host = nullptr;
-    if (nfloats == 0) return LBK_OK;
-    cudaError_t e = cudaHostAlloc((void **)host, sizeof(float) * (size_t)nfloats, cudaHostAllocDefault);
+    if (nbytes == 0) return LBK_OK;
+    cudaError_t e = cudaHostAlloc(host, (size_t)nbytes, cudaHostAllocDefault);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, LBK_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
     return LBK_OK;
 }
-extern "C" int lbk_host_free(float *host)
+extern "C" int lbk_host_free(void *host)
 {
     if (host) CU(nullptr, cudaFreeHost(host));
     return LBK_OK;
@@ -603,10 +620,11 @@ struct Operand {
 };
 
 // Validates one operand for a call over n logical elements and resolves sharding.
-static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, i64 inc, i64 n, Operand *op)
+static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, int dtype, i64 inc, i64 n, Operand *op)
 {
     if (!v) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
     if (v->ctx != c) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
+    if (v->dtype != dtype) return fail(c, LBK_ERR_ARG, std::string(who) + (dtype ? ": needs a double-precision vector" : ": needs a single-precision vector"));
     op->v = v; op->inc = inc; op->i0 = 0; op->n_local = n;
     if (n <= 0) { op->n_local = 0; return LBK_OK; }
     if (v->sharded) {
@@ -623,54 +641,71 @@ static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, i64 inc,
 }
 
 // touched byte range [lo, hi) of an operand
-static void touched(const Operand &o, const float **lo, const float **hi)
+static void touched(const Operand &o, const char **lo, const char **hi)
 {
     const i64 n = o.n_local;
     *lo = o.v->ptr;
-    *hi = o.v->ptr + (n > 0 ? 1 + (n - 1) * iabs64(o.inc) : 0);
+    *hi = o.v->ptr + (n > 0 ? 1 + (n - 1) * iabs64(o.inc) : 0) * esz(o.v->dtype);
 }
-static bool overlap(const Operand &a, const Operand &b)
+template <class T> static inline int misalign(const T *p, int vec) { return (int)(((uintptr_t)p / sizeof(T)) % (uintptr_t)vec); }
+// elements per access of a variant for element type T: the table is in floats (4/16/32 bytes)
+template <class T> static inline int variant_vec(int variant)
 {
-    const float *al, *ah, *bl, *bh;
-    touched(a, &al, &ah); touched(b, &bl, &bh);
-    return al < bh && bl < ah;
+    const int f = kVariantVec[variant];
+    return sizeof(T) == 4 ? f : (f > 1 ? f / 2 : 1);
 }
-
-static inline int misalign(const float *p, int vec) { return (int)(((uintptr_t)p >> 2) % (uintptr_t)vec); }
 
 // Picks the variant that the pointers' alignment allows and the scalar head count.
-static void resolve_alignment(int *variant, i64 *head, const float *const *ptrs, int nptr, i64 n)
+template <class T>
+static void resolve_alignment(int *variant, i64 *head, const T *const *ptrs, int nptr, i64 n)
 {
     for (;;) {
-        const int vec = kVariantVec[*variant];
+        const int vec = variant_vec<T>(*variant);
         if (vec == 1) { *head = 0; return; }
         const int m = misalign(ptrs[0], vec);
         bool same = true;
         for (int i = 1; i < nptr; ++i) same = same && misalign(ptrs[i], vec) == m;
         if (same) { *head = std::min<i64>((vec - m) % vec, n); return; }
-        *variant = (vec == 8) ? kVec4Fallback : kScalarVariant;
+        *variant = (kVariantVec[*variant] == 8) ? kVec4Fallback : kScalarVariant;
     }
+}
+// Reversed pairing: x+head and (y+n)-head must both be pack aligned; otherwise the scalar shape is used.
+template <class T>
+static void resolve_alignment_rev(int *variant, i64 *head, const T *const *xptrs, int nx, const T *const *yptrs, int ny, i64 n)
+{
+    const int vec = variant_vec<T>(kVec4Fallback);
+    const int m = misalign(xptrs[0], vec);
+    const i64 h = (vec - m) % vec;          // x + h is aligned; y + n - h must be too  <=>  misalign(y + n) == h
+    bool ok = h <= n;
+    for (int i = 0; i < nx; ++i) ok = ok && misalign(xptrs[i], vec) == m;
+    for (int i = 0; i < ny; ++i) ok = ok && misalign(yptrs[i] + n, vec) == (int)h;
+    if (ok) { *variant = kVec4Fallback; *head = h; }      // 16-byte packs, UNROLL 4
+    else { *variant = kScalarVariant; *head = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
 // map launchers
 // ------------------------------------------------------------------------------------------------
+template <class T> constexpr int vec_t(int vec_f32) { return sizeof(T) == 4 ? vec_f32 : (vec_f32 > 1 ? vec_f32 / 2 : 1); }
+
 template <class F>
 static const void *map_kernel_ptr(int variant)
 {
+    using T = typename F::Scalar;
     switch (variant) {
-#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::map_unit_kernel<F, VEC, UNROLL, POLICY>;
+#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::map_unit_kernel<F, vec_t<T>(VEC), UNROLL, POLICY>;
         LBK_VARIANTS(X)
 #undef X
     }
     return nullptr;
 }
-// the reversed pairing is built for two shapes only: (VEC 4, UNROLL 4) and the any-alignment scalar one
+// the reversed pairing is built for two shapes only: 16-byte packs x UNROLL 4, and the any-alignment scalar one
 template <class F>
 static const void *map_kernel_ptr_rev(int variant)
 {
+    using T = typename F::Scalar;
     return variant == kScalarVariant ? (const void *)lbk::map_unit_kernel<F, 1, 4, 1, true>
-                                     : (const void *)lbk::map_unit_kernel<F, 4, 4, 1, true>;
+                                     : (const void *)lbk::map_unit_kernel<F, vec_t<T>(4), 4, 1, true>;
 }
 static int variant_unroll(int variant)
 {
@@ -697,11 +732,11 @@ static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int th
 // Launches a unit-stride kernel, as a PDL secondary when the preceding reduction's tail is still open
 // and none of this kernel's operands overlaps what that tail writes.
 static int launch_stream_kernel(lbk_ctx *c, const void *k, int grid, int threads, void **args,
-                                const float *const *ptrs, const i64 *lens, int nptr)
+                                const void *const *ptrs, const i64 *nbytes, int nptr)
 {
     bool pdl = c->tail_open && c->pdl_enabled;
     for (int i = 0; pdl && i < nptr; ++i) {
-        const char *lo = (const char *)ptrs[i], *hi = lo + 4 * lens[i];
+        const char *lo = (const char *)ptrs[i], *hi = lo + nbytes[i];
         if (ptrs[i] && lo < c->tail_hi && c->tail_lo < hi) pdl = false;
     }
     cudaLaunchConfig_t lc = {};
@@ -717,60 +752,50 @@ static int launch_stream_kernel(lbk_ctx *c, const void *k, int grid, int threads
     return LBK_OK;
 }
 
-// Reversed pairing: x+head and (y+n)-head must both be pack aligned; otherwise the scalar shape is used.
-static void resolve_alignment_rev(int *variant, i64 *head, const float *const *xptrs, int nx, const float *const *yptrs, int ny, i64 n)
-{
-    const int vec = 4;
-    const int m = misalign(xptrs[0], vec);
-    const i64 h = (vec - m) % vec;          // x + h is aligned; y + n - h must be too  <=>  misalign(y + n) == h
-    bool ok = h <= n;
-    for (int i = 0; i < nx; ++i) ok = ok && misalign(xptrs[i], vec) == m;
-    for (int i = 0; i < ny; ++i) ok = ok && misalign(yptrs[i] + n, vec) == (int)h;
-    if (ok) { *variant = kVec4Fallback; *head = h; }      // (VEC 4, UNROLL 4)
-    else { *variant = kScalarVariant; *head = 0; }
-}
-
 template <class F>
-static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const float *xr, const float *yr, float *xw, float *yw, i64 n, int default_variant, bool rev = false)
+static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Scalar *xr, const typename F::Scalar *yr,
+                           typename F::Scalar *xw, typename F::Scalar *yw, i64 n, bool rev = false)
 {
+    using T = typename F::Scalar;
     const LaunchCfg &cfg = c->cfg[rid];
-    int variant = cfg.variant >= 0 ? cfg.variant : default_variant;
+    int variant = cfg.variant;
     const int threads = cfg.threads > 0 ? cfg.threads : 256;
     i64 head = 0;
     const void *k;
     if (rev) {
-        const float *xp[2], *yp[2]; int nx = 0, ny = 0;
+        const T *xp[2], *yp[2]; int nx = 0, ny = 0;
         if (F::RX) xp[nx++] = xr;
         if (F::WX) xp[nx++] = xw;
         if (F::RY) yp[ny++] = yr;
         if (F::WY) yp[ny++] = yw;
-        resolve_alignment_rev(&variant, &head, xp, nx, yp, ny, n);
+        resolve_alignment_rev<T>(&variant, &head, xp, nx, yp, ny, n);
         k = map_kernel_ptr_rev<F>(variant);
     } else {
-        const float *ptrs[4]; int np = 0;
+        const T *ptrs[4]; int np = 0;
         if (F::RX) ptrs[np++] = xr;
         if (F::RY) ptrs[np++] = yr;
         if (F::WX) ptrs[np++] = xw;
         if (F::WY) ptrs[np++] = yw;
-        resolve_alignment(&variant, &head, ptrs, np, n);
+        resolve_alignment<T>(&variant, &head, ptrs, np, n);
         k = map_kernel_ptr<F>(variant);
     }
-    const i64 npack = (n - head) / kVariantVec[variant];
+    const i64 npack = (n - head) / variant_vec<T>(variant);
     const i64 per_tile = (i64)variant_unroll(variant) * threads;
     int grid;
     int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid);
     if (s) return s;
     F fc = f;
     void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n};
-    const float *ops[4] = {xr, yr, xw, yw};
-    const i64 lens[4] = {n, n, n, n};
+    const void *ops[4] = {xr, yr, xw, yw};
+    const i64 nb = n * (i64)sizeof(T);
+    const i64 lens[4] = {nb, nb, nb, nb};
     return launch_stream_kernel(c, k, grid, threads, args, ops, lens, 4);
 }
 
 template <class F>
-static int launch_map_strided(lbk_ctx *c, const F &f, const float *xr, float *xw, i64 incx_r, i64 incx_w, i64 kx0_r, i64 kx0_w,
-                              const float *yr, float *yw, i64 incy_r, i64 incy_w, i64 ky0_r, i64 ky0_w,
-                              i64 i_begin, i64 n, int x_last, int y_last)
+static int launch_map_strided(lbk_ctx *c, const F &f, const typename F::Scalar *xr, typename F::Scalar *xw, i64 incx_r, i64 incx_w,
+                              i64 kx0_r, i64 kx0_w, const typename F::Scalar *yr, typename F::Scalar *yw, i64 incy_r, i64 incy_w,
+                              i64 ky0_r, i64 ky0_w, i64 i_begin, i64 n, int x_last, int y_last)
 {
     const int threads = 256;
     const int grid = stream_grid(c, (n - i_begin + lbk::kStridedUnroll - 1) / lbk::kStridedUnroll, threads);
@@ -781,83 +806,98 @@ static int launch_map_strided(lbk_ctx *c, const F &f, const float *xr, float *xw
     return LBK_OK;
 }
 
-// In-place (xw == xr, yw == yr) or out-of-place update of n logical elements.  `xo`/`yo` are the
-// destinations; a destination that differs from its source must already hold a copy of the source
-// wherever this call does not write (map_entry arranges that).
+// In-place (xw == xr, yw == yr) or out-of-place update of n logical elements.  A destination that
+// differs from its source must already hold a copy of the source wherever this call does not write
+// (map_entry arranges that).
 template <class F>
-static int map_dispatch(lbk_ctx *c, int rid, const F &f, i64 n,
-                        const Operand &X, float *xw, const Operand &Y, float *yw, int default_variant)
+static int map_dispatch(lbk_ctx *c, int rid, const F &f, i64 n, const Operand &X, typename F::Scalar *xw,
+                        const Operand &Y, typename F::Scalar *yw)
 {
+    using T = typename F::Scalar;
     if (n <= 0) return LBK_OK;
     CU(c, cudaSetDevice(c->device));
     const bool use_x = F::RX || F::WX, use_y = F::RY || F::WY;
-    const float *xr = use_x ? X.v->ptr : nullptr;
-    const float *yr = use_y ? Y.v->ptr : nullptr;
+    const T *xr = use_x ? (const T *)X.v->ptr : nullptr;
+    const T *yr = use_y ? (const T *)Y.v->ptr : nullptr;
     const i64 incx = use_x ? X.inc : 1, incy = use_y ? Y.inc : 1;
     const i64 nl = use_x ? X.n_local : Y.n_local;   // sharded operands agree (checked by the caller)
     if (nl <= 0) return LBK_OK;
     // unit stride; (-1,-1) visits the same pairs in the opposite order, which an elementwise update cannot see
     const bool unit = (incx == 1 && incy == 1) || (use_x && use_y && incx == -1 && incy == -1) ||
                       (!use_y && incx == 1) || (!use_x && incy == 1);
-    if (unit) return launch_map_unit<F>(c, rid, f, xr, yr, xw, yw, nl, default_variant);
+    if (unit) return launch_map_unit<F>(c, rid, f, xr, yr, xw, yw, nl);
     // (1,-1) and (-1,1) pair x[k] with y[n-1-k]: the same set of pairs, handled by the reversed-lane unit kernel
     if (use_x && use_y && ((incx == 1 && incy == -1) || (incx == -1 && incy == 1)))
-        return launch_map_unit<F>(c, rid, f, xr, yr, xw, yw, nl, default_variant, true);
+        return launch_map_unit<F>(c, rid, f, xr, yr, xw, yw, nl, true);
 
     i64 kx0 = first_index(nl, incx), ky0 = first_index(nl, incy);
-    i64 incx_r = incx, incx_w = incx, incy_r = incy, incy_w = incy, kx0_r = kx0, ky0_r = ky0;
+    i64 kx0_r = kx0, ky0_r = ky0;
     int x_last = 0, y_last = 0;
+    T *snap = (T *)c->snap;
     if (F::WX && incx == 0) {            // n sequential writes to x[0]: the last wins, all read the original
         x_last = 1;
-        if (F::RX) { c->tail_open = false; CU(c, cudaMemcpyAsync(c->snap, xr, sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); xr = c->snap; kx0_r = 0; }
+        if (F::RX) { c->tail_open = false; CU(c, cudaMemcpyAsync(snap, xr, sizeof(T), cudaMemcpyDeviceToDevice, c->stream)); xr = snap; kx0_r = 0; }
     }
     if (F::WY && incy == 0) {
         y_last = 1;
-        if (F::RY) { c->tail_open = false; CU(c, cudaMemcpyAsync(c->snap + 1, yr, sizeof(float), cudaMemcpyDeviceToDevice, c->stream)); yr = c->snap + 1; ky0_r = 0; }
+        if (F::RY) { c->tail_open = false; CU(c, cudaMemcpyAsync(snap + 1, yr, sizeof(T), cudaMemcpyDeviceToDevice, c->stream)); yr = snap + 1; ky0_r = 0; }
     }
     const bool only_last = (!F::WX || x_last) && (!F::WY || y_last);
-    return launch_map_strided<F>(c, f, xr, xw, incx_r, incx_w, kx0_r, kx0, yr, yw, incy_r, incy_w, ky0_r, ky0,
+    return launch_map_strided<F>(c, f, xr, xw, incx, incx, kx0_r, kx0, yr, yw, incy, incy, ky0_r, ky0,
                                  only_last ? nl - 1 : 0, nl, x_last, y_last);
 }
 
 // Shared front end of the elementwise routines.  xo / yo: optional out-of-place destinations.
 template <class F>
 static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
-                     const lbk_vec *x, i64 incx, const lbk_vec *y, i64 incy,
-                     lbk_vec *xo, lbk_vec *yo, int default_variant)
+                     const lbk_vec *x, i64 incx, const lbk_vec *y, i64 incy, lbk_vec *xo, lbk_vec *yo)
 {
+    using T = typename F::Scalar;
+    constexpr int dtype = sizeof(T) == 8 ? 1 : 0;
     if (!c) return fail(nullptr, LBK_ERR_ARG, std::string(who) + ": null context");
     const bool use_x = F::RX || F::WX, use_y = F::RY || F::WY;
     Operand X{}, Y{};
     int s;
-    if (use_x && (s = check_operand(c, who, x, incx, n, &X))) return s;
-    if (use_y && (s = check_operand(c, who, y, incy, n, &Y))) return s;
+    if (use_x && (s = check_operand(c, who, x, dtype, incx, n, &X))) return s;
+    if (use_y && (s = check_operand(c, who, y, dtype, incy, n, &Y))) return s;
     if (use_x && use_y && (x->sharded != y->sharded || (x->sharded && (x->global_len != y->global_len))))
         return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": operands must be sharded alike");
-    float *xw = nullptr, *yw = nullptr;
+    T *xw = nullptr, *yw = nullptr;
     if (F::WX) {
         lbk_vec *d = xo ? xo : const_cast<lbk_vec *>(x);
-        if (d->ctx != c || d->len != x->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
-        xw = d->ptr;
+        if (d->ctx != c || d->len != x->len || d->dtype != dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
+        xw = (T *)d->ptr;
     }
     if (F::WY) {
         lbk_vec *d = yo ? yo : const_cast<lbk_vec *>(y);
-        if (d->ctx != c || d->len != y->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
-        yw = d->ptr;
+        if (d->ctx != c || d->len != y->len || d->dtype != dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
+        yw = (T *)d->ptr;
     }
-    if (n > 0 && use_x && use_y && (F::WX || F::WY) && overlap(X, Y))
-        return fail(c, LBK_ERR_ALIAS, std::string(who) + ": x and y overlap");
+    // A written span must not overlap any OTHER span this call touches (reads may alias each other freely,
+    // and a destination may be its own source: that is the in-place form).
+    if (n > 0) {
+        const char *xl = nullptr, *xh = nullptr, *yl = nullptr, *yh = nullptr;
+        if (use_x) touched(X, &xl, &xh);
+        if (use_y) touched(Y, &yl, &yh);
+        auto hits = [](const char *al, const char *ah, const char *bl, const char *bh) { return al && bl && al < bh && bl < ah; };
+        const char *xwl = (const char *)xw, *xwh = xwl ? xwl + (xh - xl) : nullptr;
+        const char *ywl = (const char *)yw, *ywh = ywl ? ywl + (yh - yl) : nullptr;
+        bool bad = false;
+        if (F::WX) bad = bad || hits(xwl, xwh, yl, yh) || (xwl != xl && hits(xwl, xwh, xl, xh)) || (F::WY && hits(xwl, xwh, ywl, ywh));
+        if (F::WY) bad = bad || hits(ywl, ywh, xl, xh) || (ywl != yl && hits(ywl, ywh, yl, yh));
+        if (bad) return fail(c, LBK_ERR_ALIAS, std::string(who) + ": a written span overlaps another operand");
+    }
     // out of place: everything this call does not write is a copy of the source (Util.hs:134-142:
     // unsafeUpdate_ clones the whole destination first).  Fused into the update when the update covers
     // the vector; otherwise the remainder (unit stride) or the whole vector (strided) is copied.
-    auto prepare = [&](const Operand &O, float *w, bool writes) -> int {
-        if (!writes || w == O.v->ptr || O.v->len == 0) return LBK_OK;
+    auto prepare = [&](const Operand &O, T *w, bool writes) -> int {
+        if (!writes || (char *)w == O.v->ptr || O.v->len == 0) return LBK_OK;
         const i64 nl = n > 0 ? O.n_local : 0;
         const bool unit_cover = nl > 0 && (O.inc == 1 || O.inc == -1);
         const i64 from = unit_cover ? nl : 0;
         if (from < O.v->len) {
             c->tail_open = false;
-            CU(c, cudaMemcpyAsync(w + from, O.v->ptr + from, sizeof(float) * (size_t)(O.v->len - from), cudaMemcpyDeviceToDevice, c->stream));
+            CU(c, cudaMemcpyAsync(w + from, (const T *)O.v->ptr + from, sizeof(T) * (size_t)(O.v->len - from), cudaMemcpyDeviceToDevice, c->stream));
         }
         return LBK_OK;
     };
@@ -867,9 +907,9 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
     Operand Xs = X, Ys = Y;
     lbk_vec xtmp, ytmp;
     const bool x_unit = use_x && (X.inc == 1 || X.inc == -1), y_unit = use_y && (Y.inc == 1 || Y.inc == -1);
-    if (F::WX && xw != x->ptr && !x_unit) { xtmp = *x; xtmp.ptr = xw; Xs.v = &xtmp; }
-    if (F::WY && yw != y->ptr && !y_unit) { ytmp = *y; ytmp.ptr = yw; Ys.v = &ytmp; }
-    return map_dispatch<F>(c, rid, f, n, Xs, xw, Ys, yw, default_variant);
+    if (F::WX && (char *)xw != x->ptr && !x_unit) { xtmp = *x; xtmp.ptr = (char *)xw; Xs.v = &xtmp; }
+    if (F::WY && (char *)yw != y->ptr && !y_unit) { ytmp = *y; ytmp.ptr = (char *)yw; Ys.v = &ytmp; }
+    return map_dispatch<F>(c, rid, f, n, Xs, xw, Ys, yw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -878,8 +918,9 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
 template <class Op>
 static const void *reduce_kernel_ptr(int variant)
 {
+    using T = typename Op::Scalar;
     switch (variant) {
-#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::reduce_unit_kernel<Op, VEC, UNROLL, POLICY>;
+#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::reduce_unit_kernel<Op, vec_t<T>(VEC), UNROLL, POLICY>;
         LBK_VARIANTS(X)
 #undef X
     }
@@ -887,21 +928,22 @@ static const void *reduce_kernel_ptr(int variant)
 }
 
 // Runs the local reduction and, on a communicator with sharded operands, the exchange + finish.
-// `out` is a device-visible address that receives the float (or the int64 for isamax).
+// `out` is a device-visible address that receives the scalar (T, or the int64 for iamax).
 template <class Op>
-static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &X, const Operand *Y,
-                           double sb, void *out, int default_variant)
+static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &X, const Operand *Y, double sb, void *out)
 {
+    using T = typename Op::Scalar;
     CU(c, cudaSetDevice(c->device));
     const bool exchange = c->nranks > 1 && X.v->sharded;
-    const i64 nl = X.n_local;
-    const float *x = X.v->ptr, *y = Y ? Y->v->ptr : nullptr;
-    const i64 incx = X.inc, incy = Y ? Y->inc : 1;
     const bool fused = exchange && c->fused_exchange;
+    const i64 nl = X.n_local;
+    const T *x = (const T *)X.v->ptr, *y = Y ? (const T *)Y->v->ptr : nullptr;
+    const i64 incx = X.inc, incy = Y ? Y->inc : 1;
     FinishArgs fa;
     memset(&fa, 0, sizeof fa);
     fa.kind = kind;
     fa.mode = exchange ? (fused ? 2 : 1) : 0;
+    fa.is_f64 = (kind != 3 && sizeof(T) == 8) ? 1 : 0;
     if (fused) {
         if (++c->exchange_seq == 0) ++c->exchange_seq;    // tag 0 means "empty slot"
         fa.peers = c->peers_dev; fa.nranks = c->nranks; fa.rank = c->rank; fa.seq = c->exchange_seq;
@@ -917,20 +959,20 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
     const bool unit = nl > 0 && ((incx == 1 && (!Y || incy == 1)) || (Y && incx == -1 && incy == -1) || rev);
     if (unit) {
         const LaunchCfg &cfg = c->cfg[rid];
-        int variant = cfg.variant >= 0 ? cfg.variant : default_variant;
+        int variant = cfg.variant;
         const int threads = cfg.threads > 0 ? cfg.threads : 256;
-        const float *ptrs[2] = {x, y};
+        const T *ptrs[2] = {x, y};
         i64 head = 0;
         const void *k;
         if (rev) {
-            resolve_alignment_rev(&variant, &head, &x, 1, &y, 1, nl);
+            resolve_alignment_rev<T>(&variant, &head, &x, 1, &y, 1, nl);
             k = variant == kScalarVariant ? (const void *)lbk::reduce_unit_kernel<Op, 1, 4, 1, true>
-                                          : (const void *)lbk::reduce_unit_kernel<Op, 4, 4, 1, true>;
+                                          : (const void *)lbk::reduce_unit_kernel<Op, vec_t<T>(4), 4, 1, true>;
         } else {
-            resolve_alignment(&variant, &head, ptrs, Y ? 2 : 1, nl);
+            resolve_alignment<T>(&variant, &head, ptrs, Y ? 2 : 1, nl);
             k = reduce_kernel_ptr<Op>(variant);
         }
-        const i64 npack = (nl - head) / kVariantVec[variant];
+        const i64 npack = (nl - head) / variant_vec<T>(variant);
         const i64 per_tile = (i64)variant_unroll(variant) * threads;
         int grid;
         int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid);
@@ -938,8 +980,8 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         i64 nn = nl, ib = idx_base;
         void *args[] = {(void *)&x, (void *)&y, (void *)&head, (void *)&nn, (void *)&ib, (void *)&c->partials, (void *)&c->ticket, (void *)&fa};
         // `out` is not listed: a reduction writes its result only after griddepcontrol.wait
-        const float *ops[2] = {x, y};
-        const i64 lens[2] = {nl, nl};
+        const void *ops[2] = {x, y};
+        const i64 lens[2] = {nl * (i64)sizeof(T), nl * (i64)sizeof(T)};
         s = launch_stream_kernel(c, k, grid, threads, args, ops, lens, 2);
         if (s) return s;
         if (!exchange || fused) {   // the next unit-stride kernel may start under this kernel's tail
@@ -947,7 +989,6 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
             c->tail_lo = (const char *)out; c->tail_hi = c->tail_lo + 8;
         }
     } else {
-        c->tail_open = false;
         const int threads = 256;
         const int grid = stream_grid(c, std::max<i64>(nl, 1), threads);
         c->tail_open = false;
@@ -959,141 +1000,137 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         c->tail_open = false;
         NC(c, nccl_api()->AllGather(c->rec_send, c->rec_all, sizeof(Record), ncclChar, c->comm, c->stream));
         fa.mode = 0;
-        c->tail_open = false;
         lbk::finish_records_kernel<<<1, 32, 0, c->stream>>>(c->rec_all, c->nranks, fa);
         KERNEL_CHECK(c);
     }
     return LBK_OK;
 }
 
-static int store_f32(lbk_ctx *c, void *out, float v)
+template <class T>
+static int store_value(lbk_ctx *c, void *out, T v)
 {
     CU(c, cudaSetDevice(c->device));
     c->tail_open = false;
-    lbk::store_f32_kernel<<<1, 32, 0, c->stream>>>((float *)out, v);
-    KERNEL_CHECK(c);
-    return LBK_OK;
-}
-static int store_i64(lbk_ctx *c, void *out, i64 v)
-{
-    CU(c, cudaSetDevice(c->device));
-    c->tail_open = false;
-    lbk::store_i64_kernel<<<1, 32, 0, c->stream>>>((i64 *)out, v);
+    lbk::store_scalar_kernel<T><<<1, 32, 0, c->stream>>>((T *)out, v);
     KERNEL_CHECK(c);
     return LBK_OK;
 }
 
-static int check_out_vec(lbk_ctx *c, const char *who, lbk_vec *o, i64 need)
+static int check_out_vec(lbk_ctx *c, const char *who, lbk_vec *o, int dtype, i64 need_bytes)
 {
-    if (!o || o->ctx != c || o->len < need) return fail(c, LBK_ERR_ARG, std::string(who) + ": result vector is null, foreign or too short");
+    if (!o || o->ctx != c || o->dtype != dtype || o->len * esz(o->dtype) < need_bytes)
+        return fail(c, LBK_ERR_ARG, std::string(who) + ": result vector is null, foreign, of the wrong type or too short");
     if ((uintptr_t)o->ptr & 7) return fail(c, LBK_ERR_ARG, std::string(who) + ": result vector must be 8-byte aligned");
     return LBK_OK;
 }
 
-// kind: 0 sdot, 3 sdsdot
+// dot (kind 0) for T, sdsdot (kind 3) for float
+template <class T>
 static int dot_common(lbk_ctx *c, const char *who, int rid, int kind, i64 n, float sb, const lbk_vec *x, i64 incx,
                       const lbk_vec *y, i64 incy, void *out_dev)
 {
+    constexpr int dtype = sizeof(T) == 8 ? 1 : 0;
     Operand X{}, Y{};
     int s;
-    if ((s = check_operand(c, who, x, incx, n, &X))) return s;
-    if ((s = check_operand(c, who, y, incy, n, &Y))) return s;
+    if ((s = check_operand(c, who, x, dtype, incx, n, &X))) return s;
+    if ((s = check_operand(c, who, y, dtype, incy, n, &Y))) return s;
     if (x->sharded != y->sharded || (x->sharded && x->global_len != y->global_len))
         return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": operands must be sharded alike");
-    if (n <= 0) return store_f32(c, out_dev, kind == 3 ? sb : 0.f);       // Single.hs:81 (empty fold), :239
-    if (kind == 3) return reduce_dispatch<lbk::DsdotOp>(c, rid, 3, n, X, &Y, (double)sb, out_dev, 0);
-    return reduce_dispatch<lbk::DotOp>(c, rid, 0, n, X, &Y, 0.0, out_dev, 0);
+    if (n <= 0) return store_value<T>(c, out_dev, kind == 3 ? (T)sb : (T)0);       // Single.hs:81 (empty fold), :239
+    if constexpr (sizeof(T) == 4) {
+        if (kind == 3) return reduce_dispatch<lbk::DsdotOp>(c, rid, 3, n, X, &Y, (double)sb, out_dev);
+    }
+    return reduce_dispatch<lbk::DotOp<T>>(c, rid, 0, n, X, &Y, 0.0, out_dev);
 }
 
-template <class T>
-static int finish_sync(lbk_ctx *c, int s, T *out)
+template <class R>
+static int finish_sync(lbk_ctx *c, int s, R *out)
 {
     if (s) return s;
     CU(c, cudaStreamSynchronize(c->stream));
-    *out = *reinterpret_cast<volatile T *>(c->result_host);
+    *out = *reinterpret_cast<volatile R *>(c->result_host);
     return check_exchange_error(c);
 }
 
-extern "C" int lbk_sdot(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out)
+// asum (kind 0 with AsumOp), nrm2 (kind 1), iamax (kind 2): one vector, positive increments
+template <class T>
+static int ivi_common(lbk_ctx *c, const char *who, int rid, i64 n, const lbk_vec *x, i64 incx, void *out_dev)
 {
-    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_sdot: null argument");
-    return finish_sync(c, dot_common(c, "lbk_sdot", R_SDOT, 0, n, 0.f, x, incx, y, incy, c->result_dev), out);
+    constexpr int dtype = sizeof(T) == 8 ? 1 : 0;
+    if (!x) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
+    if (x->ctx != c) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
+    if (x->dtype != dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector has the wrong element type");
+    // the reference's guards come first: Single.hs:162 (asum), :181 (nrm2), :218 (iamax)
+    if (n < 1 || incx < 1) return rid == R_IAMAX ? store_value<i64>(c, out_dev, -1) : store_value<T>(c, out_dev, (T)0);
+    Operand X{};
+    int s;
+    if ((s = check_operand(c, who, x, dtype, incx, n, &X))) return s;
+    if (rid == R_ASUM) return reduce_dispatch<lbk::AsumOp<T>>(c, rid, 0, n, X, nullptr, 0.0, out_dev);
+    if (rid == R_NRM2) return reduce_dispatch<lbk::Nrm2Op<T>>(c, rid, 1, n, X, nullptr, 0.0, out_dev);
+    return reduce_dispatch<lbk::IamaxOp<T>>(c, rid, 2, n, X, nullptr, 0.0, out_dev);
 }
-extern "C" int lbk_sdot_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *o)
-{
-    if (!c) return fail(c, LBK_ERR_ARG, "lbk_sdot_async: null context");
-    int s = check_out_vec(c, "lbk_sdot_async", o, 1);
-    return s ? s : dot_common(c, "lbk_sdot_async", R_SDOT, 0, n, 0.f, x, incx, y, incy, o->ptr);
-}
+
+#define LBK_REDUCTIONS(P, T, DT, IPFX)                                                                                         \
+    extern "C" int lbk_##P##dot(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, T *out)  \
+    {                                                                                                                          \
+        if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_" #P "dot: null argument");                                           \
+        return finish_sync(c, dot_common<T>(c, "lbk_" #P "dot", R_DOT, 0, n, 0.f, x, incx, y, incy, c->result_dev), out);       \
+    }                                                                                                                          \
+    extern "C" int lbk_##P##dot_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *o) \
+    {                                                                                                                          \
+        if (!c) return fail(c, LBK_ERR_ARG, "lbk_" #P "dot_async: null context");                                              \
+        int s = check_out_vec(c, "lbk_" #P "dot_async", o, DT, sizeof(T));                                                     \
+        return s ? s : dot_common<T>(c, "lbk_" #P "dot_async", R_DOT, 0, n, 0.f, x, incx, y, incy, o->ptr);                     \
+    }                                                                                                                          \
+    extern "C" int lbk_##P##asum(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, T *out)                                 \
+    {                                                                                                                          \
+        if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_" #P "asum: null argument");                                          \
+        return finish_sync(c, ivi_common<T>(c, "lbk_" #P "asum", R_ASUM, n, x, incx, c->result_dev), out);                      \
+    }                                                                                                                          \
+    extern "C" int lbk_##P##nrm2(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, T *out)                                 \
+    {                                                                                                                          \
+        if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_" #P "nrm2: null argument");                                          \
+        return finish_sync(c, ivi_common<T>(c, "lbk_" #P "nrm2", R_NRM2, n, x, incx, c->result_dev), out);                      \
+    }                                                                                                                          \
+    extern "C" int lbk_##IPFX##amax(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, int64_t *out)                        \
+    {                                                                                                                          \
+        if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_" #IPFX "amax: null argument");                                       \
+        return finish_sync(c, ivi_common<T>(c, "lbk_" #IPFX "amax", R_IAMAX, n, x, incx, c->result_dev), out);                  \
+    }                                                                                                                          \
+    extern "C" int lbk_##P##asum_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)                       \
+    {                                                                                                                          \
+        if (!c) return fail(c, LBK_ERR_ARG, "lbk_" #P "asum_async: null context");                                             \
+        int s = check_out_vec(c, "lbk_" #P "asum_async", o, DT, sizeof(T));                                                    \
+        return s ? s : ivi_common<T>(c, "lbk_" #P "asum_async", R_ASUM, n, x, incx, o->ptr);                                    \
+    }                                                                                                                          \
+    extern "C" int lbk_##P##nrm2_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)                       \
+    {                                                                                                                          \
+        if (!c) return fail(c, LBK_ERR_ARG, "lbk_" #P "nrm2_async: null context");                                             \
+        int s = check_out_vec(c, "lbk_" #P "nrm2_async", o, DT, sizeof(T));                                                    \
+        return s ? s : ivi_common<T>(c, "lbk_" #P "nrm2_async", R_NRM2, n, x, incx, o->ptr);                                    \
+    }                                                                                                                          \
+    extern "C" int lbk_##IPFX##amax_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)                    \
+    {                                                                                                                          \
+        if (!c) return fail(c, LBK_ERR_ARG, "lbk_" #IPFX "amax_async: null context");                                          \
+        int s = check_out_vec(c, "lbk_" #IPFX "amax_async", o, DT, 8);                                                         \
+        return s ? s : ivi_common<T>(c, "lbk_" #IPFX "amax_async", R_IAMAX, n, x, incx, o->ptr);                                \
+    }
+LBK_REDUCTIONS(s, float, 0, is)
+LBK_REDUCTIONS(d, double, 1, id)
+
 extern "C" int lbk_sdsdot(lbk_ctx *c, int64_t n, float sb, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out)
 {
     if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_sdsdot: null argument");
-    return finish_sync(c, dot_common(c, "lbk_sdsdot", R_SDSDOT, 3, n, sb, x, incx, y, incy, c->result_dev), out);
-}
-
-// sasum (kind 0 with AsumOp), snrm2 (kind 1), isamax (kind 2): one vector, positive increments
-static int ivi_common(lbk_ctx *c, const char *who, int rid, i64 n, const lbk_vec *x, i64 incx, void *out_dev)
-{
-    if (!x) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
-    if (x->ctx != c) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
-    // the reference's guards come first: Single.hs:162 (asum), :181 (nrm2), :218 (iamax)
-    if (n < 1 || incx < 1) return rid == R_ISAMAX ? store_i64(c, out_dev, -1) : store_f32(c, out_dev, 0.f);
-    Operand X{};
-    int s;
-    if ((s = check_operand(c, who, x, incx, n, &X))) return s;
-    if (rid == R_SASUM) return reduce_dispatch<lbk::AsumOp>(c, rid, 0, n, X, nullptr, 0.0, out_dev, 0);
-    if (rid == R_SNRM2) return reduce_dispatch<lbk::Nrm2Op>(c, rid, 1, n, X, nullptr, 0.0, out_dev, 0);
-    return reduce_dispatch<lbk::IamaxOp>(c, rid, 2, n, X, nullptr, 0.0, out_dev, 0);
-}
-
-extern "C" int lbk_sasum(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, float *out)
-{
-    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_sasum: null argument");
-    return finish_sync(c, ivi_common(c, "lbk_sasum", R_SASUM, n, x, incx, c->result_dev), out);
-}
-extern "C" int lbk_snrm2(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, float *out)
-{
-    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_snrm2: null argument");
-    return finish_sync(c, ivi_common(c, "lbk_snrm2", R_SNRM2, n, x, incx, c->result_dev), out);
-}
-extern "C" int lbk_isamax(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, int64_t *out)
-{
-    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_isamax: null argument");
-    return finish_sync(c, ivi_common(c, "lbk_isamax", R_ISAMAX, n, x, incx, c->result_dev), out);
-}
-extern "C" int lbk_sasum_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)
-{
-    if (!c) return fail(c, LBK_ERR_ARG, "lbk_sasum_async: null context");
-    int s = check_out_vec(c, "lbk_sasum_async", o, 1);
-    return s ? s : ivi_common(c, "lbk_sasum_async", R_SASUM, n, x, incx, o->ptr);
-}
-extern "C" int lbk_snrm2_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)
-{
-    if (!c) return fail(c, LBK_ERR_ARG, "lbk_snrm2_async: null context");
-    int s = check_out_vec(c, "lbk_snrm2_async", o, 1);
-    return s ? s : ivi_common(c, "lbk_snrm2_async", R_SNRM2, n, x, incx, o->ptr);
-}
-extern "C" int lbk_isamax_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)
-{
-    if (!c) return fail(c, LBK_ERR_ARG, "lbk_isamax_async: null context");
-    int s = check_out_vec(c, "lbk_isamax_async", o, 2);
-    return s ? s : ivi_common(c, "lbk_isamax_async", R_ISAMAX, n, x, incx, o->ptr);
+    return finish_sync(c, dot_common<float>(c, "lbk_sdsdot", R_SDSDOT, 3, n, sb, x, incx, y, incy, c->result_dev), out);
 }
 
 // ------------------------------------------------------------------------------------------------
 // elementwise entry points
 // ------------------------------------------------------------------------------------------------
-extern "C" int lbk_saxpy(lbk_ctx *c, int64_t n, float a, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy)
-{ return map_entry(c, "lbk_saxpy", R_SAXPY, lbk::AxpyF{a}, n, x, incx, y, incy, nullptr, nullptr, 0); }
-extern "C" int lbk_saxpy_oop(lbk_ctx *c, int64_t n, float a, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout)
-{
-    if (!yout) return fail(c, LBK_ERR_ARG, "lbk_saxpy_oop: null output");
-    return map_entry(c, "lbk_saxpy_oop", R_SAXPY, lbk::AxpyF{a}, n, x, incx, y, incy, nullptr, yout, 0);
-}
-
 // Single.hs:108-111: the index stream `sampleIndices n incx` is empty for incx < 0 and n > 1, and
 // yields slot 0 (n times for incx == 0, once for n == 1), each write being x[0]*a.
-static int scal_common(lbk_ctx *c, const char *who, i64 n, float a, const lbk_vec *x, i64 incx, lbk_vec *xout)
+template <class T>
+static int scal_common(lbk_ctx *c, const char *who, i64 n, T a, const lbk_vec *x, i64 incx, lbk_vec *xout)
 {
     if (!c) return fail(nullptr, LBK_ERR_ARG, std::string(who) + ": null context");
     if (!x) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
@@ -1104,93 +1141,85 @@ static int scal_common(lbk_ctx *c, const char *who, i64 n, float a, const lbk_ve
         if (x->sharded) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take unit increments only");
     }
     if (n_eff <= 0 && xout && xout->ptr != x->ptr) {      // nothing to scale: the pure result is a copy
-        if (xout->ctx != c || xout->len != x->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
-        if (x->len) { c->tail_open = false; CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, sizeof(float) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream)); }
+        if (xout->ctx != c || xout->len != x->len || xout->dtype != x->dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
+        if (x->len) { c->tail_open = false; CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, (size_t)esz(x->dtype) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream)); }
         return LBK_OK;
     }
-    return map_entry(c, who, R_SSCAL, lbk::ScalF{a}, n_eff, x, inc_eff, nullptr, 1, xout, nullptr, 0);
-}
-extern "C" int lbk_sscal(lbk_ctx *c, int64_t n, float a, lbk_vec *x, int64_t incx)
-{ return scal_common(c, "lbk_sscal", n, a, x, incx, nullptr); }
-extern "C" int lbk_sscal_oop(lbk_ctx *c, int64_t n, float a, const lbk_vec *x, int64_t incx, lbk_vec *xout)
-{
-    if (!xout) return fail(c, LBK_ERR_ARG, "lbk_sscal_oop: null output");
-    return scal_common(c, "lbk_sscal_oop", n, a, x, incx, xout);
-}
-
-extern "C" int lbk_scopy(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy)
-{ return map_entry(c, "lbk_scopy", R_SCOPY, lbk::CopyF{}, n, x, incx, y, incy, nullptr, nullptr, 0); }
-extern "C" int lbk_scopy_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout)
-{
-    if (!yout) return fail(c, LBK_ERR_ARG, "lbk_scopy_oop: null output");
-    return map_entry(c, "lbk_scopy_oop", R_SCOPY, lbk::CopyF{}, n, x, incx, y, incy, nullptr, yout, 0);
-}
-
-extern "C" int lbk_sswap(lbk_ctx *c, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy)
-{ return map_entry(c, "lbk_sswap", R_SSWAP, lbk::SwapF{}, n, x, incx, y, incy, nullptr, nullptr, 0); }
-extern "C" int lbk_sswap_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *xout, lbk_vec *yout)
-{
-    if (!xout || !yout) return fail(c, LBK_ERR_ARG, "lbk_sswap_oop: null output");
-    return map_entry(c, "lbk_sswap_oop", R_SSWAP, lbk::SwapF{}, n, x, incx, y, incy, xout, yout, 0);
-}
-
-extern "C" int lbk_srot(lbk_ctx *c, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, float cs, float sn)
-{ return map_entry(c, "lbk_srot", R_SROT, lbk::RotF{cs, sn}, n, x, incx, y, incy, nullptr, nullptr, 0); }
-extern "C" int lbk_srot_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float cs, float sn, lbk_vec *xout, lbk_vec *yout)
-{
-    if (!xout || !yout) return fail(c, LBK_ERR_ARG, "lbk_srot_oop: null output");
-    return map_entry(c, "lbk_srot_oop", R_SROT, lbk::RotF{cs, sn}, n, x, incx, y, incy, xout, yout, 0);
+    return map_entry(c, who, R_SCAL, lbk::ScalF<T>{a}, n_eff, x, inc_eff, nullptr, 1, xout, nullptr);
 }
 
 // Single.hs:472-482; param = [flag,h11,h21,h12,h22] (test/Foreign.hs:276-280)
+template <class T>
 static int rotm_common(lbk_ctx *c, const char *who, i64 n, const lbk_vec *x, i64 incx, const lbk_vec *y, i64 incy,
-                       const float *p, lbk_vec *xout, lbk_vec *yout)
+                       const T *p, lbk_vec *xout, lbk_vec *yout)
 {
     if (!c) return fail(nullptr, LBK_ERR_ARG, std::string(who) + ": null context");
     if (!p) return fail(c, LBK_ERR_ARG, std::string(who) + ": null param");
-    const float flag = p[0];
-    if (flag == -2.0f) {          // FLAGNEG2: the inputs come back as they are (Single.hs:473)
-        if (xout && x && xout->ptr != x->ptr && x->len) {
-            if (xout->len != x->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
-            c->tail_open = false;
-            CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, sizeof(float) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream));
-        }
-        if (yout && y && yout->ptr != y->ptr && y->len) {
-            if (yout->len != y->len) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length");
-            c->tail_open = false;
-            CU(c, cudaMemcpyAsync(yout->ptr, y->ptr, sizeof(float) * (size_t)y->len, cudaMemcpyDeviceToDevice, c->stream));
-        }
+    const T flag = p[0];
+    if (flag == (T)-2) {          // FLAGNEG2: the inputs come back as they are (Single.hs:473)
+        const lbk_vec *src[2] = {x, y};
+        lbk_vec *dst[2] = {xout, yout};
+        for (int i = 0; i < 2; ++i)
+            if (dst[i] && src[i] && dst[i]->ptr != src[i]->ptr && src[i]->len) {
+                if (dst[i]->len != src[i]->len || dst[i]->dtype != src[i]->dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
+                c->tail_open = false;
+                CU(c, cudaMemcpyAsync(dst[i]->ptr, src[i]->ptr, (size_t)esz(src[i]->dtype) * (size_t)src[i]->len, cudaMemcpyDeviceToDevice, c->stream));
+            }
         return LBK_OK;
     }
-    if (flag < 0.0f) return map_entry(c, who, R_SROTM, lbk::RotmNeg1F{p[1], p[3], p[2], p[4]}, n, x, incx, y, incy, xout, yout, 0);
-    if (flag == 0.0f) return map_entry(c, who, R_SROTM, lbk::Rotm0F{p[3], p[2]}, n, x, incx, y, incy, xout, yout, 0);
-    return map_entry(c, who, R_SROTM, lbk::Rotm1F{p[1], p[4]}, n, x, incx, y, incy, xout, yout, 0);
+    if (flag < (T)0) return map_entry(c, who, R_ROTM, lbk::RotmNeg1F<T>{p[1], p[3], p[2], p[4]}, n, x, incx, y, incy, xout, yout);
+    if (flag == (T)0) return map_entry(c, who, R_ROTM, lbk::Rotm0F<T>{p[3], p[2]}, n, x, incx, y, incy, xout, yout);
+    return map_entry(c, who, R_ROTM, lbk::Rotm1F<T>{p[1], p[4]}, n, x, incx, y, incy, xout, yout);
 }
-extern "C" int lbk_srotm(lbk_ctx *c, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, const float param[5])
-{ return rotm_common(c, "lbk_srotm", n, x, incx, y, incy, param, nullptr, nullptr); }
-extern "C" int lbk_srotm_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, const float param[5], lbk_vec *xout, lbk_vec *yout)
-{
-    if (!xout || !yout) return fail(c, LBK_ERR_ARG, "lbk_srotm_oop: null output");
-    return rotm_common(c, "lbk_srotm_oop", n, x, incx, y, incy, param, xout, yout);
-}
+
+#define LBK_NEED(p, name) if (!(p)) return fail(c, LBK_ERR_ARG, name ": null output")
+#define LBK_MAPS(P, T)                                                                                                          \
+    extern "C" int lbk_##P##axpy(lbk_ctx *c, int64_t n, T a, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy)          \
+    { return map_entry(c, "lbk_" #P "axpy", R_AXPY, lbk::AxpyF<T>{a}, n, x, incx, y, incy, nullptr, nullptr); }                 \
+    extern "C" int lbk_##P##axpy_oop(lbk_ctx *c, int64_t n, T a, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout) \
+    { LBK_NEED(yout, "lbk_" #P "axpy_oop"); return map_entry(c, "lbk_" #P "axpy_oop", R_AXPY, lbk::AxpyF<T>{a}, n, x, incx, y, incy, nullptr, yout); } \
+    extern "C" int lbk_##P##scal(lbk_ctx *c, int64_t n, T a, lbk_vec *x, int64_t incx)                                          \
+    { return scal_common<T>(c, "lbk_" #P "scal", n, a, x, incx, nullptr); }                                                     \
+    extern "C" int lbk_##P##scal_oop(lbk_ctx *c, int64_t n, T a, const lbk_vec *x, int64_t incx, lbk_vec *xout)                 \
+    { LBK_NEED(xout, "lbk_" #P "scal_oop"); return scal_common<T>(c, "lbk_" #P "scal_oop", n, a, x, incx, xout); }              \
+    extern "C" int lbk_##P##copy(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy)               \
+    { return map_entry(c, "lbk_" #P "copy", R_COPY, lbk::CopyF<T>{}, n, x, incx, y, incy, nullptr, nullptr); }                  \
+    extern "C" int lbk_##P##copy_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *yout) \
+    { LBK_NEED(yout, "lbk_" #P "copy_oop"); return map_entry(c, "lbk_" #P "copy_oop", R_COPY, lbk::CopyF<T>{}, n, x, incx, y, incy, nullptr, yout); } \
+    extern "C" int lbk_##P##swap(lbk_ctx *c, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy)                     \
+    { return map_entry(c, "lbk_" #P "swap", R_SWAP, lbk::SwapF<T>{}, n, x, incx, y, incy, nullptr, nullptr); }                  \
+    extern "C" int lbk_##P##swap_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *xout, lbk_vec *yout) \
+    { LBK_NEED(xout && yout, "lbk_" #P "swap_oop"); return map_entry(c, "lbk_" #P "swap_oop", R_SWAP, lbk::SwapF<T>{}, n, x, incx, y, incy, xout, yout); } \
+    extern "C" int lbk_##P##rot(lbk_ctx *c, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, T cs, T sn)          \
+    { return map_entry(c, "lbk_" #P "rot", R_ROT, lbk::RotF<T>{cs, sn}, n, x, incx, y, incy, nullptr, nullptr); }               \
+    extern "C" int lbk_##P##rot_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, T cs, T sn, lbk_vec *xout, lbk_vec *yout) \
+    { LBK_NEED(xout && yout, "lbk_" #P "rot_oop"); return map_entry(c, "lbk_" #P "rot_oop", R_ROT, lbk::RotF<T>{cs, sn}, n, x, incx, y, incy, xout, yout); } \
+    extern "C" int lbk_##P##rotm(lbk_ctx *c, int64_t n, lbk_vec *x, int64_t incx, lbk_vec *y, int64_t incy, const T param[5])   \
+    { return rotm_common<T>(c, "lbk_" #P "rotm", n, x, incx, y, incy, param, nullptr, nullptr); }                               \
+    extern "C" int lbk_##P##rotm_oop(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, const T param[5], lbk_vec *xout, lbk_vec *yout) \
+    { LBK_NEED(xout && yout, "lbk_" #P "rotm_oop"); return rotm_common<T>(c, "lbk_" #P "rotm_oop", n, x, incx, y, incy, param, xout, yout); }
+LBK_MAPS(s, float)
+LBK_MAPS(d, double)
 
 // ------------------------------------------------------------------------------------------------
 // host statement of the cross-rank combine (tests of the multi-GPU path on CPU)
 // ------------------------------------------------------------------------------------------------
-extern "C" int lbk_combine_records(int kind, const lbk_record *recs, int nranks, float *fout, int64_t *iout)
+extern "C" int lbk_combine_records(int kind, int is_f64, const lbk_record *recs, int nranks, double *fout, int64_t *iout)
 {
     if (!recs || nranks < 1) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: bad argument");
     const Record *r = reinterpret_cast<const Record *>(recs);
+    if (kind != LBK_RED_SUM && kind != LBK_RED_NRM2 && kind != LBK_RED_IAMAX) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: unknown kind");
+    const Record a = lbk::fold_by_kind(r, nranks, kind);
     if (kind == LBK_RED_IAMAX) {
         if (!iout) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: null out pointer");
-        *iout = lbk::fold_ranks<lbk::IamaxOp>(r, nranks).idx;
-    } else if (kind == LBK_RED_NRM2) {
-        if (!fout) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: null out pointer");
-        Record a = lbk::fold_ranks<lbk::Nrm2Op>(r, nranks);
-        *fout = lbk::nrm2_finish(a.f[0], a.f[1], a.f[2]);
-    } else if (kind == LBK_RED_SUM) {
-        if (!fout) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: null out pointer");
-        *fout = lbk::fold_ranks<lbk::DotOp>(r, nranks).f[0];
-    } else return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: unknown kind");
+        *iout = a.idx;
+        return LBK_OK;
+    }
+    if (!fout) return fail(nullptr, LBK_ERR_ARG, "lbk_combine_records: null out pointer");
+    double v = a.f[0];
+    if (kind == LBK_RED_NRM2)
+        v = is_f64 ? lbk::nrm2_finish(a.f[0], a.f[1], a.f[2], (double)lbk::Blue<double>::sbig, (double)lbk::Blue<double>::ssml)
+                   : lbk::nrm2_finish(a.f[0], a.f[1], a.f[2], (double)lbk::Blue<float>::sbig, (double)lbk::Blue<float>::ssml);
+    *fout = is_f64 ? v : (double)(float)v;
     return LBK_OK;
 }

@@ -36,9 +36,9 @@ def attach_torch_distributed(ctx: Context) -> Context:
     return ctx
 
 
-def combine_records(kind: int, records) -> float | int:
+def combine_records(kind: int, records, is_f64: bool = False) -> float | int:
     """Host statement of the cross-rank fold (lbk_combine_records); used by the CPU tests."""
     arr = (_ffi.Record * len(records))(*records)
-    f, i = C.c_float(), C.c_int64()
-    _ffi.check(_ffi.lib().lbk_combine_records(kind, arr, len(records), C.byref(f), C.byref(i)))
+    f, i = C.c_double(), C.c_int64()
+    _ffi.check(_ffi.lib().lbk_combine_records(kind, int(is_f64), arr, len(records), C.byref(f), C.byref(i)))
     return i.value if kind == 2 else f.value

@@ -18,6 +18,10 @@ import numpy as np
 from . import _ffi
 
 
+def _is64(dtype) -> bool:
+    return np.dtype(dtype) == np.float64
+
+
 class Context:
     """One GPU, one stream, scratch for the reductions, and (optionally) the NCCL communicator."""
 
@@ -90,29 +94,35 @@ class Context:
     def set_fused_exchange(self, enabled: bool) -> None:
         _ffi.check(_ffi.lib().lbk_set_fused_exchange(self.handle, int(enabled)), self.handle)
 
-    # ---- vectors ----
-    def alloc(self, n: int) -> "DVector":
+    # ---- vectors (dtype: np.float32 = Vector Float, np.float64 = Vector Double) ----
+    def alloc(self, n: int, dtype=np.float32) -> "DVector":
         h = C.c_void_p()
-        _ffi.check(_ffi.lib().lbk_vec_alloc(self.handle, n, C.byref(h)), self.handle)
+        fn = _ffi.lib().lbk_vec_alloc_f64 if _is64(dtype) else _ffi.lib().lbk_vec_alloc
+        _ffi.check(fn(self.handle, n, C.byref(h)), self.handle)
         return DVector(self, h)
 
-    def alloc_sharded(self, global_len: int) -> "DVector":
+    def alloc_sharded(self, global_len: int, dtype=np.float32) -> "DVector":
         h = C.c_void_p()
-        _ffi.check(_ffi.lib().lbk_vec_alloc_sharded(self.handle, global_len, C.byref(h)), self.handle)
+        fn = _ffi.lib().lbk_vec_alloc_sharded_f64 if _is64(dtype) else _ffi.lib().lbk_vec_alloc_sharded
+        _ffi.check(fn(self.handle, global_len, C.byref(h)), self.handle)
         return DVector(self, h)
 
-    def wrap(self, device_ptr: int, n: int, keepalive=None) -> "DVector":
+    def wrap(self, device_ptr: int, n: int, keepalive=None, dtype=np.float32) -> "DVector":
         h = C.c_void_p()
-        _ffi.check(_ffi.lib().lbk_vec_wrap(self.handle, C.c_void_p(device_ptr), n, C.byref(h)), self.handle)
+        fn = _ffi.lib().lbk_vec_wrap_f64 if _is64(dtype) else _ffi.lib().lbk_vec_wrap
+        _ffi.check(fn(self.handle, C.c_void_p(device_ptr), n, C.byref(h)), self.handle)
         v = DVector(self, h)
         v._keep = keepalive
         return v
 
-    def to_device(self, host) -> "DVector":
-        a = np.ascontiguousarray(host, dtype=np.float32)
+    def to_device(self, host, dtype=None) -> "DVector":
+        """Explicit host -> device transfer.  float64 input makes a double-precision vector, anything else single."""
+        if dtype is None:
+            dtype = np.float64 if getattr(host, "dtype", None) == np.float64 else np.float32
+        a = np.ascontiguousarray(host, dtype=dtype)
         if a.ndim != 1:
             raise ValueError("vectors are one-dimensional")
-        v = self.alloc(a.size)
+        v = self.alloc(a.size, dtype)
         if a.size:
             _ffi.check(_ffi.lib().lbk_vec_upload(v.handle, a.ctypes.data_as(C.c_void_p), a.size), self.handle)
         return v
@@ -185,6 +195,10 @@ class DVector:
     def ptr(self) -> int:
         return int(_ffi.lib().lbk_vec_ptr(self._h) or 0)
 
+    @property
+    def dtype(self):
+        return np.dtype(np.float64 if _ffi.lib().lbk_vec_elem_size(self._h) == 8 else np.float32)
+
     def clone(self) -> "DVector":
         h = C.c_void_p()
         _ffi.check(_ffi.lib().lbk_vec_clone(self._h, C.byref(h)), self.ctx.handle)
@@ -197,25 +211,25 @@ class DVector:
 
     def to_host(self) -> np.ndarray:
         n = len(self)
-        out = np.empty(n, dtype=np.float32)
+        out = np.empty(n, dtype=self.dtype)
         if n:
             _ffi.check(_ffi.lib().lbk_vec_download(self._h, out.ctypes.data_as(C.c_void_p), n), self.ctx.handle)
         return out
 
     def upload(self, host) -> "DVector":
-        a = np.ascontiguousarray(host, dtype=np.float32)
+        a = np.ascontiguousarray(host, dtype=self.dtype)
         _ffi.check(_ffi.lib().lbk_vec_upload(self._h, a.ctypes.data_as(C.c_void_p), a.size), self.ctx.handle)
         return self
 
     def upload_async(self, host: np.ndarray) -> "DVector":
         """Enqueue host -> device (host should come from pinned_array); returns at once."""
-        assert host.dtype == np.float32 and host.flags.c_contiguous
+        assert host.dtype == self.dtype and host.flags.c_contiguous
         _ffi.check(_ffi.lib().lbk_vec_upload_async(self._h, host.ctypes.data_as(C.c_void_p), host.size), self.ctx.handle)
         return self
 
     def download_async(self, out: np.ndarray) -> np.ndarray:
         """Enqueue device -> host into `out` (pinned); valid after ctx.sync()."""
-        assert out.dtype == np.float32 and out.flags.c_contiguous
+        assert out.dtype == self.dtype and out.flags.c_contiguous
         _ffi.check(_ffi.lib().lbk_vec_download_async(self._h, out.ctypes.data_as(C.c_void_p), out.size), self.ctx.handle)
         return out
 
@@ -237,10 +251,10 @@ class DVector:
 
 
 class _Pinned:
-    def __init__(self, n: int):
-        p = C.POINTER(C.c_float)()
-        _ffi.check(_ffi.lib().lbk_host_alloc(n, C.byref(p)))
-        self.p, self.n = p, n
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        _ffi.check(_ffi.lib().lbk_host_alloc(nbytes, C.byref(p)))
+        self.p, self.n = p, nbytes
 
     def __del__(self):
         try:
@@ -249,12 +263,14 @@ class _Pinned:
             pass
 
 
-def pinned_array(n: int) -> np.ndarray:
-    """A float32 numpy array over page-locked host memory (lbk_host_alloc), for async transfers."""
+def pinned_array(n: int, dtype=np.float32) -> np.ndarray:
+    """A numpy array over page-locked host memory (lbk_host_alloc), for async transfers."""
+    dtype = np.dtype(dtype)
     if n == 0:
-        return np.empty(0, dtype=np.float32)
-    owner = _Pinned(n)
-    arr = np.ctypeslib.as_array(owner.p, shape=(n,))
+        return np.empty(0, dtype=dtype)
+    owner = _Pinned(n * dtype.itemsize)
+    ctype = C.c_double if dtype == np.float64 else C.c_float
+    arr = np.ctypeslib.as_array(C.cast(owner.p, C.POINTER(ctype)), shape=(n,))
     # keep the allocation alive as long as any view of the array is
     out = arr.view(_PinnedArray)
     out._owner = owner
@@ -269,17 +285,18 @@ class _PinnedArray(np.ndarray):
             self._owner = getattr(obj, "_owner", None)
 
 
-def hash_fill_reference(n: int, seed: int, lo: float = -1.0, hi: float = 1.0, offset: int = 0) -> np.ndarray:
-    """numpy statement of lbk_vec_fill_hash: v[i] = lo + (hi-lo) * u24(splitmix64(seed*2^40 + offset+i))."""
+def hash_fill_reference(n: int, seed: int, lo: float = -1.0, hi: float = 1.0, offset: int = 0, dtype=np.float32) -> np.ndarray:
+    """numpy statement of lbk_vec_fill_hash: v[i] = lo + (hi-lo) * u24(splitmix64(seed*2^40 + offset+i)), in `dtype`."""
+    R = np.dtype(dtype).type
     i = (np.arange(n, dtype=np.uint64) + np.uint64(offset)) + (np.uint64(seed) << np.uint64(40))
     with np.errstate(over="ignore"):
         z = i + np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z = z ^ (z >> np.uint64(31))
-    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)
-    span = np.float32(np.float32(hi) - np.float32(lo))
-    return (np.float32(lo) + span * u).astype(np.float32)
+    u = (z >> np.uint64(40)).astype(R) * R(2.0 ** -24)
+    span = R(R(hi) - R(lo))
+    return (R(lo) + span * u).astype(R)
 
 
 # ---- the reference's ADTs ---------------------------------------------------------------------------
@@ -296,27 +313,27 @@ class GivensRot(NamedTuple):
 class ModGivensRot:
     """Types.hs:15-20.  `flag` names the constructor: -2 FLAGNEG2, -1 FLAGNEG1, 0 FLAG0, 1 FLAG1."""
     flag: int
-    d1: np.float32 = np.float32(0)
-    d2: np.float32 = np.float32(0)
-    x1: np.float32 = np.float32(0)
-    h11: np.float32 = np.float32(0)
-    h12: np.float32 = np.float32(0)
-    h21: np.float32 = np.float32(0)
-    h22: np.float32 = np.float32(0)
+    d1: float = np.float32(0)
+    d2: float = np.float32(0)
+    x1: float = np.float32(0)
+    h11: float = np.float32(0)
+    h12: float = np.float32(0)
+    h21: float = np.float32(0)
+    h22: float = np.float32(0)
 
     @property
     def constructor(self) -> str:
         return {-2: "FLAGNEG2", -1: "FLAGNEG1", 0: "FLAG0", 1: "FLAG1"}[self.flag]
 
-    def sparam(self) -> np.ndarray:
+    def sparam(self, dtype=np.float32) -> np.ndarray:
         """BLAS sparam [flag,h11,h21,h12,h22], filled the way test/Foreign.hs:276-280 pokes it."""
         if self.flag == -2:
-            return np.array([-2, 1, 0, 0, 1], dtype=np.float32)
+            return np.array([-2, 1, 0, 0, 1], dtype=dtype)
         if self.flag == -1:
-            return np.array([-1, self.h11, self.h21, self.h12, self.h22], dtype=np.float32)
+            return np.array([-1, self.h11, self.h21, self.h12, self.h22], dtype=dtype)
         if self.flag == 0:
-            return np.array([0, 0, self.h21, self.h12, 0], dtype=np.float32)
-        return np.array([1, self.h11, 0, 0, self.h22], dtype=np.float32)
+            return np.array([0, 0, self.h21, self.h12, 0], dtype=dtype)
+        return np.array([1, self.h11, 0, 0, self.h22], dtype=dtype)
 
 
 FLAGNEG2 = ModGivensRot(-2)

@@ -10,24 +10,32 @@ EVERYDAY_LO = np.float32(2.0 ** -24)
 EVERYDAY_HI = np.float32(2.0 ** 24 - 1)
 
 
-def gen_everyday(rng: np.random.Generator, size) -> np.ndarray:
-    return rng.uniform(float(EVERYDAY_LO), float(EVERYDAY_HI), size=size).astype(np.float32)
+def everyday_range(dtype=np.float32):
+    """Gen.hs:208-214: (2^-p, 2^p - 1) with p = floatDigits: 24 for Float, 53 for Double."""
+    p = 24 if np.dtype(dtype) == np.float32 else 53
+    return 2.0 ** -p, 2.0 ** p - 1
 
 
-def gen_nice_float(rng: np.random.Generator, size) -> np.ndarray:
+def gen_everyday(rng: np.random.Generator, size, dtype=np.float32) -> np.ndarray:
+    lo, hi = everyday_range(dtype)
+    return rng.uniform(lo, hi, size=size).astype(dtype)
+
+
+def gen_nice_float(rng: np.random.Generator, size, dtype=np.float32) -> np.ndarray:
+    """genNiceFloat / genNiceDouble (Gen.hs:39-52)."""
     kind = rng.choice(3, size=size, p=[10 / 90, 40 / 90, 40 / 90])
-    v = gen_everyday(rng, size)
-    v = np.where(kind == 0, np.float32(0), np.where(kind == 1, v, -v))
-    return v.astype(np.float32)
+    v = gen_everyday(rng, size, dtype)
+    v = np.where(kind == 0, 0, np.where(kind == 1, v, -v))
+    return v.astype(dtype)
 
 
-def nice_scalar(rng) -> np.float32:
-    return gen_nice_float(rng, 1)[0]
+def nice_scalar(rng, dtype=np.float32):
+    return gen_nice_float(rng, 1, dtype)[0]
 
 
-def gen_unit(rng: np.random.Generator, size) -> np.ndarray:
+def gen_unit(rng: np.random.Generator, size, dtype=np.float32) -> np.ndarray:
     """U(-1,1): the large-n bench distribution."""
-    return rng.uniform(-1.0, 1.0, size=size).astype(np.float32)
+    return rng.uniform(-1.0, 1.0, size=size).astype(dtype)
 
 
 def span(n: int, inc: int, extra: int = 0) -> int:

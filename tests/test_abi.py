@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(blas):
     from lambda_blas_b200 import _ffi
     L = _ffi.lib()
     names = declared_symbols()
-    assert len(names) >= 55
+    assert len(names) >= 85
     for n in names:
         assert hasattr(L, n), f"liblbk.so does not export {n}"
     assert sorted(_ffi.PROTOTYPES) == names, "the ctypes binding and the header disagree"
@@ -45,17 +45,24 @@ def bits(a):
     return np.asarray(a, dtype=np.float32).view(np.uint32)
 
 
-def test_host_scalars_bit_exact(blas, oracle):      # Main.hs:31,33 (srotg, srotmg): product code, runs on the CPU
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_host_scalars_bit_exact(blas, oracle, dtype):      # Main.hs:31-34 (rotg, rotmg at Float and Double): product code on the CPU
     rng = np.random.default_rng(5)
     seen = set()
-    for _ in range(5000):
-        a = [nice_scalar(rng) for _ in range(4)]
-        assert np.array_equal(bits(list(blas.srotg(a[0], a[1]))), bits(list(oracle.srotg(a[0], a[1]))))
-        g, w = blas.srotmg(*a), oracle.srotmg(*a)
+    U = np.uint32 if dtype == np.float32 else np.uint64
+    bits = lambda a: np.asarray(a, dtype=dtype).view(U)  # noqa: E731
+    p = "s" if dtype == np.float32 else "d"
+    rotg, rotmg, orotg, orotmg = (getattr(m, p + n) for m in (blas, oracle) for n in ("rotg", "rotmg"))
+    for it in range(6000):
+        # the reference's domain (genNiceFloat / genNiceDouble); at Double its magnitudes (~1e15) always trip
+        # checkscale, so 1000 moderate cases are added to reach the FLAG0 / FLAG1 constructors there too
+        a = [nice_scalar(rng, dtype) for _ in range(4)] if it < 5000 else list(rng.uniform(-4, 4, 4).astype(dtype))
+        assert np.array_equal(bits(list(rotg(a[0], a[1]))), bits(list(orotg(a[0], a[1]))))
+        g, w = rotmg(*a), orotmg(*a)
         seen.add(g.flag)
         assert g.flag == w.flag
         assert np.array_equal(bits([g.d1, g.d2, g.x1, g.h11, g.h12, g.h21, g.h22]), bits(list(w)[1:]))
-        assert np.array_equal(bits(g.sparam()), bits(w.sparam()))
+        assert np.array_equal(bits(g.sparam(dtype)), bits(w.sparam(dtype)))
     assert seen == {-2, -1, 0, 1}
     assert blas.srotmg(1.5, 0.75, 2.0, 0.5).constructor == "FLAG0"
     assert list(blas.srotg(0, 0)) == [0, 0, 1, 0]          # Single.hs:281
@@ -86,7 +93,7 @@ def test_record_fold(blas):
     from lambda_blas_b200._ffi import Record
 
     def rec(f=(0, 0, 0), key=0, idx=-1):
-        return Record((C.c_float * 3)(*f), key, idx, 0)
+        return Record((C.c_double * 3)(*(list(f) + [0, 0, 0])[:3]), key, idx, 0)
     key = lambda v: int(np.float32(abs(v)).view(np.uint32))  # noqa: E731
     # sum in rank order
     assert sharded.combine_records(0, [rec((1.5,)), rec((2.25,)), rec((-0.75,))]) == 3.0
@@ -94,7 +101,7 @@ def test_record_fold(blas):
     assert sharded.combine_records(2, [rec(key=key(3.0), idx=5), rec(key=key(-3.0), idx=1000), rec()]) == 5
     assert sharded.combine_records(2, [rec(key=key(1.0), idx=5), rec(key=key(-3.0), idx=1000)]) == 1000
     assert sharded.combine_records(2, [rec(), rec(key=0, idx=77)]) == 77
-    assert sharded.combine_records(2, [rec(key=0xFFFFFFFF, idx=0), rec(key=key(np.inf), idx=9)]) == 0   # NaN at index 0 stays
+    assert sharded.combine_records(2, [rec(key=2 ** 64 - 1, idx=0), rec(key=key(np.inf), idx=9)]) == 0   # NaN at index 0 stays
     # nrm2: the three scaled sums add, then the Blue combine
     got = sharded.combine_records(1, [rec((0, 9.0, 0)), rec((0, 16.0, 0))])
     assert got == 5.0

@@ -9,24 +9,28 @@ from tests.gen import gen_unit
 pytestmark = pytest.mark.gpu
 
 
-def test_fill_hash_matches_numpy(blas, ctx):
-    v = ctx.alloc(100003).fill_hash(7, -1.0, 1.0)
-    P.assert_same(v.to_host(), blas.hash_fill_reference(100003, 7, -1.0, 1.0))
+@pytest.mark.parametrize("dtype", P.DTYPES)
+def test_fill_hash_matches_numpy(blas, ctx, dtype):
+    v = ctx.alloc(100003, dtype).fill_hash(7, -1.0, 1.0)
+    assert v.dtype == dtype
+    P.assert_same(v.to_host(), blas.hash_fill_reference(100003, 7, -1.0, 1.0, dtype=dtype))
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 31, 33, 1000, 4099, 65537, 1 << 20, (1 << 20) + 3])
 @pytest.mark.parametrize("off", [0, 1, 3, 5])
-def test_unit_paths_all_alignments(blas, ctx, oracle, n, off):
+@pytest.mark.parametrize("dtype", P.DTYPES)
+def test_unit_paths_all_alignments(blas, ctx, oracle, n, off, dtype):
     rng = np.random.default_rng(n * 8 + off)
-    u, v = gen_unit(rng, n + off), gen_unit(rng, n + off + 2)
+    E = float(P.eps_of(dtype))
+    u, v = gen_unit(rng, n + off, dtype), gen_unit(rng, n + off + 2, dtype)
     du, dv = ctx.to_device(u).view(off, n), ctx.to_device(v).view(off + 2 if off % 2 else off, n)
     hu, hv = du.to_host(), dv.to_host()
     got = blas.sdot(n, du, 1, dv, 1)
     want = oracle.sdot(n, hu, 1, hv, 1)
-    assert abs(float(got) - float(want)) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(hu.astype(np.float64) * hv)))
+    assert abs(float(got) - float(want)) <= 2 * n * E * float(np.sum(np.abs(hu.astype(np.float64) * hv)))
     assert blas.isamax(n, du, 1) == oracle.isamax(n, hu, 1)
-    assert abs(float(blas.snrm2(n, du, 1)) - float(oracle.snrm2(n, hu, 1))) <= 2 * n * 2.0 ** -24 * float(oracle.snrm2(n, hu, 1))
-    assert abs(float(blas.sasum(n, du, 1)) - float(oracle.sasum(n, hu, 1))) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(hu)))
+    assert abs(float(blas.snrm2(n, du, 1)) - float(oracle.snrm2(n, hu, 1))) <= 2 * n * E * float(oracle.snrm2(n, hu, 1))
+    assert abs(float(blas.sasum(n, du, 1)) - float(oracle.sasum(n, hu, 1))) <= 2 * n * E * float(np.sum(np.abs(hu)))
     P.assert_same(blas.saxpy(n, 1.000123, du, 1, dv, 1).to_host(), oracle.saxpy(n, 1.000123, hu, 1, hv, 1))
     xo, yo = blas.srot(n, du, 1, dv, 1, np.cos(0.3), np.sin(0.3))
     wx, wy = oracle.srot(n, hu, 1, hv, 1, np.cos(0.3), np.sin(0.3))
@@ -35,18 +39,20 @@ def test_unit_paths_all_alignments(blas, ctx, oracle, n, off):
 
 @pytest.mark.parametrize("variant", range(15))
 @pytest.mark.parametrize("threads", [128, 512])
-def test_every_variant(blas, ctx, oracle, variant, threads):
+@pytest.mark.parametrize("dtype", P.DTYPES)
+def test_every_variant(blas, ctx, oracle, variant, threads, dtype):
     n = 300007
     rng = np.random.default_rng(variant)
-    u, v = gen_unit(rng, n), gen_unit(rng, n)
+    E = float(P.eps_of(dtype))
+    u, v = gen_unit(rng, n, dtype), gen_unit(rng, n, dtype)
     u[12345] = -3.0; u[99999] = 3.0          # tie: the first wins
     du, dv = ctx.to_device(u), ctx.to_device(v)
     ctx.set_launch("all", variant, threads, 0)
     try:
         assert blas.isamax(n, du, 1) == 12345
         want = oracle.sdot(n, u, 1, v, 1)
-        assert abs(float(blas.sdot(n, du, 1, dv, 1)) - float(want)) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(u.astype(np.float64) * v)))
-        assert abs(float(blas.snrm2(n, du, 1)) - float(oracle.snrm2(n, u, 1))) <= 2 * n * 2.0 ** -24 * float(oracle.snrm2(n, u, 1))
+        assert abs(float(blas.sdot(n, du, 1, dv, 1)) - float(want)) <= 2 * n * E * float(np.sum(np.abs(u.astype(np.float64) * v)))
+        assert abs(float(blas.snrm2(n, du, 1)) - float(oracle.snrm2(n, u, 1))) <= 2 * n * E * float(oracle.snrm2(n, u, 1))
         y = dv.clone()
         blas.inplace.saxpy_(n, 0.5, du, 1, y, 1)
         P.assert_same(y.to_host(), oracle.saxpy(n, 0.5, u, 1, v, 1))
@@ -105,17 +111,20 @@ def test_cpp_mirror_example(tmp_path):
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 64, 1001, 4100, (1 << 20) + 1, (1 << 20) + 2])
 @pytest.mark.parametrize("offs", [(0, 0), (1, 0), (0, 3), (2, 1), (3, 3)])
-def test_reversed_pairing_paths(blas, ctx, oracle, n, offs):
+@pytest.mark.parametrize("dtype", P.DTYPES)
+def test_reversed_pairing_paths(blas, ctx, oracle, n, offs, dtype):
     """(incx,incy) = (1,-1) and (-1,1): the reversed-lane vector path and its scalar fallback, all alignments."""
     ox, oy = offs
     rng = np.random.default_rng(n + 7 * ox + 31 * oy)
-    u, v = gen_unit(rng, n + ox), gen_unit(rng, n + oy)
+    E = float(P.eps_of(dtype))
+    u, v = gen_unit(rng, n + ox, dtype), gen_unit(rng, n + oy, dtype)
     du, dv = ctx.to_device(u).view(ox, n), ctx.to_device(v).view(oy, n)
     hu, hv = u[ox:], v[oy:]
     for incx, incy in ((1, -1), (-1, 1)):
         want = oracle.sdot(n, hu, incx, hv, incy)
-        assert abs(float(blas.sdot(n, du, incx, dv, incy)) - float(want)) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(hu.astype(np.float64) * hv[::-1])))
-        assert abs(float(blas.sdsdot(n, 0.5, du, incx, dv, incy)) - float(oracle.sdsdot(n, 0.5, hu, incx, hv, incy))) <= float(np.spacing(np.float32(abs(oracle.sdsdot(n, 0.5, hu, incx, hv, incy)))))
+        assert abs(float(blas.sdot(n, du, incx, dv, incy)) - float(want)) <= 2 * n * E * float(np.sum(np.abs(hu.astype(np.float64) * hv[::-1])))
+        if dtype == np.float32:
+            assert abs(float(blas.sdsdot(n, 0.5, du, incx, dv, incy)) - float(oracle.sdsdot(n, 0.5, hu, incx, hv, incy))) <= float(np.spacing(np.float32(abs(oracle.sdsdot(n, 0.5, hu, incx, hv, incy)))))
         P.assert_same(blas.saxpy(n, 0.75, du, incx, dv, incy).to_host(), oracle.saxpy(n, 0.75, hu, incx, hv, incy))
         P.assert_same(blas.scopy(n, du, incx, dv, incy).to_host(), oracle.scopy(n, hu, incx, hv, incy))
         for got, wnt in zip(blas.sswap(n, du, incx, dv, incy), oracle.sswap(n, hu, incx, hv, incy)):
@@ -123,14 +132,16 @@ def test_reversed_pairing_paths(blas, ctx, oracle, n, offs):
         for got, wnt in zip(blas.srot(n, du, incx, dv, incy, 0.6, 0.8), oracle.srot(n, hu, incx, hv, incy, 0.6, 0.8)):
             P.assert_same(got.to_host(), wnt)
         for args in ((1.5, 0.75, 2.0, 0.5), (1.0, 2.0, 0.5, 3.0), (1e-9, 1.0, 1.0, 1.0)):
-            fl, ofl = blas.srotmg(*args), oracle.srotmg(*args)
+            pre = "s" if dtype == np.float32 else "d"
+            fl, ofl = getattr(blas, pre + "rotmg")(*args), getattr(oracle, pre + "rotmg")(*args)
             for got, wnt in zip(blas.srotm(fl, n, du, incx, dv, incy), oracle.srotm(ofl, n, hu, incx, hv, incy)):
                 P.assert_same(got.to_host(), wnt)
 
 
 @pytest.mark.parametrize("n", [1, 7, 8, 33, 1000, 65537])
 @pytest.mark.parametrize("incs", [(1, 1), (-1, -1), (1, -1), (-1, 1), (2, 3), (-3, 1), (0, 1), (1, 0)])
-def test_guard_bands_stay_untouched(blas, ctx, oracle, n, incs):
+@pytest.mark.parametrize("dtype", P.DTYPES)
+def test_guard_bands_stay_untouched(blas, ctx, oracle, n, incs, dtype):
     """compute-sanitizer is closed on this pool, so out-of-bounds WRITES are looked for directly: every in-place
     routine works on a window in the middle of a larger buffer of sentinels, and the sentinels must survive."""
     from lambda_blas_b200 import inplace as ip
@@ -138,15 +149,16 @@ def test_guard_bands_stay_untouched(blas, ctx, oracle, n, incs):
     G = 37                                              # odd guard: the window is misaligned on purpose
     lx, ly = 1 + (n - 1) * abs(incx), 1 + (n - 1) * abs(incy)
     rng = np.random.default_rng(n * 131 + incx * 7 + incy)
-    sent = np.float32(-12345.678)
+    sent = dtype(-12345.678)
 
     def fresh():
-        bx, by = np.full(lx + 2 * G, sent, np.float32), np.full(ly + 2 * G, sent, np.float32)
-        bx[G:G + lx] = gen_unit(rng, lx); by[G:G + ly] = gen_unit(rng, ly)
+        bx, by = np.full(lx + 2 * G, sent, dtype), np.full(ly + 2 * G, sent, dtype)
+        bx[G:G + lx] = gen_unit(rng, lx, dtype); by[G:G + ly] = gen_unit(rng, ly, dtype)
         dx, dy = ctx.to_device(bx), ctx.to_device(by)
         return bx, by, dx, dy, dx.view(G, lx), dy.view(G, ly)
 
-    fl, ofl = blas.srotmg(1.0, 2.0, 0.5, 3.0), oracle.srotmg(1.0, 2.0, 0.5, 3.0)
+    pre = "s" if dtype == np.float32 else "d"
+    fl, ofl = getattr(blas, pre + "rotmg")(1.0, 2.0, 0.5, 3.0), getattr(oracle, pre + "rotmg")(1.0, 2.0, 0.5, 3.0)
     ops = [
         ("saxpy", lambda x, y: ip.saxpy_(n, 0.5, x, incx, y, incy), lambda hx, hy: (hx, oracle.saxpy(n, 0.5, hx, incx, hy, incy))),
         ("scopy", lambda x, y: ip.scopy_(n, x, incx, y, incy), lambda hx, hy: (hx, oracle.scopy(n, hx, incx, hy, incy))),

@@ -12,24 +12,36 @@ import pytest
 from tests.gen import gen_nice_float, nice_scalar, span
 
 CASES = 300
-_FP = C.POINTER(C.c_float)
+DTYPES = [np.float32, np.float64]            # the reference runs every property for Float and Double (Main.hs:28-52)
 
 
 def p(a):
-    return a.ctypes.data_as(_FP)
+    return a.ctypes.data_as(C.POINTER(C.c_double if a.dtype == np.float64 else C.c_float))
 
 
-def bits(a):
-    return np.asarray(a, dtype=np.float32).view(np.uint32)
+def bits(a, dtype=None):
+    a = np.asarray(a) if dtype is None else np.asarray(a, dtype=dtype)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float32)
+    return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
 
 
-def same(a, b):
-    return np.array_equal(bits(a), bits(b))
+def same(a, b, dtype=None):
+    if dtype is None:
+        dtype = np.asarray(a).dtype if np.asarray(a).dtype in (np.float32, np.float64) else np.float32
+    return np.array_equal(bits(a, dtype), bits(b, dtype))
 
 
-def eq(a, b):
-    """Haskell's Eq on Float, which is what runTest uses (Main.hs:262-270): -0 == 0, NaN /= NaN."""
-    return np.array_equal(np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32))
+def eq(a, b, dtype=np.float32):
+    """Haskell's Eq on Float/Double, which is what runTest uses (Main.hs:262-270): -0 == 0, NaN /= NaN."""
+    return np.array_equal(np.asarray(a, dtype=dtype), np.asarray(b, dtype=dtype))
+
+
+def nl(oracle, dtype, name):
+    pre = "d" if dtype == np.float64 else "s"
+    if name == "iamax":
+        return getattr(oracle.netlib(), "nl_i" + pre + "amax")
+    return getattr(oracle.netlib(), "nl_" + pre + name)
 
 
 def test_readme_worked_example(oracle):
@@ -37,17 +49,18 @@ def test_readme_worked_example(oracle):
     assert oracle.sdot(3, [1, 2, 3], 1, [4, 5, 6], 1) == np.float32(32)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("seed", range(3))
-def test_dot_property(oracle, seed):          # Main.hs:28,59-79
-    rng, nl = np.random.default_rng(100 + seed), oracle.netlib()
+def test_dot_property(oracle, seed, dtype):   # Main.hs:28-29,59-79
+    rng = np.random.default_rng(100 + seed)
     for _ in range(CASES):
         n = int(rng.integers(1, 101)); incx, incy = (int(v) for v in rng.integers(-5, 6, 2))
-        u = gen_nice_float(rng, span(n, incx)); v = gen_nice_float(rng, span(n, incy))
-        assert same(oracle.sdot(n, u, incx, v, incy), nl.nl_sdot(n, p(u), incx, p(v), incy))
+        u = gen_nice_float(rng, span(n, incx), dtype); v = gen_nice_float(rng, span(n, incy), dtype)
+        assert same(oracle.dot(n, u, incx, v, incy), dtype(nl(oracle, dtype, "dot")(n, p(u), incx, p(v), incy)))
 
 
 def test_sdsdot_property(oracle):             # Main.hs:30,84-102
-    rng, nl = np.random.default_rng(7), oracle.netlib()
+    rng, nl = np.random.default_rng(7), oracle.netlib()  # noqa: F811
     for _ in range(CASES):
         n = int(rng.integers(1, 101)); a = nice_scalar(rng)
         incx, incy = (int(v) for v in rng.integers(-5, 6, 2))
@@ -55,36 +68,39 @@ def test_sdsdot_property(oracle):             # Main.hs:30,84-102
         assert same(oracle.sdsdot(n, a, u, incx, v, incy), nl.nl_sdsdot(n, float(a), p(u), incx, p(v), incy))
 
 
-@pytest.mark.parametrize("name", ["sasum", "snrm2", "isamax"])
-def test_ivi_property(oracle, name):          # Main.hs:37-42,239-257 (n from 0, incx in 1..5)
-    rng, nl = np.random.default_rng(11), oracle.netlib()
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name", ["asum", "nrm2", "iamax"])
+def test_ivi_property(oracle, name, dtype):   # Main.hs:37-42,239-257 (n from 0, incx in 1..5)
+    rng = np.random.default_rng(11)
     for _ in range(CASES):
         n = int(rng.integers(0, 101)); incx = int(rng.integers(1, 6))
-        u = gen_nice_float(rng, max(1 + (n - 1) * incx, 0))
-        if name == "isamax":                  # compared as succ (iamax ..), Main.hs:41
-            assert oracle.isamax(n, u, incx) + 1 == nl.nl_isamax(n, p(u) if u.size else None, incx)
+        u = gen_nice_float(rng, max(1 + (n - 1) * incx, 0), dtype)
+        want = nl(oracle, dtype, name)(n, p(u) if u.size else None, incx)
+        if name == "iamax":                   # compared as succ (iamax ..), Main.hs:41
+            assert oracle.iamax(n, u, incx) + 1 == want
         else:
-            want = getattr(nl, "nl_" + name)(n, p(u) if u.size else None, incx)
-            assert same(getattr(oracle, name)(n, u, incx), want)
+            assert same(getattr(oracle, name)(n, u, incx), dtype(want))
 
 
-def test_scal_property(oracle):               # Main.hs:43,405-424
-    rng, nl = np.random.default_rng(13), oracle.netlib()
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_scal_property(oracle, dtype):        # Main.hs:43-44,405-424
+    rng = np.random.default_rng(13)
     for _ in range(CASES):
-        n = int(rng.integers(1, 101)); a = nice_scalar(rng); incx = int(rng.integers(1, 6))
-        u = gen_nice_float(rng, span(n, incx)); w = u.copy()
-        nl.nl_sscal(n, float(a), p(w), incx)
-        assert same(oracle.sscal(n, a, u, incx), w)
+        n = int(rng.integers(1, 101)); a = nice_scalar(rng, dtype); incx = int(rng.integers(1, 6))
+        u = gen_nice_float(rng, span(n, incx), dtype); w = u.copy()
+        nl(oracle, dtype, "scal")(n, float(a), p(w), incx)
+        assert same(oracle.scal(n, a, u, incx), w)
 
 
-def test_copy_property(oracle):               # Main.hs:45,429-451 (inc 0 included, tails kept)
-    rng, nl = np.random.default_rng(17), oracle.netlib()
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_copy_property(oracle, dtype):        # Main.hs:45-46,429-451 (inc 0 included, tails kept)
+    rng = np.random.default_rng(17)
     for _ in range(CASES * 3):
         n = int(rng.integers(1, 6)); mx, my = (int(v) for v in rng.integers(1, 3, 2))
         incx, incy = (int(v) for v in rng.integers(-5, 6, 2))
-        u = gen_nice_float(rng, span(n, incx, mx)); v = gen_nice_float(rng, span(n, incy, my)); w = v.copy()
-        nl.nl_scopy(n, p(u), incx, p(w), incy)
-        assert same(oracle.scopy(n, u, incx, v, incy), w)
+        u = gen_nice_float(rng, span(n, incx, mx), dtype); v = gen_nice_float(rng, span(n, incy, my), dtype); w = v.copy()
+        nl(oracle, dtype, "copy")(n, p(u), incx, p(w), incy)
+        assert same(oracle.copy(n, u, incx, v, incy), w)
 
 
 def _nz(rng, lo, hi):
@@ -94,61 +110,67 @@ def _nz(rng, lo, hi):
             return v
 
 
-def test_swap_property(oracle):               # Main.hs:47,107-129
-    rng, nl = np.random.default_rng(19), oracle.netlib()
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_swap_property(oracle, dtype):        # Main.hs:47-48,107-129
+    rng = np.random.default_rng(19)
     for _ in range(CASES * 3):
         n = int(rng.integers(1, 6)); mx, my = (int(v) for v in rng.integers(0, 3, 2))
         incx, incy = _nz(rng, -5, 5), _nz(rng, -5, 5)
-        u = gen_nice_float(rng, span(n, incx, mx)); v = gen_nice_float(rng, span(n, incy, my))
+        u = gen_nice_float(rng, span(n, incx, mx), dtype); v = gen_nice_float(rng, span(n, incy, my), dtype)
         a, b = u.copy(), v.copy()
-        nl.nl_sswap(n, p(a), incx, p(b), incy)
-        xo, yo = oracle.sswap(n, u, incx, v, incy)
+        nl(oracle, dtype, "swap")(n, p(a), incx, p(b), incy)
+        xo, yo = oracle.swap(n, u, incx, v, incy)
         assert same(xo, a) and same(yo, b)
 
 
-def test_rot_property(oracle):                # Main.hs:49,153-176 (inc in {-5,5}, c=cos a, s=sin a)
-    rng, nl = np.random.default_rng(23), oracle.netlib()
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_rot_property(oracle, dtype):         # Main.hs:49-50,153-176 (inc in {-5,5}, c=cos a, s=sin a)
+    rng = np.random.default_rng(23)
     for _ in range(CASES):
-        n = int(rng.integers(1, 101)); ang = nice_scalar(rng)
+        n = int(rng.integers(1, 101)); ang = nice_scalar(rng, dtype)
         incx, incy = (int(v) for v in rng.choice([-5, 5], 2))
-        c, s = np.float32(np.cos(ang)), np.float32(np.sin(ang))
-        u = gen_nice_float(rng, span(n, incx)); v = gen_nice_float(rng, span(n, incy))
+        c, s = dtype(np.cos(ang)), dtype(np.sin(ang))
+        u = gen_nice_float(rng, span(n, incx), dtype); v = gen_nice_float(rng, span(n, incy), dtype)
         a, b = u.copy(), v.copy()
-        nl.nl_srot(n, p(a), incx, p(b), incy, float(c), float(s))
-        xo, yo = oracle.srot(n, u, incx, v, incy, c, s)
+        nl(oracle, dtype, "rot")(n, p(a), incx, p(b), incy, float(c), float(s))
+        xo, yo = oracle.rot(n, u, incx, v, incy, c, s)
         assert same(xo, a) and same(yo, b)
 
 
-def test_axpy_property(oracle):               # Main.hs:51,456-477
-    rng, nl = np.random.default_rng(29), oracle.netlib()
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_axpy_property(oracle, dtype):        # Main.hs:51-52,456-477
+    rng = np.random.default_rng(29)
     for _ in range(CASES):
-        n = int(rng.integers(1, 101)); a = nice_scalar(rng)
+        n = int(rng.integers(1, 101)); a = nice_scalar(rng, dtype)
         incx, incy = (int(v) for v in rng.choice([-5, 5], 2))
         mx, my = (int(v) for v in rng.integers(1, 101, 2))
-        u = gen_nice_float(rng, mx + (n - 1) * abs(incx)); v = gen_nice_float(rng, my + (n - 1) * abs(incy))
+        u = gen_nice_float(rng, mx + (n - 1) * abs(incx), dtype); v = gen_nice_float(rng, my + (n - 1) * abs(incy), dtype)
         w = v.copy()
-        nl.nl_saxpy(n, float(a), p(u), incx, p(w), incy)
-        assert same(oracle.saxpy(n, a, u, incx, v, incy), w)
+        nl(oracle, dtype, "axpy")(n, float(a), p(u), incx, p(w), incy)
+        assert same(oracle.axpy(n, a, u, incx, v, incy), w)
 
 
-def test_rotg_property(oracle):               # Main.hs:31,134-148
-    rng, nl = np.random.default_rng(31), oracle.netlib()
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_rotg_property(oracle, dtype):        # Main.hs:31-32,134-148
+    rng = np.random.default_rng(31)
+    CT = C.c_double if dtype == np.float64 else C.c_float
     for _ in range(CASES * 3):
-        sa, sb = nice_scalar(rng), nice_scalar(rng)
-        a, b, c, s = (C.c_float(float(v)) for v in (sa, sb, 0, 0))
-        nl.nl_srotg(C.byref(a), C.byref(b), C.byref(c), C.byref(s))
-        got = oracle.srotg(sa, sb)
+        sa, sb = nice_scalar(rng, dtype), nice_scalar(rng, dtype)
+        a, b, c, s = (CT(float(v)) for v in (sa, sb, 0, 0))
+        nl(oracle, dtype, "rotg")(C.byref(a), C.byref(b), C.byref(c), C.byref(s))
+        got = (oracle.drotg if dtype == np.float64 else oracle.srotg)(sa, sb)
         # value equality: for sa == 0 > sb netlib yields c = -0 where the reference writes the
         # literal 0 (Single.hs:289); the reference's `==` accepts that and so do we
-        assert eq(list(got), [a.value, b.value, c.value, s.value])
+        assert eq(list(got), [a.value, b.value, c.value, s.value], dtype)
 
 
-def _netlib_rotmg(nl, sd1, sd2, sx1, sy1):
-    d1, d2, x1 = (C.c_float(float(v)) for v in (sd1, sd2, sx1))
-    par = np.zeros(5, dtype=np.float32)
-    nl.nl_srotmg(C.byref(d1), C.byref(d2), C.byref(x1), float(sy1), p(par))
+def _netlib_rotmg(fn, dtype, sd1, sd2, sx1, sy1):
+    CT = C.c_double if dtype == np.float64 else C.c_float
+    d1, d2, x1 = (CT(float(v)) for v in (sd1, sd2, sx1))
+    par = np.zeros(5, dtype=dtype)
+    fn(C.byref(d1), C.byref(d2), C.byref(x1), float(sy1), p(par))
     flag = int(par[0])
-    f32 = np.float32
+    f32 = dtype
     # the view test/Foreign.hs:245-253 takes of the Fortran outputs
     if flag == -2:
         return (-2,)
@@ -169,29 +191,46 @@ def _view(m):
     return (1, m.d1, m.d2, m.x1, m.h11, m.h22)
 
 
-def test_rotmg_property(oracle):              # Main.hs:33,181-197
-    rng, nl = np.random.default_rng(37), oracle.netlib()
-    seen = set()
-    for _ in range(CASES * 10):
-        args = [nice_scalar(rng) for _ in range(4)]
-        want, got = _netlib_rotmg(nl, *args), _view(oracle.srotmg(*args))
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_rotmg_property(oracle, dtype):       # Main.hs:33-34,181-197
+    rng = np.random.default_rng(37)
+    seen, skipped = set(), 0
+    rotmg = oracle.drotmg if dtype == np.float64 else oracle.srotmg
+    for it in range(CASES * 12):
+        # the reference's generator; plus moderate magnitudes, which at Double are the only way to FLAG0 / FLAG1
+        args = [nice_scalar(rng, dtype) for _ in range(4)] if it < CASES * 10 else list(rng.uniform(-4, 4, 4).astype(dtype))
+        want, got = _netlib_rotmg(nl(oracle, dtype, "rotmg"), dtype, *args), _view(rotmg(*args))
+        if dtype == np.float64 and want != got:
+            # drotmg.f carries GAMSQ = 16777216, RGAMSQ = 5.9604645e-8 where the polymorphic reference uses the
+            # single-precision literals 1.67772e7, 5.96046e-8 (Single.hs:367-369) for both instances: a d1 or d2
+            # that lands between the two thresholds is rescaled by one and not by the other.  The reference's own
+            # drotmg test has the same (rare) exposure; such cases are counted, not compared.
+            mags = [abs(float(v)) for v in list(want[1:3]) + list(got[1:3]) if float(v) != 0]
+            if any(1.67772e7 <= m * s <= 16777216.0 * 1.0000001 or 5.96046e-8 * 0.9999999 <= m * s <= 5.9604645e-8
+                   for m in mags for s in (1.0, 4096.0 ** 2, 4096.0 ** -2)):
+                skipped += 1
+                continue
         seen.add(got[0])
-        assert want[0] == got[0] and same(list(want[1:]), list(got[1:])), (args, want, got)
+        assert want[0] == got[0] and same(list(want[1:]), list(got[1:]), dtype), (args, want, got)
     assert seen == {-2, -1, 0, 1}
+    assert skipped <= 3
 
 
-def test_rotm_property(oracle):               # Main.hs:35,202-225 (flags built by rotmg)
-    rng, nl = np.random.default_rng(41), oracle.netlib()
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_rotm_property(oracle, dtype):        # Main.hs:35-36,202-225 (flags built by rotmg)
+    rng = np.random.default_rng(41)
     seen = set()
-    for _ in range(CASES * 2):
-        flags = oracle.srotmg(*[nice_scalar(rng) for _ in range(4)])
+    rotmg = oracle.drotmg if dtype == np.float64 else oracle.srotmg
+    for it in range(CASES * 2):
+        args = [nice_scalar(rng, dtype) for _ in range(4)] if it % 4 else list(rng.uniform(-4, 4, 4).astype(dtype))
+        flags = rotmg(*args)
         seen.add(flags.flag)
         n = int(rng.integers(1, 101)); incx, incy = _nz(rng, -5, 5), _nz(rng, -5, 5)
         mx, my = (int(v) for v in rng.integers(1, 101, 2))
-        u = gen_nice_float(rng, mx + (n - 1) * abs(incx)); v = gen_nice_float(rng, my + (n - 1) * abs(incy))
+        u = gen_nice_float(rng, mx + (n - 1) * abs(incx), dtype); v = gen_nice_float(rng, my + (n - 1) * abs(incy), dtype)
         a, b = u.copy(), v.copy()
-        par = flags.sparam()
-        nl.nl_srotm(n, p(a), incx, p(b), incy, p(par))
-        xo, yo = oracle.srotm(flags, n, u, incx, v, incy)
+        par = flags.sparam(dtype)
+        nl(oracle, dtype, "rotm")(n, p(a), incx, p(b), incy, p(par))
+        xo, yo = oracle.rotm(flags, n, u, incx, v, incy)
         assert same(xo, a) and same(yo, b)
     assert seen == {-2, -1, 0, 1}

@@ -27,22 +27,29 @@ def _key(v):
     return 0 if b > 0x7F800000 else int(b)
 
 
+def _key64(v):
+    b = np.abs(np.float64(v)).view(np.uint64)
+    return 0 if b > 0x7FF0000000000000 else int(b)
+
+
 def _local_record(kind, xs, ys, lo):
     """What a rank's reduction kernel leaves in its record for the shard xs (global offset lo)."""
     from lambda_blas_b200._ffi import Record
-    r = Record((C.c_float * 3)(0, 0, 0), 0, -1, 0)
+    r = Record((C.c_double * 3)(0, 0, 0), 0, -1, 0)
     if xs.size == 0:
         return r
+    T = xs.dtype.type
     if kind == 0:
-        r.f[0] = float(np.sum(xs.astype(np.float32) * ys.astype(np.float32), dtype=np.float32))
+        r.f[0] = float(np.sum(xs * ys, dtype=T))
     elif kind == 1:
-        r.f[1] = float(np.sum(xs.astype(np.float32) ** 2, dtype=np.float32))
+        r.f[1] = float(np.sum(xs ** 2, dtype=T))
     else:
-        keys = np.array([_key(v) for v in xs], dtype=np.uint32)
+        kf = _key64 if xs.dtype == np.float64 else _key
+        keys = np.array([kf(v) for v in xs], dtype=np.uint64)
         i = int(np.argmax(keys))             # first maximum
         r.key, r.idx = int(keys[i]), lo + i
         if lo == 0 and np.isnan(xs[0]):
-            r.key, r.idx = 0xFFFFFFFF, 0
+            r.key, r.idx = 2 ** 64 - 1, 0
     return r
 
 
@@ -55,9 +62,10 @@ def _worker(rank, world, port, seed, out):
     from oracle import oracle
     rng = np.random.default_rng(seed)           # same stream on every rank: the "global" vectors
     ok = True
-    for n in [1, 2, 3, 101, 1000, 4097]:
-        x = rng.uniform(-1, 1, n).astype(np.float32)
-        y = rng.uniform(-1, 1, n).astype(np.float32)
+    for n, dt in [(n, dt) for dt in (np.float32, np.float64) for n in [1, 2, 3, 101, 1000, 4097]]:
+        eps = 2.0 ** -24 if dt == np.float32 else 2.0 ** -53
+        x = rng.uniform(-1, 1, n).astype(dt)
+        y = rng.uniform(-1, 1, n).astype(dt)
         if n >= 101:                             # a tie that straddles the shard boundary, and a NaN that must lose
             x[n // 2 - 1] = 5.0; x[n // 2 + 3] = -5.0; x[7] = np.nan
         lo, hi = sharded.shard_range(n, world, rank)
@@ -67,19 +75,19 @@ def _worker(rank, world, port, seed, out):
             gathered = [torch.empty_like(buf) for _ in range(world)]
             dist.all_gather(gathered, buf)
             recs = [Record.from_buffer_copy(bytes(g.numpy().tobytes())) for g in gathered]
-            got = sharded.combine_records(kind, recs)
+            got = sharded.combine_records(kind, recs, dt == np.float64)
             if kind == 2:
-                ok &= got == oracle.isamax(n, x, 1)
+                ok &= got == oracle.iamax(n, x, 1)
             elif kind == 0:
                 xx = np.where(np.isnan(x), 0, x)
                 want = float(np.dot(xx.astype(np.float64), y))
                 rec2 = [Record.from_buffer_copy(bytes(r)) for r in recs]
                 if not np.isnan(x).any():
-                    ok &= abs(got - want) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(xx.astype(np.float64) * y)))
+                    ok &= abs(got - want) <= 2 * n * eps * float(np.sum(np.abs(xx.astype(np.float64) * y)))
                 del rec2
             else:
                 if not np.isnan(x).any():
-                    ok &= abs(got - float(oracle.snrm2(n, x, 1))) <= 2 * n * 2.0 ** -24 * float(oracle.snrm2(n, x, 1))
+                    ok &= abs(got - float(oracle.nrm2(n, x, 1))) <= 2 * n * eps * float(oracle.nrm2(n, x, 1))
     t = torch.tensor([1 if ok else 0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
