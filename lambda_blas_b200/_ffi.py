@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblbk.so")
+# LBK_LIBRARY: developer knob for A/B runs of differently built libraries (tools/); the default is the in-tree build
+LIB_PATH = os.environ.get("LBK_LIBRARY") or os.path.join(_HERE, "liblbk.so")
 
 STATUS_NAMES = {0: "LBK_OK", 1: "LBK_ERR_CUDA", 2: "LBK_ERR_NCCL", 3: "LBK_ERR_ARG", 4: "LBK_ERR_RANGE",
                 5: "LBK_ERR_ALIAS", 6: "LBK_ERR_UNSUPPORTED", 7: "LBK_ERR_NOMEM"}

@@ -33,6 +33,14 @@ typedef long long i64;
 typedef unsigned long long u64;
 
 constexpr int kMaxThreads = 512;        // launch bound of every streaming kernel
+// Resident 512-thread blocks per SM the reductions are compiled for (a register cap of 40).  Left to
+// itself ptxas spends 45-60 registers on hoisting the tail's address arithmetic, which costs a resident
+// block per SM and 3-6% of the streaming rate (profiles/r01_tune_reductions_minblocks{1,3}.csv); the shapes with
+// 256 bytes in flight per operand per thread cannot fit and keep the plain bound.
+#ifndef LBK_REDUCE_MINB
+#define LBK_REDUCE_MINB 3
+#endif
+constexpr int reduce_min_blocks(int bytes_per_operand) { return bytes_per_operand >= 256 ? 1 : LBK_REDUCE_MINB; }
 constexpr u64 kNanKey = ~0ull;
 
 // ------------------------------------------------------------------------------------------------
@@ -183,6 +191,12 @@ template <class T> struct CopyF {   // Single.hs:127   \_ x -> x
     using Scalar = T;
     static constexpr bool RX = true, RY = false, WX = false, WY = true;
     __device__ __forceinline__ void operator()(T &x, T &y) const { y = x; }
+};
+template <class T> struct FillF {   // no reference counterpart: lbk_vec_fill (test / bench set-up), a pure store stream
+    using Scalar = T;
+    T value;
+    static constexpr bool RX = false, RY = false, WX = true, WY = false;
+    __device__ __forceinline__ void operator()(T &x, T &) const { x = value; }
 };
 template <class T> struct SwapF {   // Single.hs:143-145
     using Scalar = T;
@@ -363,9 +377,10 @@ map_strided_kernel(F f, const typename F::Scalar *xr, typename F::Scalar *xw, i6
 // ------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------
-// The record a block (and, across GPUs, a rank) contributes.  Layout shared with the host
-// (lbk_record in include/lbk.h): f[0..2] partial sums (held in double, so float partials are exact),
-// key/idx the iamax candidate.
+// The record a GPU contributes to a sharded reduction, and the slot a block's partial result lives in
+// between the two passes.  Layout shared with the host (lbk_record in include/lbk.h): f[0..2] partial
+// sums (held in double, so float partials are exact), key/idx the iamax candidate (or, for nrm2, the
+// bits of |x[0]| for the n == 1 rule).
 struct Record {
     double f[3];
     u64 key;
@@ -375,16 +390,14 @@ struct Record {
 static_assert(sizeof(Record) == 48, "Record is 48 bytes");
 constexpr int kRecordWords = sizeof(Record) / 4;
 
-__device__ __forceinline__ Record shfl_xor_record(const Record &r, int mask)
+__host__ __device__ __forceinline__ Record empty_record()
 {
-    Record o;
-    o.f[0] = __shfl_xor_sync(0xffffffffu, r.f[0], mask);
-    o.f[1] = __shfl_xor_sync(0xffffffffu, r.f[1], mask);
-    o.f[2] = __shfl_xor_sync(0xffffffffu, r.f[2], mask);
-    o.key = __shfl_xor_sync(0xffffffffu, r.key, mask);
-    o.idx = __shfl_xor_sync(0xffffffffu, r.idx, mask);
-    o.pad = 0;
-    return o;
+    Record r;
+    r.f[0] = r.f[1] = r.f[2] = 0.0;
+    r.key = 0ull;
+    r.idx = -1;
+    r.pad = 0;
+    return r;
 }
 
 // Blue's scaled accumulation (as in LAPACK 3.10 *nrm2): |x| > big is accumulated as (x*sbig)^2,
@@ -405,44 +418,61 @@ template <> struct Blue<double> {
     static constexpr double ssml = 4.4989137945431964e+161;    // 2^537
 };
 
-// Op concept:  Scalar, Acc, zero(), step(acc,x,y,ord) [or step_pack], to_record, single, merge
-template <class T> struct DotOp {       // Single.hs:81-82
+// Op concept
+//   Scalar, Acc, zero(), step(acc,x,y,ord) [or step_pack]      the streaming loop (registers only)
+//   Partial, empty(), merge(a,b), shfl(p,mask)                  what a thread / warp / block contributes: as
+//                                                               few registers as the routine needs, so that the
+//                                                               tail does not set the kernel's register count
+//   add_acc(p,acc), single(p,x,y,idx)                           accumulator / one scalar element -> partial
+//   store(slot,p), load(slot)                                   a block's partial in its Record slot (only the
+//                                                               fields the routine uses are moved)
+// Partial sums are doubles for both element types: a float accumulator converts exactly, and the
+// combine tree (warp, block, grid, GPUs) then adds without further float rounding.
+struct SumPartial { double s; };
+template <class Derived> struct SumOpBase {
+    using Partial = SumPartial;
+    __device__ static __forceinline__ Partial empty() { return {0.0}; }
+    __device__ static __forceinline__ Partial merge(const Partial &a, const Partial &b) { return {a.s + b.s}; }
+    __device__ static __forceinline__ Partial shfl(const Partial &p, int m) { return {__shfl_xor_sync(0xffffffffu, p.s, m)}; }
+    __device__ static __forceinline__ void store(Record *slot, const Partial &p) { __stcg(&slot->f[0], p.s); }
+    __device__ static __forceinline__ Partial load(const Record *slot) { return {__ldcg(&slot->f[0])}; }
+    __device__ static __forceinline__ void to_record(Record &r, const Partial &p) { r.f[0] = p.s; }
+};
+template <class T> struct DotOp : SumOpBase<DotOp<T>> {       // Single.hs:81-82
     using Scalar = T;
+    using Partial = SumPartial;
     static constexpr bool TWO = true, IS_IAMAX = false, HAS_PACK_STEP = false;
     struct Acc { T s; };
     __device__ static __forceinline__ Acc zero() { return {0}; }
     __device__ static __forceinline__ void step(Acc &a, T x, T y, unsigned) { a.s = fma_(x, y, a.s); }
-    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = (double)a.s; }
-    __device__ static __forceinline__ void single(Record &r, T x, T y, i64) { r.f[0] = fma((double)x, (double)y, r.f[0]); }
-    __host__ __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
-    { Record o = a; o.f[0] = a.f[0] + b.f[0]; return o; }
+    __device__ static __forceinline__ void add_acc(Partial &p, const Acc &a) { p.s += (double)a.s; }
+    __device__ static __forceinline__ void single(Partial &p, T x, T y, i64) { p.s = fma((double)x, (double)y, p.s); }
 };
-struct DsdotOp {     // Single.hs:238-262: float inputs, products and sum in double
+struct DsdotOp : SumOpBase<DsdotOp> {     // Single.hs:238-262: float inputs, products and sum in double
     using Scalar = float;
+    using Partial = SumPartial;
     static constexpr bool TWO = true, IS_IAMAX = false, HAS_PACK_STEP = false;
     struct Acc { double s; };
     __device__ static __forceinline__ Acc zero() { return {0.0}; }
     __device__ static __forceinline__ void step(Acc &a, float x, float y, unsigned) { a.s = fma((double)x, (double)y, a.s); }
-    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = a.s; }
-    __device__ static __forceinline__ void single(Record &r, float x, float y, i64) { r.f[0] = fma((double)x, (double)y, r.f[0]); }
-    __host__ __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
-    { Record o = a; o.f[0] = a.f[0] + b.f[0]; return o; }
+    __device__ static __forceinline__ void add_acc(Partial &p, const Acc &a) { p.s += a.s; }
+    __device__ static __forceinline__ void single(Partial &p, float x, float y, i64) { p.s = fma((double)x, (double)y, p.s); }
 };
-template <class T> struct AsumOp {      // Single.hs:163
+template <class T> struct AsumOp : SumOpBase<AsumOp<T>> {     // Single.hs:163
     using Scalar = T;
+    using Partial = SumPartial;
     static constexpr bool TWO = false, IS_IAMAX = false, HAS_PACK_STEP = false;
     struct Acc { T s; };
     __device__ static __forceinline__ Acc zero() { return {0}; }
     __device__ static __forceinline__ void step(Acc &a, T x, T, unsigned) { a.s += abs_(x); }
-    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = (double)a.s; }
-    __device__ static __forceinline__ void single(Record &r, T x, T, i64) { r.f[0] += (double)abs_(x); }
-    __host__ __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
-    { Record o = a; o.f[0] = a.f[0] + b.f[0]; return o; }
+    __device__ static __forceinline__ void add_acc(Partial &p, const Acc &a) { p.s += (double)a.s; }
+    __device__ static __forceinline__ void single(Partial &p, T x, T, i64) { p.s += (double)abs_(x); }
 };
 template <class T> struct Nrm2Op {      // Single.hs:180-199, restated as Blue's three accumulators
     using Scalar = T;
     static constexpr bool TWO = false, IS_IAMAX = false, HAS_PACK_STEP = true;
     struct Acc { T big, med, sml; };
+    struct Partial { double big, med, sml; };
     __device__ static __forceinline__ Acc zero() { return {0, 0, 0}; }
     __device__ static __forceinline__ void step(Acc &a, T x, T, unsigned)
     {
@@ -468,31 +498,41 @@ template <class T> struct Nrm2Op {      // Single.hs:180-199, restated as Blue's
             for (int l = 0; l < VEC; ++l) step(a, x.v[l], T(0), 0u);
         }
     }
-    __device__ static __forceinline__ void to_record(Record &r, const Acc &a) { r.f[0] = (double)a.big; r.f[1] = (double)a.med; r.f[2] = (double)a.sml; }
-    __device__ static __forceinline__ void single(Record &r, T x, T, i64)
-    {   // the strided / scalar path classifies in T and accumulates in the record's doubles
+    __device__ static __forceinline__ Partial empty() { return {0.0, 0.0, 0.0}; }
+    __device__ static __forceinline__ Partial merge(const Partial &a, const Partial &b) { return {a.big + b.big, a.med + b.med, a.sml + b.sml}; }
+    __device__ static __forceinline__ Partial shfl(const Partial &p, int m)
+    { return {__shfl_xor_sync(0xffffffffu, p.big, m), __shfl_xor_sync(0xffffffffu, p.med, m), __shfl_xor_sync(0xffffffffu, p.sml, m)}; }
+    __device__ static __forceinline__ void add_acc(Partial &p, const Acc &a) { p.big += (double)a.big; p.med += (double)a.med; p.sml += (double)a.sml; }
+    __device__ static __forceinline__ void single(Partial &p, T x, T, i64)
+    {   // the strided / scalar path classifies in T and accumulates in the partial's doubles
         const T ax = abs_(x);
-        if (ax > Blue<T>::big) { const double t = (double)(ax * Blue<T>::sbig); r.f[0] = fma(t, t, r.f[0]); }
-        else if (ax < Blue<T>::sml) { const double t = (double)(ax * Blue<T>::ssml); r.f[2] = fma(t, t, r.f[2]); }
-        else { const double t = (double)ax; r.f[1] = fma(t, t, r.f[1]); }
+        if (ax > Blue<T>::big) { const double t = (double)(ax * Blue<T>::sbig); p.big = fma(t, t, p.big); }
+        else if (ax < Blue<T>::sml) { const double t = (double)(ax * Blue<T>::ssml); p.sml = fma(t, t, p.sml); }
+        else { const double t = (double)ax; p.med = fma(t, t, p.med); }
     }
-    __host__ __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
-    { Record o = a; o.f[0] = a.f[0] + b.f[0]; o.f[1] = a.f[1] + b.f[1]; o.f[2] = a.f[2] + b.f[2]; return o; }
+    __device__ static __forceinline__ void store(Record *slot, const Partial &p) { __stcg(&slot->f[0], p.big); __stcg(&slot->f[1], p.med); __stcg(&slot->f[2], p.sml); }
+    __device__ static __forceinline__ Partial load(const Record *slot) { return {__ldcg(&slot->f[0]), __ldcg(&slot->f[1]), __ldcg(&slot->f[2])}; }
+    __device__ static __forceinline__ void to_record(Record &r, const Partial &p) { r.f[0] = p.big; r.f[1] = p.med; r.f[2] = p.sml; }
 };
 // iamax (Single.hs:217-220).  key = bit pattern of |x| (monotone for non-NaN), NaN -> 0 so that it
 // can never displace an earlier element (`|best| < |NaN|` is false in the reference's fold); the
-// "NaN at logical index 0 is never displaced" half of the rule is applied once, at the finish.
-template <class T> __device__ __forceinline__ u64 amax_key(T x)
+// "NaN at logical index 0 is never displaced" half of the rule is one extra candidate (all-ones key,
+// index 0) contributed by the thread that owns element 0.
+template <class T> struct AmaxKey { typedef unsigned type; };
+template <> struct AmaxKey<double> { typedef u64 type; };
+template <class T> __device__ __forceinline__ typename AmaxKey<T>::type amax_key(T x)
 {
-    const u64 b = abs_bits(x);
-    return (x != x) ? 0ull : b;
+    return (x != x) ? (typename AmaxKey<T>::type)0 : (typename AmaxKey<T>::type)abs_bits(x);
 }
 template <class T> struct IamaxOp {
     using Scalar = T;
+    using Key = typename AmaxKey<T>::type;
     static constexpr bool TWO = false, IS_IAMAX = true, HAS_PACK_STEP = true;
+    static constexpr Key kKeyMax = ~(Key)0;
     // running maximum of |x| (-1 = nothing seen yet; any |x| >= 0 beats it) and the ordinal, within this
     // thread's element sequence, of the FIRST element that reached it
     struct Acc { T val; unsigned ord; };
+    struct Partial { i64 idx; Key key; };      // idx < 0: no candidate
     __device__ static __forceinline__ Acc zero() { return {T(-1), 0u}; }
     __device__ static __forceinline__ void step(Acc &a, T x, T, unsigned ord)
     {
@@ -515,49 +555,43 @@ template <class T> struct IamaxOp {
             a.val = m; a.ord = ord0 + lane;
         }
     }
-    __device__ static __forceinline__ void to_record(Record &, const Acc &) {}
-    __device__ static __forceinline__ void single(Record &r, T x, T, i64 idx)
-    {
-        const u64 k = amax_key(x);
-        if (r.idx < 0 || k > r.key || (k == r.key && idx < r.idx)) { r.key = k; r.idx = idx; }
-    }
-    // larger key wins; on a tie the lower index; idx < 0 means "no candidate"
-    __host__ __device__ static __forceinline__ Record merge(const Record &a, const Record &b)
+    __device__ static __forceinline__ Partial empty() { return {-1, 0}; }
+    __device__ static __forceinline__ Partial nan_at_zero() { return {0, kKeyMax}; }
+    __device__ static __forceinline__ Partial candidate(T absval, i64 idx) { return {idx, (Key)abs_bits(absval)}; }
+    // larger key wins; on a tie the lower index
+    __device__ static __forceinline__ Partial merge(const Partial &a, const Partial &b)
     {
         if (b.idx < 0) return a;
         if (a.idx < 0) return b;
         if (b.key > a.key || (b.key == a.key && b.idx < a.idx)) return b;
         return a;
     }
+    __device__ static __forceinline__ Partial shfl(const Partial &p, int m)
+    { return {__shfl_xor_sync(0xffffffffu, p.idx, m), __shfl_xor_sync(0xffffffffu, p.key, m)}; }
+    __device__ static __forceinline__ void single(Partial &p, T x, T, i64 idx) { p = merge(p, Partial{idx, amax_key(x)}); }
+    __device__ static __forceinline__ void store(Record *slot, const Partial &p) { __stcg(&slot->key, (u64)p.key); __stcg(&slot->idx, p.idx); }
+    __device__ static __forceinline__ Partial load(const Record *slot) { return {__ldcg(&slot->idx), (Key)__ldcg(&slot->key)}; }
+    __device__ static __forceinline__ void to_record(Record &r, const Partial &p) { r.key = p.key == kKeyMax ? kNanKey : (u64)p.key; r.idx = p.idx; }
 };
-
-__host__ __device__ __forceinline__ Record empty_record()
-{
-    Record r;
-    r.f[0] = r.f[1] = r.f[2] = 0.0;
-    r.key = 0ull;
-    r.idx = -1;
-    r.pad = 0;
-    return r;
-}
 
 // Block-wide fixed-order combine; the result is valid in thread 0.
 template <class Op>
-__device__ __forceinline__ Record block_combine(Record r, Record *smem)
+__device__ __forceinline__ typename Op::Partial block_combine(typename Op::Partial p)
 {
+    __shared__ typename Op::Partial smem[32];
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) r = Op::merge(r, shfl_xor_record(r, m));
+    for (int m = 16; m >= 1; m >>= 1) p = Op::merge(p, Op::shfl(p, m));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = (blockDim.x + 31) >> 5;
     __syncthreads();                       // smem may still be in use by a previous combine
-    if (lane == 0) smem[warp] = r;
+    if (lane == 0) smem[warp] = p;
     __syncthreads();
     if (warp == 0) {
-        r = lane < nwarps ? smem[lane] : empty_record();
+        p = lane < nwarps ? smem[lane] : Op::empty();
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) r = Op::merge(r, shfl_xor_record(r, m));
+        for (int m = 16; m >= 1; m >>= 1) p = Op::merge(p, Op::shfl(p, m));
     }
-    return r;
+    return p;
 }
 
 // What the last block does with the folded record.
@@ -618,16 +652,6 @@ __host__ __device__ __forceinline__ double nrm2_finish(double abig, double amed,
     return scl * sqrt(sumsq);
 }
 
-// Applies the rules that depend on logical element 0 to this rank's record (before any exchange).
-// x0_bits / x0_nan describe element 0, read at kernel start (a PDL secondary may overwrite x later).
-__device__ __forceinline__ void localize_record(Record &r, const FinishArgs &fa, u64 x0_bits, bool x0_nan)
-{
-    if (fa.x0 != nullptr) {
-        if (fa.kind == 2 && x0_nan) { r.key = kNanKey; r.idx = 0; }      // NaN at index 0 stays
-        if (fa.kind == 1) r.key = x0_bits;                                // nrm2 n==1 -> |x[0]|
-    }
-}
-
 __device__ __forceinline__ void store_result(const FinishArgs &fa, double v)
 {
     if (fa.is_f64) *reinterpret_cast<double *>(fa.out) = v;
@@ -651,60 +675,60 @@ __device__ __forceinline__ void finish_record(const Record &r, const FinishArgs 
 }
 
 // Cross-GPU fold: every rank holds all ranks' records (rank order) and folds them identically.
-template <class Op>
-__host__ __device__ __forceinline__ Record fold_ranks(const Record *recs, int nranks)
-{
-    Record acc = recs[0];
-    for (int r = 1; r < nranks; ++r) acc = Op::merge(acc, recs[r]);
-    return acc;
-}
+// iamax: larger key, then lower index, idx < 0 = no candidate; everything else: the sums add, and the
+// key (nrm2: bits of |x[0]|) is rank 0's.
 __host__ __device__ __forceinline__ Record fold_by_kind(const Record *recs, int nranks, int kind)
 {
-    Record acc;
-    if (kind == 2) acc = fold_ranks<IamaxOp<float>>(recs, nranks);          // the merges do not depend on T
-    else if (kind == 1) { acc = fold_ranks<Nrm2Op<float>>(recs, nranks); acc.key = recs[0].key; }   // |x[0]| travels in rank 0's key
-    else acc = fold_ranks<DotOp<float>>(recs, nranks);
+    Record acc = recs[0];
+    for (int r = 1; r < nranks; ++r) {
+        const Record &b = recs[r];
+        if (kind == 2) {
+            if (b.idx >= 0 && (acc.idx < 0 || b.key > acc.key || (b.key == acc.key && b.idx < acc.idx))) acc = b;
+        } else {
+            acc.f[0] += b.f[0]; acc.f[1] += b.f[1]; acc.f[2] += b.f[2];
+        }
+    }
     return acc;
 }
 
+// Second pass and finish.  `p` is this thread's partial; x0_bits (block 0, thread 0 only) the bit pattern
+// of |logical element 0|, read before this block released its PDL dependents.
 template <class Op>
-__device__ __forceinline__ void grid_finish(Record r, Record *partials, unsigned *ticket,
-                                            const FinishArgs &fa, Record *smem, u64 x0_bits, bool x0_nan)
+__device__ __forceinline__ void grid_finish(typename Op::Partial p, Record *partials, unsigned *ticket,
+                                            const FinishArgs &fa, u64 x0_bits)
 {
     __shared__ bool is_last;
-    r = block_combine<Op>(r, smem);
+    p = block_combine<Op>(p);
     pdl_wait();          // the scratch below may still be in use by the preceding reduction's tail
     if (threadIdx.x == 0) {
-        partials[blockIdx.x] = r;
-        __threadfence();
-        const unsigned t = atomicInc(ticket, gridDim.x - 1);   // wraps to 0: ready for the next launch
-        is_last = (t == gridDim.x - 1);
+        Op::store(&partials[blockIdx.x], p);
+        if (blockIdx.x == 0 && fa.kind == 1) __stcg(&partials[0].key, x0_bits);
+        // release this block's slot / acquire the others' with the ticket itself (no separate fence)
+        unsigned t;
+        asm volatile("atom.acq_rel.gpu.global.inc.u32 %0, [%1], %2;" : "=r"(t) : "l"(ticket), "r"(gridDim.x - 1) : "memory");
+        is_last = (t == gridDim.x - 1);                        // the ticket wraps to 0: ready for the next launch
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    Record acc = empty_record();
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-        // other blocks' records: read through L2 (L1 is not coherent across SMs)
-        union { int4 q[3]; Record r; } u;
-        const int4 *src = reinterpret_cast<const int4 *>(&partials[b]);
-        u.q[0] = __ldcg(src); u.q[1] = __ldcg(src + 1); u.q[2] = __ldcg(src + 2);
-        acc = Op::merge(acc, u.r);
-    }
-    acc = block_combine<Op>(acc, smem);
-    if (fa.mode != 2) {
-        if (threadIdx.x == 0) {
-            localize_record(acc, fa, x0_bits, x0_nan);
-            if (fa.mode == 0) finish_record(acc, fa);
-            else *fa.rec_out = acc;
-        }
-        return;
-    }
-    // ---- fused exchange over peer memory ----
+    typename Op::Partial acc = Op::empty();
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+        acc = Op::merge(acc, Op::load(&partials[b]));          // other blocks' slots: read through L2
+    acc = block_combine<Op>(acc);
     __shared__ Record mine;
+    if (threadIdx.x == 0) {
+        Record r = empty_record();
+        Op::to_record(r, acc);
+        if (fa.kind == 1 && fa.x0 != nullptr) r.key = __ldcg(&partials[0].key);     // nrm2 n==1 -> |x[0]|
+        if (fa.mode == 0) finish_record(r, fa);
+        else if (fa.mode == 1) *fa.rec_out = r;
+        else mine = r;
+    }
+    if (fa.mode != 2) return;
+    // ---- fused exchange over peer memory ----
     __shared__ Record all[kMaxRanks];
     __shared__ int timed_out;
-    if (threadIdx.x == 0) { localize_record(acc, fa, x0_bits, x0_nan); mine = acc; timed_out = 0; }
+    if (threadIdx.x == 0) timed_out = 0;
     __syncthreads();
     const unsigned par = fa.seq & 1u;
     const unsigned *words = reinterpret_cast<const unsigned *>(&mine);
@@ -745,31 +769,34 @@ __device__ __forceinline__ void pack_step(typename Op::Acc &acc, const Pack<type
     }
 }
 
-template <class T> __device__ __forceinline__ void read_x0(const FinishArgs &fa, u64 &bits, bool &is_nan)
+// Rules that depend on logical element 0, applied by the one thread that owns it (block 0, thread 0) while
+// the block's loads are still ahead of its launch_dependents -- a PDL secondary may overwrite x later.
+template <class Op>
+__device__ __forceinline__ u64 apply_x0(typename Op::Partial &p, const FinishArgs &fa)
 {
-    bits = 0; is_nan = false;
-    if (fa.x0 != nullptr) {
+    using T = typename Op::Scalar;
+    u64 bits = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && fa.x0 != nullptr) {
         const T v = *reinterpret_cast<const T *>(fa.x0);
-        bits = abs_bits(v); is_nan = (v != v);
+        bits = abs_bits(v);
+        if constexpr (Op::IS_IAMAX) { if (v != v) p = Op::nan_at_zero(); }    // NaN at index 0 stays
     }
+    return bits;
 }
 
 // reduce, unit stride.  idx_base = global logical index of element 0 of this shard (iamax).
 template <class Op, int VEC, int UNROLL, int POLICY, bool REV = false>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(kMaxThreads, reduce_min_blocks(VEC * UNROLL * (int)sizeof(typename Op::Scalar)))
 reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i64 head, i64 n, i64 idx_base,
                    Record *partials, unsigned *ticket, FinishArgs fa)
 {
     using T = typename Op::Scalar;
     constexpr int YS = REV ? -1 : 1;     // REV: element i pairs x[i] with y[n-1-i] (see map_unit_kernel)
-    __shared__ Record smem[32];
     const i64 body = n - head;
     const i64 npack = body / VEC;
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
     const T *bx = x + head, *by = REV ? y + (n - head) - VEC : y + head;
-    u64 x0_bits; bool x0_nan;
-    read_x0<T>(fa, x0_bits, x0_nan);     // read now: a PDL secondary may overwrite x later
 
     typename Op::Acc acc = Op::zero();
     unsigned it = 0;
@@ -798,32 +825,28 @@ reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i
             }
         }
     }
-    Record r = empty_record();
+    typename Op::Partial p = Op::empty();
     if (blockIdx.x == 0) {      // scalar head and tail
         const i64 tail0 = head + npack * VEC;
         const i64 nscalar = head + (n - tail0);
         for (i64 t = threadIdx.x; t < nscalar; t += blockDim.x) {
             const i64 e = t < head ? t : tail0 + (t - head);
-            Op::single(r, x[e], Op::TWO ? y[REV ? n - 1 - e : e] : T(0), idx_base + e);
+            Op::single(p, x[e], Op::TWO ? y[REV ? n - 1 - e : e] : T(0), idx_base + e);
         }
     }
+    const u64 x0_bits = apply_x0<Op>(p, fa);
     pdl_launch_dependents();    // every load of this block has been issued and consumed
     if constexpr (Op::IS_IAMAX) {
         if (acc.val >= T(0)) {    // saw >= 1 non-NaN element; ordinal -> global index
             const unsigned per = UNROLL * VEC;
             const unsigned iter = acc.ord / per, rem = acc.ord % per, u = rem / VEC, l = rem % VEC;
             const i64 tile = (i64)blockIdx.x + (i64)iter * gridDim.x;
-            Record v = empty_record();
-            v.key = abs_bits(acc.val);
-            v.idx = idx_base + head + ((tile * UNROLL + u) * blockDim.x + threadIdx.x) * VEC + l;
-            r = Op::merge(v, r);
+            p = Op::merge(Op::candidate(acc.val, idx_base + head + ((tile * UNROLL + u) * blockDim.x + threadIdx.x) * VEC + l), p);
         }
     } else {
-        Record v = empty_record();
-        Op::to_record(v, acc);
-        r = Op::merge(v, r);
+        Op::add_acc(p, acc);
     }
-    grid_finish<Op>(r, partials, ticket, fa, smem, x0_bits, x0_nan);
+    grid_finish<Op>(p, partials, ticket, fa, x0_bits);
 }
 
 // reduce, any increments: logical element i at x[kx0 + i*incx] (, y[ky0 + i*incy]).
@@ -833,17 +856,15 @@ reduce_strided_kernel(const typename Op::Scalar *x, i64 incx, i64 kx0, const typ
                       i64 idx_base, Record *partials, unsigned *ticket, FinishArgs fa)
 {
     using T = typename Op::Scalar;
-    __shared__ Record smem[32];
-    u64 x0_bits; bool x0_nan;
-    read_x0<T>(fa, x0_bits, x0_nan);
-    Record r = empty_record();
+    typename Op::Partial p = Op::empty();
     // a plain grid-stride loop: the compiler unrolls it four times with the loads hoisted, which measured
     // faster than explicit tiling (ptxas interleaves predicated tile loads with their uses)
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        Op::single(r, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : T(0), idx_base + i);
+        Op::single(p, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : T(0), idx_base + i);
+    const u64 x0_bits = apply_x0<Op>(p, fa);
     pdl_launch_dependents();
-    grid_finish<Op>(r, partials, ticket, fa, smem, x0_bits, x0_nan);
+    grid_finish<Op>(p, partials, ticket, fa, x0_bits);
 }
 
 __global__ void finish_records_kernel(const Record *recs, int nranks, FinishArgs fa)

@@ -40,17 +40,17 @@ constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
 
 // launch shapes are per routine and shared by the Float and Double instances (they are in bytes per access)
-enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_COUNT };
-static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm"};
+enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_FILL, R_COUNT };
+static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm", "fill"};
 struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
 // Defaults from the n = 2^28 sweeps on B200 (profiles/r01_tune_*.csv; tools/tune.py), reductions tuned
 // with their tails overlapped (PDL).  blocks_per_sm 0 = one resident wave (occupancy x SMs); larger
 // values oversubscribe the SMs and let the hardware block scheduler balance the load.
 static const LaunchCfg kDefaultCfg[R_COUNT] = {
-    /* dot  */ {3, 512, 8},   /* sdsdot */ {3, 512, 8},   /* asum */ {10, 512, 0},
-    /* nrm2 */ {4, 256, 8},   /* iamax  */ {0, 512, 8},   /* axpy */ {4, 128, 64},
-    /* scal */ {4, 256, 32},  /* copy   */ {4, 256, 32},  /* swap */ {4, 128, 64},
-    /* rot  */ {4, 128, 64},  /* rotm   */ {4, 128, 64},
+    /* dot  */ {4, 256, 16},   /* sdsdot */ {3, 512, 8},    /* asum */ {4, 512, 8},
+    /* nrm2 */ {3, 256, 16},   /* iamax  */ {3, 256, 16},   /* axpy */ {4, 128, 256},
+    /* scal */ {10, 512, 256}, /* copy   */ {3, 512, 256},  /* swap */ {4, 128, 128},
+    /* rot  */ {4, 512, 128},  /* rotm   */ {4, 512, 128},  /* fill */ {4, 256, 256},
 };
 
 constexpr int kMaxGrid = 148 * 32 * 2;   // partial-record scratch (blocks)
@@ -540,19 +540,6 @@ extern "C" int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, double lo, double hi
     KERNEL_CHECK(c);
     return LBK_OK;
 }
-extern "C" int lbk_vec_fill(lbk_vec *v, double value)
-{
-    if (!v) return fail(nullptr, LBK_ERR_ARG, "lbk_vec_fill: null vector");
-    if (!v->len) return LBK_OK;
-    lbk_ctx *c = v->ctx;
-    CU(c, cudaSetDevice(c->device));
-    c->tail_open = false;
-    const int grid = stream_grid(c, v->len, 256);
-    if (v->dtype) lbk::fill_kernel<double><<<grid, 256, 0, c->stream>>>((double *)v->ptr, v->len, value);
-    else lbk::fill_kernel<float><<<grid, 256, 0, c->stream>>>((float *)v->ptr, v->len, (float)value);
-    KERNEL_CHECK(c);
-    return LBK_OK;
-}
 
 extern "C" int lbk_host_alloc(int64_t nbytes, void **host)
 {
@@ -717,7 +704,7 @@ static int variant_unroll(int variant)
     return 1;
 }
 
-static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int threads, i64 ntiles, int *grid)
+static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int threads, i64 ntiles, int *grid, i64 max_grid = kMaxGrid)
 {
     int bps = cfg.blocks_per_sm;
     if (bps <= 0) {
@@ -725,7 +712,7 @@ static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int th
         if (bps < 1) bps = 1;
     }
     i64 g = std::min<i64>(std::max<i64>(ntiles, 1), (i64)c->sms * bps);
-    *grid = (int)std::min<i64>(g, kMaxGrid);
+    *grid = (int)std::min<i64>(g, max_grid);
     return LBK_OK;
 }
 
@@ -782,7 +769,7 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
     const i64 npack = (n - head) / variant_vec<T>(variant);
     const i64 per_tile = (i64)variant_unroll(variant) * threads;
     int grid;
-    int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid);
+    int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid, 0x7fffffff);   // maps keep no per-block scratch
     if (s) return s;
     F fc = f;
     void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n};
@@ -790,6 +777,16 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
     const i64 nb = n * (i64)sizeof(T);
     const i64 lens[4] = {nb, nb, nb, nb};
     return launch_stream_kernel(c, k, grid, threads, args, ops, lens, 4);
+}
+
+extern "C" int lbk_vec_fill(lbk_vec *v, double value)
+{
+    if (!v) return fail(nullptr, LBK_ERR_ARG, "lbk_vec_fill: null vector");
+    if (!v->len) return LBK_OK;
+    lbk_ctx *c = v->ctx;
+    CU(c, cudaSetDevice(c->device));
+    if (v->dtype) return launch_map_unit(c, R_FILL, lbk::FillF<double>{value}, (const double *)nullptr, (const double *)nullptr, (double *)v->ptr, (double *)nullptr, v->len);
+    return launch_map_unit(c, R_FILL, lbk::FillF<float>{(float)value}, (const float *)nullptr, (const float *)nullptr, (float *)v->ptr, (float *)nullptr, v->len);
 }
 
 template <class F>

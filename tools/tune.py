@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lambda_blas_b200 as lb  # noqa: E402
 from lambda_blas_b200 import inplace as ip  # noqa: E402
 
-BYTES = {"sdot": 8, "sasum": 4, "snrm2": 4, "isamax": 4, "saxpy": 12, "sscal": 8, "scopy": 8, "sswap": 16, "srot": 16, "srotm": 16}
+BYTES = {"sdot": 8, "sasum": 4, "snrm2": 4, "isamax": 4, "saxpy": 12, "sscal": 8, "scopy": 8, "sswap": 16, "srot": 16, "srotm": 16, "fill": 4}
 
 
 def main():
@@ -23,11 +23,15 @@ def main():
     ap.add_argument("--threads", default="128,256,512")
     ap.add_argument("--bps", default="0,-2,-4")   # 0: one resident wave; -k: k resident waves (grid = k * occupancy * SMs)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="Float or Double instance (same bytes: n is halved for f64)")
     a = ap.parse_args()
     ctx = lb.Context(0)
-    n = a.n
-    x, y = ctx.alloc(n).fill_hash(1), ctx.alloc(n).fill_hash(2)
-    out = ctx.alloc(4)
+    import numpy as np
+    dt = np.float64 if a.dtype == "f64" else np.float32
+    esz = 8 if a.dtype == "f64" else 4
+    n = a.n // (esz // 4)
+    x, y = ctx.alloc(n, dt).fill_hash(1), ctx.alloc(n, dt).fill_hash(2)
+    out = ctx.alloc(4, dt)
     flags = lb.srotmg(1.5, 0.75, 2.0, 0.5)
     c, s = math.cos(0.3), math.sin(0.3)
     calls = {
@@ -41,6 +45,7 @@ def main():
         "sswap": lambda: ip.sswap_(n, x, 1, y, 1),
         "srot": lambda: ip.srot_(n, x, 1, y, 1, c, s),
         "srotm": lambda: ip.srotm_(flags, n, x, 1, y, 1),
+        "fill": lambda: y.fill(0.5),
     }
     print("routine,variant,threads,bps,ms,GBps")
     e0, e1 = ctx.event(), ctx.event()
@@ -59,7 +64,7 @@ def main():
                 calls[r]()
             e1.record()
             ms = e0.elapsed_ms(e1) / a.iters
-            gbs = BYTES[r] * n / ms / 1e6
+            gbs = BYTES[r] * (esz // 4) * n / ms / 1e6
             print(f"{r},{v},{t},{bps},{ms:.4f},{gbs:.1f}", flush=True)
             if gbs > best[0]:
                 best = (gbs, (v, t, bps))
