@@ -22,7 +22,12 @@
  *     equal, bit for bit, oracle/netlib_l1.c (a restatement of the published
  *     netlib BLAS 3.7.0 routines the reference's tests bind in
  *     test/Foreign.hs:32-81) over the input domains of test/Main.hs;
- *   - scipy's OpenBLAS for the order-independent routines.
+ *   - a real compiled BLAS behind the same Fortran interface the reference's
+ *     tests bind: scipy's OpenBLAS (tests/test_oracle_openblas.py, run here and
+ *     on the GPU box) -- bit for bit for copy/swap/scal/iamax, within one
+ *     rounding per term for axpy/rot/rotm, within the reduction bound for
+ *     dot/sdsdot/asum/nrm2 (OpenBLAS vectorises sums and contracts FMAs, so it is
+ *     not netlib; it is an independent implementation, not a restatement).
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile); no
  * -march=native, so no FMA contraction and no vectorised reassociation: every
