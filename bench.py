@@ -302,6 +302,37 @@ def run_ours(args) -> None:
                        "pct_of_8TBs_per_gpu": round(100 * gbs / world / NOMINAL_HBM_GBS, 1),
                        "frac_of_measured_peak": round(gbs / world / peak, 3)}
 
+    # ---- the Double instances (ddot, daxpy, ...: SURVEY.md 8f.3) on the same bytes: n/2 doubles per GPU ----
+    routines_f64 = {}
+    if not args.no_f64:
+        nd, ngd = n // 2, (n // 2) * world
+        xd, yd = ctx.alloc_sharded(ngd, np.float64).fill_hash(1), ctx.alloc_sharded(ngd, np.float64).fill_hash(2)
+        resd = ctx.alloc(8, np.float64)
+        dcalls = {
+            "ddot": lambda: ip.ddot_async(ngd, xd, 1, yd, 1, resd), "daxpy": lambda: ip.daxpy_(ngd, SAXPY_A, xd, 1, yd, 1),
+            "dnrm2": lambda: ip.dnrm2_async(ngd, xd, 1, resd), "dasum": lambda: ip.dasum_async(ngd, xd, 1, resd),
+            "idamax": lambda: ip.idamax_async(ngd, xd, 1, resd), "dscal": lambda: ip.dscal_(ngd, SAXPY_A, xd, 1),
+            "dcopy": lambda: ip.dcopy_(ngd, xd, 1, yd, 1), "dswap": lambda: ip.dswap_(ngd, xd, 1, yd, 1),
+            "drot": lambda: ip.drot_(ngd, xd, 1, yd, 1, cs, sn), "drotm": lambda: ip.drotm_(flags, ngd, xd, 1, yd, 1),
+        }
+        dtimes = []
+        for r, f in dcalls.items():
+            xd.fill_hash(1); yd.fill_hash(2)
+            for _ in range(3):
+                f()
+            barrier()
+            a = ctx.event().record()
+            for _ in range(K):
+                f()
+            b = ctx.event().record()
+            barrier()
+            dtimes.append(a.elapsed_ms(b) / K)
+        dtimes = max_over_ranks(dtimes)
+        for (r, _), ms in zip(dcalls.items(), dtimes):
+            gbs = 2 * BYTES_PER_ELEM["s" + r[1:] if r != "idamax" else "isamax"] * ngd / ms / 1e6
+            routines_f64[r] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "pct_of_8TBs_per_gpu": round(100 * gbs / world / NOMINAL_HBM_GBS, 1)}
+        del xd, yd, resd
+
     # ---- end to end: host buffers in, host results out, copies inside the timed region ----
     # The caller's x, y live in pinned HOST memory.  Per step: upload x and y in chunks; each chunk's saxpy goes
     # out of place into y' (lbk_saxpy_oop, so y stays intact for the reductions) as soon as the chunk has landed;
@@ -378,7 +409,7 @@ def run_ours(args) -> None:
             "pct_of_8TBs_per_gpu": round(100 * value / world / NOMINAL_HBM_GBS, 1),
             "frac_of_measured_peak_per_gpu": round(value / world / peak, 3),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "pdl_launches": int(pdl_launches), "clocks": clocks, "routines": routines,
+            "pdl_launches": int(pdl_launches), "clocks": clocks, "routines": routines, "routines_f64": routines_f64,
             "step_routines_ms": {r: round(v, 4) for r, v in per_routine_in_step.items()},
             "last_snrm2": float(step_check[0]),
         }
@@ -407,6 +438,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks per vector in the end-to-end pipeline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-f64", action="store_true", help="skip the table of the Double instances")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
                     help="how sharded reductions end: in-kernel over NVLink peer memory, or ncclAllGather + finish kernel")
     args = ap.parse_args()

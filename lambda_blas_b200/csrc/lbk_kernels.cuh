@@ -75,6 +75,8 @@ template <> __device__ __forceinline__ double from_abs_bits<double>(u64 b) { ret
 // once), read-only operands through the non-coherent path.  POLICY 2..5 add L2 hints on 256-bit
 // accesses (2/3: evict-first loads, 3/5: evict-first stores, 4: 256-byte L2 prefetch + st.cs); they were
 // measured to make no difference (profiles/r01_tune_l2policy_writers.csv) and exist for tools/tune.py.
+// POLICY 6 = POLICY 1 plus, in the map kernel, a data dependency that holds a thread's stores back until
+// ALL of its loads have landed (see map_unit_kernel).
 // ------------------------------------------------------------------------------------------------
 template <class T, int VEC> struct alignas(VEC * sizeof(T)) Pack { T v[VEC]; };
 
@@ -257,12 +259,23 @@ template <class T> struct Rotm1F {      // Single.hs:481-482   h11*x + y ; -x + 
 // REV: the (incx, incy) = (1,-1) / (-1,1) pairing -- logical element i is x[i] and y[n-1-i] -- still moves
 // whole aligned packs: the y pack for x[e..e+VEC) is y[n-e-VEC..n-e) with its lanes in reverse order.
 // ------------------------------------------------------------------------------------------------
+// Load fence (POLICY 6).  A warp issues in order, so a store whose data has landed goes out while the
+// same warp's later loads are still in flight; for the routines with no arithmetic between load and
+// store (swap, copy) that interleaving costs up to 15% at some launch shapes, and holding every store
+// until the thread's last load has returned never loses (tools/swap_experiment.cu,
+// profiles/r01_swap_instruction_stream.log).  There is no "wait for my loads" instruction, so the fence
+// is a true dependency: one element of every loaded pack is OR-ed together, masked with a kernel
+// argument that is 0 at run time (the compiler cannot know), and added to every store address.
+__device__ __forceinline__ unsigned low_bits(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ unsigned low_bits(double v) { return (unsigned)__double2loint(v); }
+
 template <class F, int VEC, int UNROLL, int POLICY, bool REV = false>
 __global__ void __launch_bounds__(kMaxThreads)
 map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr, typename F::Scalar *xw,
-                typename F::Scalar *yw, i64 head, i64 n)
+                typename F::Scalar *yw, i64 head, i64 n, unsigned fence_mask)
 {
     using T = typename F::Scalar;
+    constexpr bool FENCE = POLICY == 6 && (F::RX || F::RY);
     const i64 body = n - head;
     const i64 npack = body / VEC;
     const i64 per_tile = (i64)UNROLL * blockDim.x;
@@ -284,6 +297,16 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
                 if constexpr (F::RX) load_pack<VEC, POLICY, !F::WX>(xv[u], bxr + e);
                 if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + YS * e);
             }
+            i64 held = 0;
+            if constexpr (FENCE) {
+                unsigned dep = 0;
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    if constexpr (F::RX) dep |= low_bits(xv[u].v[VEC - 1]);
+                    if constexpr (F::RY) dep |= low_bits(yv[u].v[VEC - 1]);
+                }
+                held = (i64)(dep & fence_mask);      // 0: fence_mask is 0
+            }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
@@ -291,7 +314,7 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
+                const i64 e = (p0 + (i64)u * blockDim.x) * VEC + held;
                 if constexpr (F::WX) store_pack<VEC, POLICY>(bxw + e, xv[u]);
                 if constexpr (F::WY) store_pack<VEC, POLICY>(byw + YS * e, yv[u]);
             }

@@ -33,9 +33,10 @@ static_assert(sizeof(lbk_record) == sizeof(Record), "host and device records sha
 #define LBK_VARIANTS(X) \
     X(0, 4, 4, 1) X(1, 4, 2, 1) X(2, 4, 8, 1) X(3, 8, 2, 1) X(4, 8, 4, 1) X(5, 4, 4, 0) \
     X(6, 8, 1, 1) X(7, 4, 1, 1) X(8, 1, 4, 1) X(9, 8, 2, 0) X(10, 8, 8, 1) \
-    X(11, 8, 4, 2) X(12, 8, 4, 3) X(13, 8, 4, 4) X(14, 8, 4, 5)
-static const int kVariantVec[16] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8, 8, 8, 8, 8, 4};
-constexpr int kNumVariants = 15;
+    X(11, 8, 4, 2) X(12, 8, 4, 3) X(13, 8, 4, 4) X(14, 8, 4, 5) \
+    X(15, 8, 4, 6) X(16, 8, 2, 6) X(17, 8, 1, 6) X(18, 8, 8, 6) X(19, 4, 4, 6) X(20, 4, 2, 6) X(21, 4, 8, 6) X(22, 4, 1, 6)
+constexpr int kNumVariants = 23;
+static const int kVariantVec[kNumVariants] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 4, 4, 4, 4};
 constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
 
@@ -45,12 +46,15 @@ static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "i
 struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
 // Defaults from the n = 2^28 sweeps on B200 (profiles/r01_tune_*.csv; tools/tune.py), reductions tuned
 // with their tails overlapped (PDL).  blocks_per_sm 0 = one resident wave (occupancy x SMs); larger
-// values oversubscribe the SMs and let the hardware block scheduler balance the load.
+// values oversubscribe the SMs and let the hardware block scheduler balance the load; kOneTilePerBlock
+// makes the grid as large as the tile count, so blocks retire front to back through the vector -- the
+// shape every writer prefers (with the load fence of POLICY 6 and 32-64 bytes per thread per operand).
+constexpr int kOneTilePerBlock = 1 << 20;
 static const LaunchCfg kDefaultCfg[R_COUNT] = {
     /* dot  */ {4, 256, 16},   /* sdsdot */ {3, 512, 8},    /* asum */ {4, 512, 8},
-    /* nrm2 */ {3, 256, 16},   /* iamax  */ {3, 256, 16},   /* axpy */ {4, 128, 256},
-    /* scal */ {10, 512, 256}, /* copy   */ {3, 512, 256},  /* swap */ {4, 128, 128},
-    /* rot  */ {4, 512, 128},  /* rotm   */ {4, 512, 128},  /* fill */ {4, 256, 256},
+    /* nrm2 */ {3, 256, 16},   /* iamax  */ {3, 256, 16},   /* axpy */ {16, 512, kOneTilePerBlock},
+    /* scal */ {20, 512, kOneTilePerBlock},  /* copy */ {20, 512, kOneTilePerBlock},  /* swap */ {19, 256, kOneTilePerBlock},
+    /* rot  */ {22, 256, kOneTilePerBlock},  /* rotm */ {22, 256, kOneTilePerBlock},  /* fill */ {4, 256, 256},
 };
 
 constexpr int kMaxGrid = 148 * 32 * 2;   // partial-record scratch (blocks)
@@ -638,7 +642,7 @@ template <class T> static inline int misalign(const T *p, int vec) { return (int
 // elements per access of a variant for element type T: the table is in floats (4/16/32 bytes)
 template <class T> static inline int variant_vec(int variant)
 {
-    const int f = kVariantVec[variant];
+    const int f = kVariantVec[(variant >= 0 && variant < kNumVariants) ? variant : 0];
     return sizeof(T) == 4 ? f : (f > 1 ? f / 2 : 1);
 }
 
@@ -772,7 +776,8 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
     int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid, 0x7fffffff);   // maps keep no per-block scratch
     if (s) return s;
     F fc = f;
-    void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n};
+    unsigned fence_mask = 0;     // see map_unit_kernel: always 0, but only known at run time
+    void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n, (void *)&fence_mask};
     const void *ops[4] = {xr, yr, xw, yw};
     const i64 nb = n * (i64)sizeof(T);
     const i64 lens[4] = {nb, nb, nb, nb};
@@ -917,7 +922,7 @@ static const void *reduce_kernel_ptr(int variant)
 {
     using T = typename Op::Scalar;
     switch (variant) {
-#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::reduce_unit_kernel<Op, vec_t<T>(VEC), UNROLL, POLICY>;
+#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::reduce_unit_kernel<Op, vec_t<T>(VEC), UNROLL, (POLICY == 6 ? 1 : POLICY)>;   // 6: a map-only policy
         LBK_VARIANTS(X)
 #undef X
     }

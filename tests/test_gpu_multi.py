@@ -30,10 +30,14 @@ def _worker(rank, world, port, q):
     ctx = sharded.attach_torch_distributed(lb.Context(rank))
     ok, notes = True, []
     fused_available = ctx.fused_exchange()
-    for n, fused in [(n, f) for f in ((True, False) if fused_available else (False,)) for n in [1, 2, 5, 1000, (1 << 20) + 3, 1 << 24]]:
+    cases = [(n, f, dt) for dt in (np.float32, np.float64) for f in ((True, False) if fused_available else (False,))
+             for n in ([1, 2, 5, 1000, (1 << 20) + 3, 1 << 24] if dt == np.float32 else [1, 5, 1000, (1 << 20) + 3])]
+    for n, fused, dt in cases:
         ctx.set_fused_exchange(fused)
-        x, y = ctx.alloc_sharded(n).fill_hash(1), ctx.alloc_sharded(n).fill_hash(2)
-        hx, hy = lb.hash_fill_reference(n, 1), lb.hash_fill_reference(n, 2)
+        u = float(np.finfo(dt).eps) / 2          # unit round-off of the instance (Float: 2^-24, Double: 2^-53)
+        bits = np.uint32 if dt == np.float32 else np.uint64
+        x, y = ctx.alloc_sharded(n, dt).fill_hash(1), ctx.alloc_sharded(n, dt).fill_hash(2)
+        hx, hy = lb.hash_fill_reference(n, 1, dtype=dt), lb.hash_fill_reference(n, 2, dtype=dt)
         lo, hi = sharded.shard_range(n, world, rank)
         assert len(x) == hi - lo and x.shard_offset == lo
         # plant a tie across the shard boundary and a maximum at the last element of shard 0
@@ -42,23 +46,23 @@ def _worker(rank, world, port, q):
             for pos, val in ((edge - 1, 7.0), (edge, -7.0), (n - 1, 7.0)):
                 hx[pos] = val
                 if lo <= pos < hi:
-                    x.view(pos - lo, 1).upload(np.array([val], dtype=np.float32)) if world == 1 else None
+                    x.view(pos - lo, 1).upload(np.array([val], dtype=dt)) if world == 1 else None
             # views of sharded vectors are refused by design: rewrite the shard through a wrapped handle
-            shard = ctx.wrap(x.ptr, len(x), keepalive=x)
+            shard = ctx.wrap(x.ptr, len(x), keepalive=x, dtype=dt)
             shard.upload(hx[lo:hi])
         prod = float(np.sum(np.abs(hx.astype(np.float64) * hy)))
         d = lb.sdot(n, x, 1, y, 1)
-        ok &= abs(float(d) - float(oracle.sdot(n, hx, 1, hy, 1))) <= 2 * n * 2.0 ** -24 * prod
+        ok &= abs(float(d) - float(oracle.sdot(n, hx, 1, hy, 1))) <= 2 * n * u * prod
         nr = lb.snrm2(n, x, 1)
-        ok &= abs(float(nr) - float(oracle.snrm2(n, hx, 1))) <= 2 * n * 2.0 ** -24 * float(oracle.snrm2(n, hx, 1))
+        ok &= abs(float(nr) - float(oracle.snrm2(n, hx, 1))) <= 2 * n * u * float(oracle.snrm2(n, hx, 1))
         sa = lb.sasum(n, x, 1)
-        ok &= abs(float(sa) - float(oracle.sasum(n, hx, 1))) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(hx)))
+        ok &= abs(float(sa) - float(oracle.sasum(n, hx, 1))) <= 2 * n * u * float(np.sum(np.abs(hx)))
         im = lb.isamax(n, x, 1)
         ok &= im == oracle.isamax(n, hx, 1)
         if n >= 5:          # n smaller than the vector: only the leading ranks take part
             m = n - 2
             ok &= lb.isamax(m, x, 1) == oracle.isamax(m, hx, 1)
-            ok &= abs(float(lb.sdot(m, x, 1, y, 1)) - float(oracle.sdot(m, hx, 1, hy, 1))) <= 2 * n * 2.0 ** -24 * prod
+            ok &= abs(float(lb.sdot(m, x, 1, y, 1)) - float(oracle.sdot(m, hx, 1, hy, 1))) <= 2 * n * u * prod
         # every rank holds the same bits
         t = torch.tensor([float(d), float(nr), float(sa), float(im)], dtype=torch.float64, device="cuda")
         lo_t, hi_t = t.clone(), t.clone()
@@ -67,14 +71,14 @@ def _worker(rank, world, port, q):
         # elementwise: no communication, shard by shard
         ip.saxpy_(n, 1.000123, x, 1, y, 1)
         want = oracle.saxpy(n, 1.000123, hx, 1, hy, 1)[lo:hi]
-        ok &= np.array_equal(y.to_host().view(np.uint32), want.view(np.uint32))
+        ok &= np.array_equal(y.to_host().view(bits), want.view(bits))
         # non-unit increments on shards are refused, not silently wrong
         try:
             lb.sdot(max(n // 2, 1), x, 2, y, 2)
             ok &= (world == 1)
         except lb.LbkError as e:
             ok &= e.status == 6
-        notes.append((n, fused, bool(ok)))
+        notes.append((n, fused, np.dtype(dt).name, bool(ok)))
     notes.append(("fused_available", fused_available))
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)

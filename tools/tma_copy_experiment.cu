@@ -56,6 +56,48 @@ __global__ void __launch_bounds__(32) bulk_copy_kernel(const char *src, char *ds
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// Non-persistent form: one CTA moves NT consecutive tiles (a contiguous NT*TILE chunk) and exits; the
+// hardware block scheduler walks the vector front to back (the shape that won for the LDG/STG maps).
+template <int NT, int TILE>
+__global__ void __launch_bounds__(32) bulk_copy_once_kernel(const char *src, char *dst)
+{
+    extern __shared__ __align__(128) char smem[];
+    __shared__ uint64_t full[NT];
+    if (threadIdx.x != 0) return;
+    for (int s = 0; s < NT; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const size_t base = (size_t)blockIdx.x * NT * TILE;
+    for (int s = 0; s < NT; ++s) {
+        mbar_expect(&full[s], TILE);
+        bulk_load(smem + (size_t)s * TILE, src + base + (size_t)s * TILE, TILE, &full[s]);
+    }
+    for (int s = 0; s < NT; ++s) {
+        mbar_wait(&full[s], 0);
+        bulk_store(dst + base + (size_t)s * TILE, smem + (size_t)s * TILE, TILE);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int NT, int TILE>
+int run_once(const char *x, char *y, size_t bytes)
+{
+    const size_t smem = (size_t)NT * TILE;
+    CK(cudaFuncSetAttribute(bulk_copy_once_kernel<NT, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)(bytes / ((size_t)NT * TILE));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < 3; ++i) bulk_copy_once_kernel<NT, TILE><<<grid, 32, smem>>>(x, y);
+    CK(cudaGetLastError());
+    cudaEventRecord(a);
+    for (int i = 0; i < 10; ++i) bulk_copy_once_kernel<NT, TILE><<<grid, 32, smem>>>(x, y);
+    cudaEventRecord(b);
+    CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    printf("one-shot CTAs: %d tiles x %6d B per CTA, grid %d : %.1f us  %.1f GB/s (read+write)\n", NT, TILE, grid, ms * 100, 2.0 * bytes / (ms / 10) / 1e6);
+    return 0;
+}
+
 template <int STAGES, int TILE>
 int run(const char *x, char *y, size_t bytes, int sms, int ctas_per_sm)
 {
@@ -94,6 +136,11 @@ int main()
     run<6, 32768>(x, y, bytes, sms, 1); run<4, 16384>(x, y, bytes, sms, 2); run<6, 16384>(x, y, bytes, sms, 2);
     run<8, 8192>(x, y, bytes, sms, 2); run<4, 8192>(x, y, bytes, sms, 4); run<3, 65536>(x, y, bytes, sms, 1);
     run<2, 32768>(x, y, bytes, sms, 3); run<13, 16384>(x, y, bytes, sms, 1);
+    run_once<1, 8192>(x, y, bytes); run_once<1, 16384>(x, y, bytes); run_once<1, 32768>(x, y, bytes); run_once<1, 65536>(x, y, bytes);
+    run_once<2, 8192>(x, y, bytes); run_once<2, 16384>(x, y, bytes); run_once<4, 8192>(x, y, bytes); run_once<4, 16384>(x, y, bytes);
+    run_once<2, 32768>(x, y, bytes); run_once<4, 4096>(x, y, bytes); run_once<8, 4096>(x, y, bytes); run_once<1, 4096>(x, y, bytes);
+    CK(cudaMemset(y, 0, bytes));
+    run_once<2, 16384>(x, y, bytes);
     unsigned char h[4];
     CK(cudaMemcpy(h, y + bytes - 4, 4, cudaMemcpyDeviceToHost));
     printf("check: %d %d\n", h[0], h[3]);
