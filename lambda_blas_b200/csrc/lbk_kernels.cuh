@@ -361,14 +361,15 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
 // ------------------------------------------------------------------------------------------------
 constexpr int kStridedUnroll = 4;   // independent scalar accesses in flight per operand per thread
 
-template <class F>
+template <class F, bool FENCED>
 __global__ void __launch_bounds__(256)
 map_strided_kernel(F f, const typename F::Scalar *xr, typename F::Scalar *xw, i64 incx_r, i64 incx_w, i64 kx0_r, i64 kx0_w,
                    const typename F::Scalar *yr, typename F::Scalar *yw, i64 incy_r, i64 incy_w, i64 ky0_r, i64 ky0_w,
-                   i64 i_begin, i64 n, int x_last_only, int y_last_only)
+                   i64 i_begin, i64 n, int x_last_only, int y_last_only, unsigned fence_mask)
 {
     using T = typename F::Scalar;
     constexpr int U = kStridedUnroll;
+    constexpr bool FENCE = FENCED && (F::RX || F::RY);      // the load fence of map_unit_kernel: stores wait for all loads
     const i64 per_tile = (i64)U * blockDim.x;
     const i64 count = n - i_begin;
     const i64 ntiles = (count + per_tile - 1) / per_tile;
@@ -385,13 +386,20 @@ map_strided_kernel(F f, const typename F::Scalar *xr, typename F::Scalar *xw, i6
                 if constexpr (F::RY) { load_pack<1, 0, !F::WY>(p, yr + ky0_r + i * incy_r); ys[u] = p.v[0]; }
             }
         }
+        i64 held = 0;
+        if constexpr (FENCE) {
+            unsigned dep = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) dep |= low_bits(xs[u]) | low_bits(ys[u]);
+            held = (i64)(dep & fence_mask);      // 0: fence_mask is 0 at run time
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const i64 i = i0 + (i64)u * blockDim.x;
             if (i < n) {
                 f(xs[u], ys[u]);
-                if constexpr (F::WX) { if (!x_last_only || i == n - 1) xw[kx0_w + i * incx_w] = xs[u]; }
-                if constexpr (F::WY) { if (!y_last_only || i == n - 1) yw[ky0_w + i * incy_w] = ys[u]; }
+                if constexpr (F::WX) { if (!x_last_only || i == n - 1) xw[kx0_w + i * incx_w + held] = xs[u]; }
+                if constexpr (F::WY) { if (!y_last_only || i == n - 1) yw[ky0_w + i * incy_w + held] = ys[u]; }
             }
         }
     }

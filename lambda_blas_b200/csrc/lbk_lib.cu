@@ -41,8 +41,8 @@ constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
 
 // launch shapes are per routine and shared by the Float and Double instances (they are in bytes per access)
-enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_FILL, R_COUNT };
-static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm", "fill"};
+enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_FILL, R_MAPSTRIDED, R_COUNT };
+static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm", "fill", "mapstrided"};
 struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
 // Defaults from the n = 2^28 sweeps on B200 (profiles/r01_tune_*.csv; tools/tune.py), reductions tuned
 // with their tails overlapped (PDL).  blocks_per_sm 0 = one resident wave (occupancy x SMs); larger
@@ -55,6 +55,8 @@ static const LaunchCfg kDefaultCfg[R_COUNT] = {
     /* nrm2 */ {3, 256, 16},   /* iamax  */ {3, 256, 16},   /* axpy */ {16, 512, kOneTilePerBlock},
     /* scal */ {20, 512, kOneTilePerBlock},  /* copy */ {20, 512, kOneTilePerBlock},  /* swap */ {19, 256, kOneTilePerBlock},
     /* rot  */ {22, 256, kOneTilePerBlock},  /* rotm */ {22, 256, kOneTilePerBlock},  /* fill */ {4, 256, 256},
+    /* the general-stride map kernel: variant 0/1 = without/with the load fence (no measurable effect
+       there); threads / blocks_per_sm 0 = chosen from the increments in launch_map_strided */ {0, 0, 0},
 };
 
 constexpr int kMaxGrid = 148 * 32 * 2;   // partial-record scratch (blocks)
@@ -750,7 +752,8 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
     using T = typename F::Scalar;
     const LaunchCfg &cfg = c->cfg[rid];
     int variant = cfg.variant;
-    const int threads = cfg.threads > 0 ? cfg.threads : 256;
+    // the reversed pairing has one shape: 16-byte packs x 4, 128 threads, no fence (config-4 sweep, profiles/)
+    const int threads = rev ? 128 : (cfg.threads > 0 ? cfg.threads : 256);
     i64 head = 0;
     const void *k;
     if (rev) {
@@ -799,11 +802,23 @@ static int launch_map_strided(lbk_ctx *c, const F &f, const typename F::Scalar *
                               i64 kx0_r, i64 kx0_w, const typename F::Scalar *yr, typename F::Scalar *yw, i64 incy_r, i64 incy_w,
                               i64 ky0_r, i64 ky0_w, i64 i_begin, i64 n, int x_last, int y_last)
 {
-    const int threads = 256;
-    const int grid = stream_grid(c, (n - i_begin + lbk::kStridedUnroll - 1) / lbk::kStridedUnroll, threads);
+    // Launch shape (profiles/r01_strided_launch_sweep.md): with an increment of 4 or more every element
+    // sits in its own 32-byte sector and one small tile per block (blocks retire front to back) is best;
+    // with increments of 1-2 on either side, fewer, longer-lived blocks of 128 threads win by 5-20%.
+    const LaunchCfg &cfg = c->cfg[R_MAPSTRIDED];
+    const bool wide = std::max(std::max(iabs64(incx_r), iabs64(incx_w)), std::max(iabs64(incy_r), iabs64(incy_w))) >= 4;
+    const int threads = (cfg.threads > 0 && cfg.threads <= 256) ? cfg.threads : (wide ? 256 : 128);
+    const i64 per_tile = (i64)lbk::kStridedUnroll * threads;
+    const i64 ntiles = (n - i_begin + per_tile - 1) / per_tile;
+    const i64 cap = cfg.blocks_per_sm > 0 ? (i64)c->sms * cfg.blocks_per_sm : (wide ? ntiles : (i64)c->sms * 256);
+    const int grid = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(ntiles, cap), 0x7fffffff));
     c->tail_open = false;
-    lbk::map_strided_kernel<F><<<grid, threads, 0, c->stream>>>(f, xr, xw, incx_r, incx_w, kx0_r, kx0_w,
-                                                                 yr, yw, incy_r, incy_w, ky0_r, ky0_w, i_begin, n, x_last, y_last);
+    if (cfg.variant == 0)
+        lbk::map_strided_kernel<F, false><<<grid, threads, 0, c->stream>>>(f, xr, xw, incx_r, incx_w, kx0_r, kx0_w,
+                                                                            yr, yw, incy_r, incy_w, ky0_r, ky0_w, i_begin, n, x_last, y_last, 0u);
+    else
+        lbk::map_strided_kernel<F, true><<<grid, threads, 0, c->stream>>>(f, xr, xw, incx_r, incx_w, kx0_r, kx0_w,
+                                                                           yr, yw, incy_r, incy_w, ky0_r, ky0_w, i_begin, n, x_last, y_last, 0u);
     KERNEL_CHECK(c);
     return LBK_OK;
 }

@@ -9,8 +9,13 @@ import lambda_blas_b200 as lb  # noqa: E402
 from lambda_blas_b200 import inplace as ip  # noqa: E402
 
 n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 26)
+# optional: "routine:variant:threads:bps" launch overrides, e.g. mapstrided:0:256:16 saxpy:0:128:64
+overrides = [a.split(":") for a in sys.argv[2:]]
 incs = [1, 2, 7, -1]
 ctx = lb.Context(0)
+for name, v, t, b in overrides:
+    ctx.set_launch(name, int(v), int(t), int(b))
+print("# overrides:", overrides)
 span = 1 + (n - 1) * 7
 x, y, out = ctx.alloc(span).fill_hash(1), ctx.alloc(span).fill_hash(2), ctx.alloc(4)
 c, s = math.cos(0.3), math.sin(0.3)
