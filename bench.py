@@ -422,6 +422,95 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
+
+# ---------------------------------------------------------------------------------------------------
+# --criterion: the reference's own benchmark matrix (test/Bench.hs), re-stated
+# ---------------------------------------------------------------------------------------------------
+# test/Bench.hs:17-113 times every Level-1 routine on 32 767-element vectors of `genEveryday` floats for
+# n in {1..9, 10..90, 100..900, 1000..9000, 10000, 20000, 30000} x inc in {1, 10, 100} with (n-1)*inc < 32767
+# (`vectorbench`, Bench.hs:116-132), naming each case `level-1/<routine>/<impl>/<routine>(n,inc)`.  Here
+#   impl = pure   the oracle (C port of the reference's Haskell, one core) -- a PORT: no GHC in this image
+#   impl = b200   the reference's call surface over device-resident vectors (lambda_blas_b200.single): scalar
+#                 routines return the scalar to the host, vector routines return a NEW device vector (the
+#                 reference's pure result) and the call is timed to completion on the stream
+# plus BASELINE.json configs[0], `sdot(1000000,1)`: mean and standard deviation over >= 10 runs.  These sizes are
+# launch-latency territory for a GPU (a 30 000-element sdot moves 240 KB): the table documents where the CPU
+# wins; it is not the bandwidth benchmark.
+NMAX = 32767
+
+
+def criterion_sizes(quick):
+    ns = list(range(1, 10)) + list(range(10, 100, 10)) + list(range(100, 1000, 100)) + list(range(1000, 10000, 1000)) + [10000, 20000, 30000]
+    return [n for n in ns if not quick or n in (1, 10, 100, 1000, 10000, 30000)]
+
+
+def criterion_measure(f, min_time=2e-3, min_runs=5):
+    """criterion in spirit: run until min_time has elapsed (at least min_runs), report mean and stddev per call."""
+    f(); f()
+    ts = []
+    t_end = time.perf_counter() + min_time
+    while len(ts) < min_runs or time.perf_counter() < t_end:
+        t0 = time.perf_counter()
+        f()
+        ts.append(time.perf_counter() - t0)
+        if len(ts) >= 2000:
+            break
+    return statistics.mean(ts), (statistics.stdev(ts) if len(ts) > 1 else 0.0), len(ts)
+
+
+def run_criterion(args) -> None:
+    """--criterion: the reference's benchmark matrix (test/Bench.hs) for the CPU port and the B200 path, as CSV on stdout."""
+    import numpy as np
+    import lambda_blas_b200 as lb
+    from oracle import oracle
+    out = _OUT if _OUT is not None else sys.stdout
+    quick = args.quick
+    oracle.build()
+    rng = np.random.default_rng(20260101)
+    lo, hi = 2.0 ** -24, 2.0 ** 24 - 1                       # genEveryday, Gen.hs:208-214
+    hv = [rng.uniform(lo, hi, NMAX).astype(np.float32) for _ in range(2)]
+    ctx = lb.Context(0)
+    dv = [ctx.to_device(h) for h in hv]
+    a = np.float32(rng.uniform(lo, hi))
+    c, s = np.float32(math.cos(0.3)), np.float32(math.sin(0.3))
+    flags_o, flags_d = oracle.srotmg(1.5, 0.75, 2.0, 0.5), lb.srotmg(1.5, 0.75, 2.0, 0.5)
+    x, y, X, Y = hv[0], hv[1], dv[0], dv[1]
+
+    def done(r):            # a vector result is complete when the stream has run it
+        ctx.sync()
+        return r
+    routines = {
+        "sdot": (lambda n, i: oracle.sdot(n, x, i, y, i), lambda n, i: lb.sdot(n, X, i, Y, i)),
+        "sasum": (lambda n, i: oracle.sasum(n, x, i), lambda n, i: lb.sasum(n, X, i)),
+        "snrm2": (lambda n, i: oracle.snrm2(n, x, i), lambda n, i: lb.snrm2(n, X, i)),
+        "isamax": (lambda n, i: oracle.isamax(n, x, i), lambda n, i: lb.isamax(n, X, i)),
+        "sscal": (lambda n, i: oracle.sscal(n, a, x, i), lambda n, i: done(lb.sscal(n, a, X, i))),
+        "scopy": (lambda n, i: oracle.scopy(n, x, i, y, i), lambda n, i: done(lb.scopy(n, X, i, Y, i))),
+        "sswap": (lambda n, i: oracle.sswap(n, x, i, y, i), lambda n, i: done(lb.sswap(n, X, i, Y, i))),
+        "saxpy": (lambda n, i: oracle.saxpy(n, a, x, i, y, i), lambda n, i: done(lb.saxpy(n, a, X, i, Y, i))),
+        "srot": (lambda n, i: oracle.srot(n, x, i, y, i, c, s), lambda n, i: done(lb.srot(n, X, i, Y, i, c, s))),
+        "srotm": (lambda n, i: oracle.srotm(flags_o, n, x, i, y, i), lambda n, i: done(lb.srotm(flags_d, n, X, i, Y, i))),
+    }
+    out.write("name,n,inc,mean_us,stddev_us,runs\n")
+    for r, (cpu, gpu) in routines.items():
+        for inc in (1, 10, 100):
+            for n in criterion_sizes(quick):
+                if (n - 1) * inc >= NMAX:
+                    continue
+                for impl, f in (("pure", cpu), ("b200", gpu)):
+                    m, sd, k = criterion_measure(lambda: f(n, inc))
+                    out.write(f"\"level-1/{r}/{impl}/{r}({n},{inc})\",{n},{inc},{m * 1e6:.2f},{sd * 1e6:.2f},{k}" + "\n"); out.flush()
+    # BASELINE.json configs[0]: sdot n = 1e6, unit stride
+    n = 1_000_000
+    hx, hy = rng.uniform(lo, hi, n).astype(np.float32), rng.uniform(lo, hi, n).astype(np.float32)
+    dx, dy = ctx.to_device(hx), ctx.to_device(hy)
+    for impl, f in (("pure", lambda: oracle.sdot(n, hx, 1, hy, 1)), ("b200", lambda: lb.sdot(n, dx, 1, dy, 1))):
+        m, sd, k = criterion_measure(f, min_time=0.2, min_runs=10)
+        out.write(f"\"level-1/sdot/{impl}/sdot({n},1)\",{n},1,{m * 1e6:.2f},{sd * 1e6:.2f},{k}" + "\n"); out.flush()
+    ctx.close()
+
+
+
 def main():
     # Libraries (NCCL's version banner, torchrun notices) may print to stdout; the contract is ONE JSON
     # line there, so everything else goes to stderr and the line is written to the saved descriptor.
@@ -439,10 +528,15 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks per vector in the end-to-end pipeline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-f64", action="store_true", help="skip the table of the Double instances")
+    ap.add_argument("--criterion", action="store_true", help="print the reference's criterion matrix (test/Bench.hs) for the CPU port and the B200 path as CSV")
+    ap.add_argument("--quick", action="store_true", help="--criterion: six sizes per routine instead of the full list")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
                     help="how sharded reductions end: in-kernel over NVLink peer memory, or ncclAllGather + finish kernel")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.criterion:
+        run_criterion(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

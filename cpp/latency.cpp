@@ -1,0 +1,53 @@
+// Per-call latency of the C ABI from a compiled host (no interpreter in the way), at the sizes of the
+// reference's criterion suite (test/Bench.hs:113: n up to 30 000 on 32 767-element vectors) and at
+// BASELINE.json configs[0] (sdot, n = 1e6).  Prints CSV: routine,form,n,mean_us,min_us.
+//   g++ -O2 -std=c++17 cpp/latency.cpp -o build/lb_latency -Llambda_blas_b200 -llbk -Wl,-rpath,$PWD/lambda_blas_b200
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <functional>
+#include <vector>
+
+#include "lambda_blas.hpp"
+
+using namespace lambda_blas;
+using clk = std::chrono::steady_clock;
+
+static void time_it(const char *routine, const char *form, long long n, const std::function<void()> &f, int reps = 300)
+{
+    for (int i = 0; i < 20; ++i) f();
+    std::vector<double> us((size_t)reps);
+    for (int i = 0; i < reps; ++i) {
+        auto t0 = clk::now();
+        f();
+        us[(size_t)i] = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
+    }
+    double sum = 0;
+    for (double v : us) sum += v;
+    std::printf("%s,%s,%lld,%.2f,%.2f\n", routine, form, n, sum / reps, *std::min_element(us.begin(), us.end()));
+}
+
+int main()
+{
+    try {
+        Context ctx(0);
+        const long long N = 1000000;
+        std::vector<float> h((size_t)N);
+        for (long long i = 0; i < N; ++i) h[(size_t)i] = (float)((i * 2654435761u) % 1000) / 1000.f - 0.5f;
+        DVector x(ctx, h), y(ctx, h);
+        std::printf("routine,form,n,mean_us,min_us\n");
+        for (long long n : {1LL, 100LL, 10000LL, 30000LL, N}) {
+            time_it("sdot", "scalar to host (lbk_sdot)", n, [&] { (void)sdot(n, x, 1, y, 1); });
+            time_it("snrm2", "scalar to host (lbk_snrm2)", n, [&] { (void)snrm2(n, x, 1); });
+            time_it("isamax", "scalar to host (lbk_isamax)", n, [&] { (void)isamax(n, x, 1); });
+            time_it("saxpy", "pure: new vector + lbk_sync (lbk_saxpy_oop)", n, [&] { DVector w = saxpy(n, 1.0f, x, 1, y, 1); ctx.sync(); });
+            time_it("saxpy", "in place + lbk_sync (lbk_saxpy)", n, [&] { ctx.check(lbk_saxpy(ctx.get(), n, 1.0f, x.get(), 1, y.get(), 1)); ctx.sync(); });
+            time_it("saxpy", "in place, enqueue only (lbk_saxpy)", n, [&] { ctx.check(lbk_saxpy(ctx.get(), n, 0.0f, x.get(), 1, y.get(), 1)); });
+            ctx.sync();
+        }
+        return 0;
+    } catch (const Error &e) {
+        std::fprintf(stderr, "lbk error %d: %s\n", e.status, e.what());
+        return 2;
+    }
+}

@@ -13,6 +13,8 @@
 #include <nccl.h>   // types only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -70,6 +72,7 @@ struct lbk_ctx {
     double *snap = nullptr;           // two slots: snapshots of x[0], y[0] for zero output increments
     void *result_host = nullptr;      // mapped pinned 64 bytes: where synchronous reductions land
     void *result_dev = nullptr;
+    unsigned result_seq = 0;          // tag of the latest synchronous result (host-polled, see finish_sync)
     Record *rec_send = nullptr;       // this rank's record
     Record *rec_all = nullptr;        // all ranks' records after the exchange
     ncclComm_t comm = nullptr;
@@ -200,6 +203,13 @@ extern "C" int lbk_init(int device, lbk_ctx **out)
     INIT(cudaSetDevice(device));
     INIT(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
     INIT(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // vectors come from the device's stream-ordered pool: the reference's pure routines allocate a result
+        // per call (Util.hs:134-142), which must not cost a cudaMalloc + a device-wide synchronise each time
+        cudaMemPool_t pool;
+        INIT(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;      // freed blocks stay cached in the pool
+        INIT(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     INIT(cudaMalloc(&c->partials, sizeof(Record) * kMaxGrid));
     INIT(cudaMalloc(&c->ticket, sizeof(unsigned)));
     INIT(cudaMemset(c->ticket, 0, sizeof(unsigned)));
@@ -430,8 +440,13 @@ static int alloc_common(lbk_ctx *c, const char *who, i64 len, i64 glen, i64 off,
     CU(c, cudaSetDevice(c->device));
     void *p = nullptr;
     if (len > 0) {
+        c->tail_open = false;
+#ifdef LBK_SYNC_MALLOC      // A/B builds only (profiles/r01_criterion_matrix*.csv): plain cudaMalloc / synchronise + cudaFree
         cudaError_t e = cudaMalloc(&p, (size_t)esz(dtype) * (size_t)len);
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, LBK_ERR_NOMEM, std::string(who) + ": cudaMalloc: " + cudaGetErrorString(e)); }
+#else
+        cudaError_t e = cudaMallocAsync(&p, (size_t)esz(dtype) * (size_t)len, c->stream);
+#endif
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, LBK_ERR_NOMEM, std::string(who) + ": cudaMallocAsync: " + cudaGetErrorString(e)); }
     }
     return make_vec(c, p, len, glen, off, true, sharded, dtype, out);
 }
@@ -472,10 +487,15 @@ extern "C" int lbk_vec_view(const lbk_vec *v, int64_t offset, int64_t len, lbk_v
 extern "C" int lbk_vec_free(lbk_vec *v)
 {
     if (!v) return LBK_OK;
-    if (v->owner && v->ptr) {
+    if (v->owner && v->ptr) {      // released in stream order: everything enqueued so far may still use it
         cudaSetDevice(v->ctx->device);
+        v->ctx->tail_open = false;
+#ifdef LBK_SYNC_MALLOC
         cudaStreamSynchronize(v->ctx->stream);
         cudaFree(v->ptr);
+#else
+        cudaFreeAsync(v->ptr, v->ctx->stream);
+#endif
     }
     delete v;
     return LBK_OK;
@@ -971,6 +991,11 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
     fa.out = out;
     fa.rec_out = c->rec_send;
     fa.x0 = (X.i0 == 0 && nl > 0) ? x : nullptr;     // logical element 0 lives at x[0] for incx >= 1
+    if (out == c->result_dev) {                        // a synchronous call: the host polls for this tag
+        if (++c->result_seq == 0) ++c->result_seq;
+        fa.done_flag = reinterpret_cast<unsigned *>(static_cast<char *>(c->result_dev) + 8);
+        fa.done_seq = c->result_seq;
+    }
     const i64 idx_base = X.i0;
     const bool rev = nl > 0 && Y && ((incx == 1 && incy == -1) || (incx == -1 && incy == 1));
     const bool unit = nl > 0 && ((incx == 1 && (!Y || incy == 1)) || (Y && incx == -1 && incy == -1) || rev);
@@ -1028,7 +1053,12 @@ static int store_value(lbk_ctx *c, void *out, T v)
 {
     CU(c, cudaSetDevice(c->device));
     c->tail_open = false;
-    lbk::store_scalar_kernel<T><<<1, 32, 0, c->stream>>>((T *)out, v);
+    unsigned *flag = nullptr;
+    if (out == c->result_dev) {
+        if (++c->result_seq == 0) ++c->result_seq;
+        flag = reinterpret_cast<unsigned *>(static_cast<char *>(c->result_dev) + 8);
+    }
+    lbk::store_scalar_kernel<T><<<1, 32, 0, c->stream>>>((T *)out, v, flag, c->result_seq);
     KERNEL_CHECK(c);
     return LBK_OK;
 }
@@ -1064,7 +1094,21 @@ template <class R>
 static int finish_sync(lbk_ctx *c, int s, R *out)
 {
     if (s) return s;
-    CU(c, cudaStreamSynchronize(c->stream));
+    // The kernel publishes the scalar into mapped host memory and then the tag; polling for the tag returns
+    // as soon as the value has crossed PCIe instead of after the stream has drained and signalled.  A result
+    // that has not arrived within the spin budget (a long kernel, or a failed one) goes through
+    // cudaStreamSynchronize, which also reports the error.
+    volatile unsigned *tag = reinterpret_cast<volatile unsigned *>(static_cast<char *>(c->result_host) + 8);
+    const unsigned want = c->result_seq;
+    bool seen = false;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int spin = 0; !seen; ++spin) {
+        seen = (*tag == want);
+        if (!seen && (spin & 63) == 63 &&
+            std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+    }
+    if (!seen) CU(c, cudaStreamSynchronize(c->stream));
+    std::atomic_thread_fence(std::memory_order_acquire);
     *out = *reinterpret_cast<volatile R *>(c->result_host);
     return check_exchange_error(c);
 }
