@@ -1,7 +1,7 @@
 """Reduce `ncu -i <rep> --page raw --csv` to the columns the roofline discussion uses and refresh
 profiles/traffic.json (DRAM bytes per launch of each headline kernel).
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > /tmp/raw.csv
-    python tools/ncu_select.py /tmp/raw.csv profiles/r01_ncu_full_selected_v2.csv profiles/traffic.json
+    python tools/ncu_select.py /tmp/raw.csv profiles/r01_ncu_full_selected.csv profiles/traffic.json
 """
 import csv
 import json
@@ -14,7 +14,7 @@ KEEP = ["ID", "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum"
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
-ROUTINE = {"AxpyF": "saxpy", "DotOp": "sdot", "Nrm2Op": "snrm2", "IamaxOp": "isamax", "SwapF": "sswap", "CopyF": "scopy", "AsumOp": "sasum",
+ROUTINE = {"AxpyF": "saxpy", "DotOp": "sdot", "Nrm2Op": "snrm2", "IamaxOp": "isamax", "SwapF": "sswap", "CopyF": "scopy", "AsumOp": "sasum", "Rotm0F": "srotm",
            "ScalF": "sscal", "RotF": "srot"}
 
 rows = list(csv.reader(open(sys.argv[1])))
