@@ -109,3 +109,35 @@ def test_record_fold(blas):
     sb = np.float32(2.0 ** -76)
     got = sharded.combine_records(1, [rec((float((big * sb) ** 2), 0, 0)), rec((float((big * sb) ** 2), 0, 0))])
     assert abs(got / (float(big) * np.sqrt(2.0)) - 1) < 1e-6
+
+
+def _header_arity():
+    """name -> number of parameters, from the prototypes of include/lbk.h."""
+    src = open(os.path.join(ROOT, "include", "lbk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for name, params in re.findall(r"\b(lbk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = params.strip()
+        out[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_haskell_shim_binds_declared_symbols_with_matching_arity():
+    """hs/Numerical/BLAS/Device.hs cannot be compiled here (no GHC): at least every `foreign import ccall` in it must
+    name a symbol of include/lbk.h, with as many arguments as the C prototype takes, and cover both instances."""
+    hs = open(os.path.join(ROOT, "hs", "Numerical", "BLAS", "Device.hs")).read()
+    arity = _header_arity()
+    imports = re.findall(r'foreign import ccall\s+(?:unsafe\s+)?"(&?)(lbk_[a-z0-9_]+)"\s+\w+\s*::\s*(.*)', hs)
+    assert len(imports) >= 50
+    for addr, name, ty in imports:
+        assert name in arity, f"Device.hs imports {name}, which include/lbk.h does not declare"
+        if addr:
+            continue                                  # an address import (the finaliser), not a call
+        nargs = len(re.split(r"\s->\s", ty)) - 1      # every "->" outside parentheses separates an argument
+        assert "(" not in ty.replace("Ptr (V Float)", "").replace("Ptr (V Double)", "").replace("Ptr (Ptr LbkCtx)", ""), ty
+        assert nargs == arity[name], f"{name}: Device.hs passes {nargs} arguments, include/lbk.h takes {arity[name]}"
+    names = {n for _, n, _ in imports}
+    for r in ("dot", "asum", "nrm2", "axpy", "scal", "copy", "swap", "rot", "rotm", "rotg", "rotmg",
+              "axpy_oop", "scal_oop", "copy_oop", "swap_oop", "rot_oop", "rotm_oop"):
+        assert f"lbk_s{r}" in names and f"lbk_d{r}" in names, r
+    assert {"lbk_isamax", "lbk_idamax", "lbk_sdsdot", "lbk_vec_alloc", "lbk_vec_alloc_f64", "lbk_vec_free"} <= names
