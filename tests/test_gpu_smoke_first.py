@@ -37,7 +37,7 @@ def test_unit_paths_all_alignments(blas, ctx, oracle, n, off, dtype):
     P.assert_same(xo.to_host(), wx); P.assert_same(yo.to_host(), wy)
 
 
-@pytest.mark.parametrize("variant", range(15))
+@pytest.mark.parametrize("variant", range(23))     # every (pack, unroll, policy) shape, the load-fenced ones included
 @pytest.mark.parametrize("threads", [128, 512])
 @pytest.mark.parametrize("dtype", P.DTYPES)
 def test_every_variant(blas, ctx, oracle, variant, threads, dtype):
@@ -61,6 +61,13 @@ def test_every_variant(blas, ctx, oracle, variant, threads, dtype):
         P.assert_same(x2.to_host(), v); P.assert_same(y2.to_host(), u)
         blas.inplace.sscal_(n, 3.0, x2, 1)
         P.assert_same(x2.to_host(), oracle.sscal(n, 3.0, v, 1))
+        x3, y3 = du.clone(), dv.clone()
+        blas.inplace.srot_(n, x3, 1, y3, 1, np.cos(0.3), np.sin(0.3))
+        wx, wy = oracle.srot(n, u, 1, v, 1, np.cos(0.3), np.sin(0.3))
+        P.assert_same(x3.to_host(), wx); P.assert_same(y3.to_host(), wy)
+        y4 = dv.clone()
+        blas.inplace.scopy_(n - 3, du.view(3, n - 3), 1, y4.view(1, n - 3), 1)      # differently misaligned operands
+        P.assert_same(y4.to_host(), np.concatenate([v[:1], u[3:], v[n - 2:]]))
     finally:
         ctx.set_launch("all", -1, 0, 0)
 
