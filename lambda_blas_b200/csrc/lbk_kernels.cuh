@@ -163,12 +163,19 @@ __device__ __forceinline__ void store_pack(double *ptr, const Pack<double, VEC> 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Programmatic dependent launch (PDL).  A reduction ends with a latency-bound tail (block combine,
-// fence, ticket, last-block fold: ~8 us, as much as 5% of a 4-byte-per-element kernel at n = 2^28).
-// Once a block of a reduction has issued its last load it lets the NEXT kernel of the stream start
-// (launch_dependents); that kernel streams through HBM while the tail drains and calls wait()
-// before it touches anything the tail still owns (scratch, ticket) or before it exits.  The host only
-// sets the launch attribute when the next kernel's operands do not overlap the tail's output.
+// Programmatic dependent launch (PDL).  Between two kernels of a stream the GPU idles for a few
+// microseconds (drain of the last blocks, launch, ramp-up), and a reduction adds a latency-bound tail
+// (block combine, ticket, last-block fold): together as much as 5% of a 4-byte-per-element kernel at
+// n = 2^28.  Every unit-stride kernel therefore releases its dependents AT ONCE
+// (griddepcontrol.launch_dependents as its first instruction): the next kernel of the stream, when the
+// host launched it with the programmatic-serialization attribute, fills SMs as this one's blocks retire.
+// What keeps that correct:
+//   * the host only sets the attribute when the next kernel reads nothing that a still-running
+//     predecessor writes (lbk_lib.cu, pdl_decide);
+//   * a kernel that WRITES something a predecessor reads or writes is told to execute
+//     griddepcontrol.wait (= all predecessors complete and visible) before its first store;
+//   * a reduction executes it before it touches the shared scratch, its result or the mailbox;
+//   * every kernel executes it before it exits, so completion stays in stream order.
 // Both instructions are no-ops in a kernel launched without the attribute.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -272,10 +279,11 @@ __device__ __forceinline__ unsigned low_bits(double v) { return (unsigned)__doub
 template <class F, int VEC, int UNROLL, int POLICY, bool REV = false>
 __global__ void __launch_bounds__(kMaxThreads)
 map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr, typename F::Scalar *xw,
-                typename F::Scalar *yw, i64 head, i64 n, unsigned fence_mask)
+                typename F::Scalar *yw, i64 head, i64 n, unsigned fence_mask, int wait_before_store)
 {
     using T = typename F::Scalar;
     constexpr bool FENCE = POLICY == 6 && (F::RX || F::RY);
+    pdl_launch_dependents();
     const i64 body = n - head;
     const i64 npack = body / VEC;
     const i64 per_tile = (i64)UNROLL * blockDim.x;
@@ -312,6 +320,7 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
 #pragma unroll
                 for (int l = 0; l < VEC; ++l) f(xv[u].v[l], yv[u].v[REV ? VEC - 1 - l : l]);
             }
+            if (wait_before_store) pdl_wait();      // a predecessor may still be reading / writing these addresses
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const i64 e = (p0 + (i64)u * blockDim.x) * VEC + held;
@@ -328,6 +337,7 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
                     if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + YS * e);
 #pragma unroll
                     for (int l = 0; l < VEC; ++l) f(xv[u].v[l], yv[u].v[REV ? VEC - 1 - l : l]);
+                    if (wait_before_store) pdl_wait();
                     if constexpr (F::WX) store_pack<VEC, POLICY>(bxw + e, xv[u]);
                     if constexpr (F::WY) store_pack<VEC, POLICY>(byw + YS * e, yv[u]);
                 }
@@ -345,11 +355,12 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
             if constexpr (F::RX) xs = xr[e];
             if constexpr (F::RY) ys = yr[ey];
             f(xs, ys);
+            if (wait_before_store) pdl_wait();
             if constexpr (F::WX) xw[e] = xs;
             if constexpr (F::WY) yw[ey] = ys;
         }
     }
-    pdl_wait();     // as a PDL secondary: do not retire before the preceding reduction has
+    pdl_wait();     // as a PDL secondary: do not retire before the predecessors have (completion stays in stream order)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -818,8 +829,8 @@ __device__ __forceinline__ void pack_step(typename Op::Acc &acc, const Pack<type
     }
 }
 
-// Rules that depend on logical element 0, applied by the one thread that owns it (block 0, thread 0) while
-// the block's loads are still ahead of its launch_dependents -- a PDL secondary may overwrite x later.
+// Rules that depend on logical element 0, applied by the one thread that owns it (block 0, thread 0).  (A PDL
+// secondary that overwrites x holds its stores until this kernel has completed, so x[0] is still the input.)
 template <class Op>
 __device__ __forceinline__ u64 apply_x0(typename Op::Partial &p, const FinishArgs &fa)
 {
@@ -837,7 +848,7 @@ __device__ __forceinline__ u64 apply_x0(typename Op::Partial &p, const FinishArg
 template <class Op, int VEC, int UNROLL, int POLICY, bool REV = false>
 __global__ void __launch_bounds__(kMaxThreads, reduce_min_blocks(VEC * UNROLL * (int)sizeof(typename Op::Scalar)))
 reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i64 head, i64 n, i64 idx_base,
-                   Record *partials, unsigned *ticket, FinishArgs fa)
+                   Record *partials, unsigned *ticket, FinishArgs fa, int late_trigger)
 {
     using T = typename Op::Scalar;
     constexpr int YS = REV ? -1 : 1;     // REV: element i pairs x[i] with y[n-1-i] (see map_unit_kernel)
@@ -846,6 +857,11 @@ reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
     const T *bx = x + head, *by = REV ? y + (n - head) - VEC : y + head;
+    // Dependents are released at once, unless the host expects the next kernel to collide with this one's
+    // operands or with a kernel still running before it (lbk_lib.cu, TriggerPredictor): then each block releases
+    // them after its last load AND after its predecessors have completed, so that the next kernel may read and
+    // write anything but this kernel's result as soon as it runs, instead of being launched the ordinary way.
+    if (!late_trigger) pdl_launch_dependents();
 
     typename Op::Acc acc = Op::zero();
     unsigned it = 0;
@@ -884,7 +900,7 @@ reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i
         }
     }
     const u64 x0_bits = apply_x0<Op>(p, fa);
-    pdl_launch_dependents();    // every load of this block has been issued and consumed
+    if (late_trigger) { pdl_wait(); pdl_launch_dependents(); }      // every load of this block has been consumed
     if constexpr (Op::IS_IAMAX) {
         if (acc.val >= T(0)) {    // saw >= 1 non-NaN element; ordinal -> global index
             const unsigned per = UNROLL * VEC;
@@ -912,7 +928,6 @@ reduce_strided_kernel(const typename Op::Scalar *x, i64 incx, i64 kx0, const typ
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         Op::single(p, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : T(0), idx_base + i);
     const u64 x0_bits = apply_x0<Op>(p, fa);
-    pdl_launch_dependents();
     grid_finish<Op>(p, partials, ticket, fa, x0_bits);
 }
 

@@ -84,7 +84,7 @@ def test_pdl_overlap_is_invisible(blas, ctx, oracle):
     outs = {}
     for pdl in (False, True):
         ctx.set_pdl(pdl)
-        x, y, r = ctx.to_device(hx), ctx.to_device(hy), ctx.alloc(16).fill(0.0)
+        x, y, z, r = ctx.to_device(hx), ctx.to_device(hy), ctx.alloc(n).fill(0.0), ctx.alloc(16).fill(0.0)
         before = ctx.pdl_count()
         for it in range(6):
             ip.sdot_async(n - 1, x.view(1, n - 1), 1, y.view(1, n - 1), 1, r.view(0, 2))
@@ -94,10 +94,17 @@ def test_pdl_overlap_is_invisible(blas, ctx, oracle):
             ip.sscal_(n, 1.5, x, 1)                           # overwrites x[0] the isamax tail depends on
             ip.sasum_async(n - 1, x.view(1, n - 1), 1, r.view(6, 2))
             ip.sdot_async(n - 1, x.view(1, n - 1), 1, x.view(1, n - 1), 1, r.view(8, 2))
-        outs[pdl] = (r.to_host(), x.to_host(), y.to_host(), ctx.pdl_count() - before)
+            # every kernel releases its dependents at once, so each hazard class must be caught on the host:
+            ip.scopy_(n, x, 1, z, 1)                          # independent of the sdot above: overlaps it
+            ip.scopy_(n, y, 1, z, 1)                          # write after write (z): stores wait for the first copy
+            ip.snrm2_async(n, z, 1, r.view(10, 2))            # read after write (z): ordinary launch
+            ip.sswap_(n, z, 1, y, 1)                          # writes z and y right after a reduction read z
+            ip.saxpy_(n, -0.5, y, 1, z, 1)                    # reads y, z the swap is still writing
+            ip.sasum_async(n, z, 1, r.view(12, 2))
+        outs[pdl] = (r.to_host(), x.to_host(), y.to_host(), z.to_host(), ctx.pdl_count() - before)
     ctx.set_pdl(True)
-    assert outs[False][3] == 0 and outs[True][3] >= 6 * 4
-    for a, b in zip(outs[False][:3], outs[True][:3]):
+    assert outs[False][4] == 0 and outs[True][4] >= 6 * 6
+    for a, b in zip(outs[False][:4], outs[True][:4]):
         P.assert_same(a, b)
     assert outs[True][0][4:6].view(np.int64)[0] == 0
 
