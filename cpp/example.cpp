@@ -28,6 +28,13 @@ int main()
         bool ok = d == 32.0f && hw[0] == 6 && hw[1] == 9 && hw[2] == 12 && hv[0] == 4 && isamax(3, v, 1) == 2 &&
                   a[0] == 6 && a[1] == 4 && a[2] == 3 && b[0] == 2 && b[1] == 5 && b[2] == 1;   // x[1-i] <-> y[2i], Util.hs:118-119
         try { sdot(5, u, 1, v, 1); ok = false; } catch (const Error &e) { ok = ok && e.status == LBK_ERR_RANGE; }
+        // the Double instance (ddot, daxpy, idamax: Single.hs:86,224,443) through the same templates
+        DVectorD ud(ctx, std::vector<double>{1, 2, 3}), vd(ctx, std::vector<double>{4, 5, 6});
+        auto wd = daxpy(3, 2.0, ud, 1, vd, 1).to_host();
+        std::printf("ddot = %g daxpy = [%g %g %g] idamax = %lld dnrm2 = %.17g\n", ddot(3, ud, 1, vd, 1), wd[0], wd[1], wd[2],
+                    (long long)idamax(3, vd, 1), dnrm2(3, vd, 1));
+        ok = ok && ddot(3, ud, 1, vd, 1) == 32.0 && wd[0] == 6 && wd[2] == 12 && idamax(3, vd, 1) == 2 &&
+             std::fabs(dnrm2(3, vd, 1) - std::sqrt(77.0)) <= 2e-15 * std::sqrt(77.0);
         std::printf(ok ? "OK\n" : "MISMATCH\n");
         return ok ? 0 : 1;
     } catch (const Error &e) {

@@ -53,7 +53,7 @@ struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: de
 // shape every writer prefers (with the load fence of POLICY 6 and 32-64 bytes per thread per operand).
 constexpr int kOneTilePerBlock = 1 << 20;
 static const LaunchCfg kDefaultCfg[R_COUNT] = {
-    /* dot  */ {4, 256, 16},   /* sdsdot */ {3, 512, 8},    /* asum */ {4, 512, 8},
+    /* dot  */ {4, 256, 16},   /* sdsdot */ {3, 512, 8},    /* asum */ {3, 256, 16},
     /* nrm2 */ {3, 256, 16},   /* iamax  */ {3, 256, 16},   /* axpy */ {16, 512, kOneTilePerBlock},
     /* scal */ {20, 512, kOneTilePerBlock},  /* copy */ {20, 512, kOneTilePerBlock},  /* swap */ {22, 512, kOneTilePerBlock},
     /* rot  */ {22, 256, kOneTilePerBlock},  /* rotm */ {22, 256, kOneTilePerBlock},  /* fill */ {4, 256, 256},
