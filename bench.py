@@ -8,7 +8,7 @@ One "step" = one pass of the hot path over one batch of synthetic fp32 data: sdo
 n = 2^28 per GPU, unit stride (BASELINE.json's metric: "sdot/saxpy/snrm2 achieved HBM GB/s at n=2^28").
 Algorithmic bytes per element: sdot 8 + saxpy 12 + snrm2 4 = 24.  Weak scaling: every
 rank holds a 2^28-element block shard of each vector; saxpy needs no communication, each reduction ends
-with one 32-byte record exchange.  Rank 0 prints ONE JSON line.
+with one 48-byte record exchange.  Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -178,7 +178,7 @@ def workload_config(args, world: int) -> dict:
                      f"(BASELINE.json metric; configs[1]-[2] class); all ten routines are reported under `routines`"),
         "n_per_gpu": n, "n_global": n * world, "bytes_per_elem_step": STEP_BYTES_PER_ELEM,
         "l2": "each vector is 1 GiB per GPU, far larger than the 126 MB L2, so no flush between iterations",
-        "parallelism": f"{world} rank(s), one per GPU; saxpy: no communication; sdot/snrm2: one 32-byte record exchange per call",
+        "parallelism": f"{world} rank(s), one per GPU; saxpy: no communication; sdot/snrm2: one 48-byte record exchange per call",
     }
 
 
@@ -205,7 +205,7 @@ def run_ours(args) -> None:
         if args.exchange != "auto":
             ctx.set_fused_exchange(args.exchange == "fused")
     exchange = ("fused: record pushed into every peer's mailbox over NVLink inside the reduction kernel" if ctx.fused_exchange()
-                else "ncclAllGather of one 32-byte record + finish kernel") if world > 1 else "none (1 rank)"
+                else "ncclAllGather of one 48-byte record + finish kernel") if world > 1 else "none (1 rank)"
 
     n = 1 << args.log2n
     ng = n * world

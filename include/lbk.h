@@ -24,8 +24,10 @@
  *     outside a vector (the reference would read out of bounds) and layouts the
  *     device path does not support (see LBK_ERR_UNSUPPORTED);
  *   - vector routines are IN PLACE on device vectors and only ENQUEUE work on the
- *     context's stream; routines returning a scalar synchronise that stream before
- *     they return.  The reference's PURE results (new vectors, inputs untouched,
+ *     context's stream; routines returning a scalar return once that scalar has
+ *     arrived on the host (the kernel publishes it in mapped memory and the host
+ *     polls; earlier work of the stream has completed by then, later calls may
+ *     be issued at once).  The reference's PURE results (new vectors, inputs untouched,
  *     Util.hs:134-142) are obtained by the host layer with lbk_vec_clone + the
  *     in-place routine, or in one pass with the *_oop ("out of place") variants;
  *   - one context per host thread, or calls on a context serialised by the caller.
@@ -73,10 +75,11 @@ int lbk_sm_count(lbk_ctx *ctx, int *sms);
 int lbk_set_launch(lbk_ctx *ctx, const char *routine, int variant, int threads, int blocks_per_sm);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int lbk_launch_count(lbk_ctx *ctx, int64_t *launches);
-/* Programmatic dependent launch (on by default): a unit-stride kernel enqueued right after a unit-stride
- * reduction may start while that reduction's latency-bound tail (block combine, last-block fold) drains,
- * provided its operands do not overlap the reduction's result.  Results are unaffected.  lbk_pdl_count
- * reports how many launches took that path. */
+/* Programmatic dependent launch (on by default): consecutive unit-stride kernels overlap at their boundary --
+ * the next kernel fills SMs while the previous one's last blocks (and a reduction's latency-bound tail)
+ * drain.  The library tracks what the kernels still in flight read and write and launches the next one
+ * the ordinary way, or makes it hold its stores, whenever the two depend on each other,
+ * so results are unaffected.  lbk_pdl_count reports how many launches took that path. */
 int lbk_set_pdl(lbk_ctx *ctx, int enabled);
 int lbk_pdl_count(lbk_ctx *ctx, int64_t *launches);
 
@@ -87,7 +90,7 @@ int lbk_pdl_count(lbk_ctx *ctx, int64_t *launches);
 int lbk_comm_unique_id(char id[128]);
 int lbk_comm_init(lbk_ctx *ctx, int nranks, int rank, const char id[128]);
 int lbk_comm_info(lbk_ctx *ctx, int *nranks, int *rank);
-/* How a sharded reduction ends.  fused = 1: the reduction kernel's last block writes this rank's 32-byte
+/* How a sharded reduction ends.  fused = 1: the reduction kernel's last block writes this rank's 48-byte
  * record straight into every peer GPU's mailbox over NVLink (peer memory mapped with CUDA IPC at
  * lbk_comm_init), waits for the peers' records and folds them in rank order -- compute and exchange in ONE
  * kernel.  fused = 0: record -> ncclAllGather -> a one-thread finish kernel.  lbk_comm_init picks fused when
@@ -101,6 +104,9 @@ int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t *lo, int64
  * The reference's routines are polymorphic with Float and Double instances (sdot/ddot, ..., Single.hs:83-87);
  * a device vector is single precision unless made by an *_f64 constructor.  The s* routines take single-,
  * the d* routines double-precision vectors (LBK_ERR_ARG otherwise).  Lengths are in ELEMENTS. */
+/* Owning vectors come from the device's stream-ordered memory pool (cudaMallocAsync on the context's stream);
+ * lbk_vec_free releases them in stream order: work already enqueued may still use the vector, and neither
+ * call synchronises. */
 int lbk_vec_alloc(lbk_ctx *ctx, int64_t len, lbk_vec **v);
 int lbk_vec_alloc_f64(lbk_ctx *ctx, int64_t len, lbk_vec **v);
 int lbk_vec_alloc_sharded(lbk_ctx *ctx, int64_t global_len, lbk_vec **v);

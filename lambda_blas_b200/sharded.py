@@ -1,7 +1,7 @@
 """Multi-GPU plumbing: one process per GPU, vectors sharded by contiguous blocks.
 
 The reference is single-process and single-threaded; sharding is new.  Elementwise
-routines need no communication.  A reduction runs the local kernel, then exchanges ONE 32-byte
+routines need no communication.  A reduction runs the local kernel, then exchanges ONE 48-byte
 record per rank (NCCL all-gather over NVLink on the library's own stream) and every rank folds the
 records in rank order, so all ranks return the same bits.  torch.distributed is used only to carry
 the 128-byte NCCL id to the other ranks and for barriers around timed regions.
