@@ -397,10 +397,11 @@ def run_ours(args) -> None:
                     "traffic": ncu_traffic("saxpy")}
         cpu_baseline = None
         if world == 1 and not args.no_cpu:
-            dt, gbs = time_cpu(1 << args.ref_log2n, 3, 1)
+            cpu_steps = 20           # about 10 s of CPU work on one core
+            dt, gbs = time_cpu(1 << args.ref_log2n, cpu_steps, 1)
             model, ncpu = cpu_info()
             cpu_baseline = {"value": round(gbs, 3), "unit": "GB/s", "cores": 1, "kind": "port",
-                            "sample": (f"3 steps of sdot+saxpy(pure)+snrm2 on a 2^{args.ref_log2n}-element sample (the oracle, C port of the "
+                            "sample": (f"{cpu_steps} steps of sdot+saxpy(pure)+snrm2 on a 2^{args.ref_log2n}-element sample (the oracle, C port of the "
                                        f"reference's Haskell, single thread as the reference is); host {model}, {ncpu} logical CPUs")}
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),

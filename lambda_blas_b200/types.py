@@ -170,34 +170,36 @@ class DVector:
 
     def __init__(self, ctx: Context, handle: C.c_void_p, parent: "Optional[DVector]" = None):
         self.ctx, self._h, self._parent, self._keep = ctx, handle, parent, None
+        # a handle's geometry never changes: read it once (the pure routines ask for it on every call)
+        L = _ffi.lib()
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _ffi.check(L.lbk_vec_len(handle, C.byref(a), C.byref(b), C.byref(c)), ctx.handle)
+        self._len, self._glen, self._off = a.value, b.value, c.value
+        self._ptr = int(L.lbk_vec_ptr(handle) or 0)
+        self._dtype = np.dtype(np.float64 if L.lbk_vec_elem_size(handle) == 8 else np.float32)
 
     @property
     def handle(self):
         return self._h
 
-    def _lens(self):
-        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
-        _ffi.check(_ffi.lib().lbk_vec_len(self._h, C.byref(a), C.byref(b), C.byref(c)), self.ctx.handle)
-        return a.value, b.value, c.value
-
     def __len__(self) -> int:
-        return self._lens()[0]
+        return self._len
 
     @property
     def global_len(self) -> int:
-        return self._lens()[1]
+        return self._glen
 
     @property
     def shard_offset(self) -> int:
-        return self._lens()[2]
+        return self._off
 
     @property
     def ptr(self) -> int:
-        return int(_ffi.lib().lbk_vec_ptr(self._h) or 0)
+        return self._ptr
 
     @property
     def dtype(self):
-        return np.dtype(np.float64 if _ffi.lib().lbk_vec_elem_size(self._h) == 8 else np.float32)
+        return self._dtype
 
     def clone(self) -> "DVector":
         h = C.c_void_p()
