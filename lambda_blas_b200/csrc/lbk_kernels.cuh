@@ -760,26 +760,31 @@ __device__ __forceinline__ void grid_finish(typename Op::Partial p, Record *part
     __shared__ bool is_last;
     p = block_combine<Op>(p);
     pdl_wait();          // the scratch below may still be in use by the preceding reduction's tail
-    if (threadIdx.x == 0) {
-        Op::store(&partials[blockIdx.x], p);
-        if (blockIdx.x == 0 && fa.kind == 1) __stcg(&partials[0].key, x0_bits);
-        // release this block's slot / acquire the others' with the ticket itself (no separate fence)
-        unsigned t;
-        asm volatile("atom.acq_rel.gpu.global.inc.u32 %0, [%1], %2;" : "=r"(t) : "l"(ticket), "r"(gridDim.x - 1) : "memory");
-        is_last = (t == gridDim.x - 1);                        // the ticket wraps to 0: ready for the next launch
+    typename Op::Partial acc = p;
+    u64 x0_key = x0_bits;
+    if (gridDim.x > 1) {                     // a one-block launch (small n) is its own last block: no second pass
+        if (threadIdx.x == 0) {
+            Op::store(&partials[blockIdx.x], p);
+            if (blockIdx.x == 0 && fa.kind == 1) __stcg(&partials[0].key, x0_bits);
+            // release this block's slot / acquire the others' with the ticket itself (no separate fence)
+            unsigned t;
+            asm volatile("atom.acq_rel.gpu.global.inc.u32 %0, [%1], %2;" : "=r"(t) : "l"(ticket), "r"(gridDim.x - 1) : "memory");
+            is_last = (t == gridDim.x - 1);                        // the ticket wraps to 0: ready for the next launch
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        acc = Op::empty();
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+            acc = Op::merge(acc, Op::load(&partials[b]));          // other blocks' slots: read through L2
+        acc = block_combine<Op>(acc);
+        if (threadIdx.x == 0 && fa.kind == 1 && fa.x0 != nullptr) x0_key = __ldcg(&partials[0].key);
     }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    typename Op::Partial acc = Op::empty();
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-        acc = Op::merge(acc, Op::load(&partials[b]));          // other blocks' slots: read through L2
-    acc = block_combine<Op>(acc);
     __shared__ Record mine;
     if (threadIdx.x == 0) {
         Record r = empty_record();
         Op::to_record(r, acc);
-        if (fa.kind == 1 && fa.x0 != nullptr) r.key = __ldcg(&partials[0].key);     // nrm2 n==1 -> |x[0]|
+        if (fa.kind == 1 && fa.x0 != nullptr) r.key = x0_key;       // nrm2 n==1 -> |x[0]|
         if (fa.mode == 0) finish_record(r, fa);
         else if (fa.mode == 1) *fa.rec_out = r;
         else mine = r;
