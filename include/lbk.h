@@ -230,6 +230,18 @@ typedef struct lbk_record { double f[3]; uint64_t key; int64_t idx; int64_t pad;
 enum lbk_reduce_kind { LBK_RED_SUM = 0, LBK_RED_NRM2 = 1, LBK_RED_IAMAX = 2 };
 int lbk_combine_records(int kind, int is_f64, const lbk_record *recs, int nranks, double *fout, int64_t *iout);
 
+/* ---- the launch planner on its own (CPU tests of the programmatic-dependent-launch rules) ------------------
+ * Feeds one unit-stride kernel at a time -- what it reads and writes as (address, bytes) pairs, whether it is a
+ * reduction, its routine id -- to the planner the library uses (lambda_blas_b200/csrc/lbk_pdl.hpp) and reports
+ * how it would be launched: mode 0 = ordinary launch, 1 = overlaps its predecessors, waits before it exits,
+ * 2 = overlaps, but waits before its first store; late = 1: a reduction that releases its dependents only after
+ * its loads.  lbk_pdl_sim_interrupt = any other operation on the stream. */
+int lbk_pdl_sim_create(void **sim);
+int lbk_pdl_sim_destroy(void *sim);
+int lbk_pdl_sim_enable(void *sim, int enabled);
+int lbk_pdl_sim_interrupt(void *sim);
+int lbk_pdl_sim_op(void *sim, int reduction, int rid, const int64_t *rd, int nrd, const int64_t *wr, int nwr, int *mode, int *late);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,11 @@ PROTOTYPES = {
     "lbk_srotmg": (_int, [_f32, _f32, _f32, _f32, _pf32, _pf32]),
     "lbk_drotmg": (_int, [_f64, _f64, _f64, _f64, _pf64, _pf64]),
     "lbk_combine_records": (_int, [_int, _int, C.POINTER(Record), _int, _pf64, _pi64]),
+    "lbk_pdl_sim_create": (_int, [_pvp]),
+    "lbk_pdl_sim_destroy": (_int, [_vp]),
+    "lbk_pdl_sim_enable": (_int, [_vp, _int]),
+    "lbk_pdl_sim_interrupt": (_int, [_vp]),
+    "lbk_pdl_sim_op": (_int, [_vp, _int, _int, _pi64, _int, _pi64, _int, _pint, _pint]),
 }
 # the Float and Double instances of every vector routine: same shapes, s/d prefix, float/double scalars
 for _p, _fx, _pfx, _ip in (("s", _f32, _pf32, "is"), ("d", _f64, _pf64, "id")):

@@ -7,6 +7,7 @@
 // shape, and -- with a communicator -- the one exchange that ends a sharded reduction.
 #include "../../include/lbk.h"
 #include "lbk_kernels.cuh"
+#include "lbk_pdl.hpp"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -85,38 +86,7 @@ struct lbk_ctx {
     unsigned exchange_seq = 0;
     int *error_flag_host = nullptr, *error_flag_dev = nullptr;   // mapped: a kernel reports an exchange timeout
     LaunchCfg cfg[R_COUNT];
-    // Programmatic dependent launch.  Every unit-stride kernel releases its dependents at once
-    // (griddepcontrol.launch_dependents at kernel start), so the NEXT unit-stride kernel can fill SMs while this
-    // one drains.  `grp` is the set of kernels that may still be running when the next one starts: the chain of
-    // PDL launches since the last ordinary launch (or other stream operation), with everything they read and
-    // write.  The next kernel is checked against it (pdl_decide): a true dependency -> ordinary launch; an
-    // anti/output dependency -> PDL, but the kernel waits for its predecessors before its first store.
-    struct Range { const char *lo, *hi; };
-    struct PdlGroup {
-        static constexpr int kCap = 24;
-        bool open = false;
-        int nr = 0, nw = 0;
-        Range r[kCap], w[kCap];
-    } grp;
-    bool pdl_enabled = true;
-    // Where should a reduction release its dependents?  At once is best when the next kernel is independent of
-    // everything still running (it overlaps the whole last wave).  After its loads and after its predecessors
-    // have completed ("late") is best when the next kernel collides with this reduction's operands or with an
-    // earlier kernel of the chain: released late, the group shrinks to this reduction's result and the next
-    // kernel runs under its tail; released at once, that kernel would store late or be launched the ordinary
-    // way.  The successor is not known at launch time, so it is predicted: what followed the same call
-    // (routine, operands) last time.
-    struct TriggerPredictor {
-        static constexpr int kSlots = 64;
-        struct Slot { const void *x = nullptr, *y = nullptr; int rid = -1; bool late = false; } slot[kSlots];
-        // the reduction launched last, until the next unit-stride kernel tells what it was followed by:
-        // `hyp` is the group as it would stand had that reduction released its dependents at once
-        bool pending = false;
-        int pending_slot = 0;
-        PdlGroup hyp;
-        static int hash(int rid, const void *x, const void *y)
-        { return (int)((((uintptr_t)x >> 8) * 31u + ((uintptr_t)y >> 8) * 17u + (unsigned)rid) % kSlots); }
-    } trig;
+    lbk_pdl::State pdl;               // which kernels of the stream may overlap: see lbk_pdl.hpp
     int64_t launches = 0;
     int64_t pdl_launches = 0;
     std::string err;
@@ -331,7 +301,7 @@ extern "C" int lbk_launch_count(lbk_ctx *c, int64_t *launches)
 extern "C" int lbk_set_pdl(lbk_ctx *c, int enabled)
 {
     if (!c) return fail(c, LBK_ERR_ARG, "lbk_set_pdl: null context");
-    c->pdl_enabled = enabled != 0;
+    c->pdl.enabled = enabled != 0;
     return LBK_OK;
 }
 
@@ -467,7 +437,7 @@ static int alloc_common(lbk_ctx *c, const char *who, i64 len, i64 glen, i64 off,
     CU(c, cudaSetDevice(c->device));
     void *p = nullptr;
     if (len > 0) {
-        c->grp.open = false;
+        lbk_pdl::interrupt(c->pdl);
 #ifdef LBK_SYNC_MALLOC      // A/B builds only (profiles/r01_criterion_matrix*.csv): plain cudaMalloc / synchronise + cudaFree
         cudaError_t e = cudaMalloc(&p, (size_t)esz(dtype) * (size_t)len);
 #else
@@ -516,7 +486,7 @@ extern "C" int lbk_vec_free(lbk_vec *v)
     if (!v) return LBK_OK;
     if (v->owner && v->ptr) {      // released in stream order: everything enqueued so far may still use it
         cudaSetDevice(v->ctx->device);
-        v->ctx->grp.open = false;
+        lbk_pdl::interrupt(v->ctx->pdl);
 #ifdef LBK_SYNC_MALLOC
         cudaStreamSynchronize(v->ctx->stream);
         cudaFree(v->ptr);
@@ -542,7 +512,7 @@ extern "C" void *lbk_vec_ptr(const lbk_vec *v) { return v ? (void *)v->ptr : nul
 extern "C" int lbk_vec_upload_async(lbk_vec *v, const void *host, int64_t len)
 {
     if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_upload: bad argument");
-    if (len) { v->ctx->grp.open = false; CU(v->ctx, cudaMemcpyAsync(v->ptr, host, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream)); }
+    if (len) { lbk_pdl::interrupt(v->ctx->pdl); CU(v->ctx, cudaMemcpyAsync(v->ptr, host, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream)); }
     return LBK_OK;
 }
 extern "C" int lbk_vec_upload(lbk_vec *v, const void *host, int64_t len)
@@ -553,7 +523,7 @@ extern "C" int lbk_vec_upload(lbk_vec *v, const void *host, int64_t len)
 extern "C" int lbk_vec_download_async(const lbk_vec *v, void *host, int64_t len)
 {
     if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_download: bad argument");
-    if (len) { v->ctx->grp.open = false; CU(v->ctx, cudaMemcpyAsync(host, v->ptr, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyDeviceToHost, v->ctx->stream)); }
+    if (len) { lbk_pdl::interrupt(v->ctx->pdl); CU(v->ctx, cudaMemcpyAsync(host, v->ptr, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyDeviceToHost, v->ctx->stream)); }
     return LBK_OK;
 }
 extern "C" int lbk_vec_download(const lbk_vec *v, void *host, int64_t len)
@@ -570,7 +540,7 @@ extern "C" int lbk_vec_clone(const lbk_vec *v, lbk_vec **out)
     if (s) return s;
     w->global_len = v->global_len; w->shard_off = v->shard_off; w->sharded = v->sharded;
     if (v->len) {
-        v->ctx->grp.open = false;
+        lbk_pdl::interrupt(v->ctx->pdl);
         cudaError_t e = cudaMemcpyAsync(w->ptr, v->ptr, (size_t)esz(v->dtype) * (size_t)v->len, cudaMemcpyDeviceToDevice, v->ctx->stream);
         if (e != cudaSuccess) { lbk_vec_free(w); return fail(v->ctx, LBK_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e)); }
     }
@@ -586,7 +556,7 @@ extern "C" int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, double lo, double hi
     if (!v->len) return LBK_OK;
     lbk_ctx *c = v->ctx;
     CU(c, cudaSetDevice(c->device));
-    c->grp.open = false;
+    lbk_pdl::interrupt(c->pdl);
     const int grid = stream_grid(c, v->len, 256);
     if (v->dtype) lbk::fill_hash_kernel<double><<<grid, 256, 0, c->stream>>>((double *)v->ptr, v->len, v->shard_off, seed, lo, hi - lo);
     else lbk::fill_hash_kernel<float><<<grid, 256, 0, c->stream>>>((float *)v->ptr, v->len, v->shard_off, seed, (float)lo, (float)hi - (float)lo);
@@ -625,14 +595,14 @@ extern "C" int lbk_event_create(lbk_ctx *c, lbk_event **out)
 extern "C" int lbk_event_record(lbk_event *e)
 {
     if (!e) return fail(nullptr, LBK_ERR_ARG, "lbk_event_record: null event");
-    e->ctx->grp.open = false;
+    lbk_pdl::interrupt(e->ctx->pdl);
     CU(e->ctx, cudaEventRecord(e->ev, e->ctx->stream));
     return LBK_OK;
 }
 extern "C" int lbk_wait_event(lbk_ctx *c, lbk_event *e)
 {
     if (!c || !e) return fail(c, LBK_ERR_ARG, "lbk_wait_event: null argument");
-    c->grp.open = false;
+    lbk_pdl::interrupt(c->pdl);
     CU(c, cudaStreamWaitEvent(c->stream, e->ev, 0));
     return LBK_OK;
 }
@@ -769,85 +739,21 @@ static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int th
     return LBK_OK;
 }
 
-// ---- programmatic dependent launch: hazards between the kernels that may run at the same time ----
-enum PdlMode { PDL_NONE = 0, PDL_WAIT_AT_EXIT = 1, PDL_WAIT_BEFORE_STORE = 2 };
-
-static bool group_hits(const lbk_ctx::Range *set, int n, const void *p, i64 nbytes)
-{
-    if (!p || nbytes <= 0) return false;
-    const char *lo = (const char *)p, *hi = lo + nbytes;
-    for (int i = 0; i < n; ++i)
-        if (lo < set[i].hi && set[i].lo < hi) return true;
-    return false;
-}
-
-// How may a kernel that reads `rd` and writes `wr` (pointer, bytes) be launched behind the open group?
-// `writes_after_wait`: a reduction writes (scratch, result) only after griddepcontrol.wait, so only what it
-// READS can collide with its predecessors.
-static PdlMode group_decide(const lbk_ctx::PdlGroup &g, const void *const *rd, const i64 *rdn, int nrd, const void *const *wr,
-                            const i64 *wrn, int nwr, bool writes_after_wait)
-{
-    if (!g.open) return PDL_NONE;
-    for (int i = 0; i < nrd; ++i)
-        if (group_hits(g.w, g.nw, rd[i], rdn[i])) return PDL_NONE;            // reads what a predecessor writes
-    if (writes_after_wait) return PDL_WAIT_AT_EXIT;
-    for (int i = 0; i < nwr; ++i)
-        if (group_hits(g.r, g.nr, wr[i], wrn[i]) || group_hits(g.w, g.nw, wr[i], wrn[i])) return PDL_WAIT_BEFORE_STORE;
-    return PDL_WAIT_AT_EXIT;
-}
-static PdlMode pdl_decide(lbk_ctx *c, const void *const *rd, const i64 *rdn, int nrd, const void *const *wr, const i64 *wrn,
-                          int nwr, bool writes_after_wait)
-{
-    return c->pdl_enabled ? group_decide(c->grp, rd, rdn, nrd, wr, wrn, nwr, writes_after_wait) : PDL_NONE;
-}
-
-static void group_add(lbk_ctx::Range *set, int *n, const void *p, i64 nbytes, bool *full)
-{
-    if (!p || nbytes <= 0) return;
-    const char *lo = (const char *)p, *hi = lo + nbytes;
-    for (int i = 0; i < *n; ++i)
-        if (set[i].lo <= lo && hi <= set[i].hi) return;                      // already covered
-    if (*n == lbk_ctx::PdlGroup::kCap) { *full = true; return; }
-    set[(*n)++] = lbk_ctx::Range{lo, hi};
-}
-
-// Launches a unit-stride kernel (as a PDL secondary unless mode is PDL_NONE) and records it in the group.
-// `reduction`: its writes come after griddepcontrol.wait; `late`: it releases its dependents only after its
-// loads, so what it reads is no longer in use when a dependent runs and stays out of the group.
-static int launch_stream_kernel(lbk_ctx *c, const void *k, int grid, int threads, void **args, PdlMode mode,
-                                const void *const *rd, const i64 *rdn, int nrd, const void *const *wr, const i64 *wrn, int nwr,
-                                bool reduction = false, bool late = false)
+// Launches a unit-stride kernel the way lbk_pdl planned it and records it in the group of kernels in flight.
+static int launch_stream_kernel(lbk_ctx *c, const void *k, int grid, int threads, void **args, const lbk_pdl::Op &op,
+                                const lbk_pdl::Plan &plan)
 {
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = 0; lc.stream = c->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = mode != PDL_NONE ? 1 : 0;
-    lbk_ctx::PdlGroup &g = c->grp;
-    if (c->trig.pending) {      // teach the predictor: released at once, would the last reduction have held this kernel back?
-        c->trig.slot[c->trig.pending_slot].late =
-            group_decide(c->trig.hyp, rd, rdn, nrd, wr, wrn, nwr, reduction) != PDL_WAIT_AT_EXIT;
-        c->trig.pending = false;
-    }
-    if (mode == PDL_NONE) { g.nr = g.nw = 0; }          // an ordinary launch starts after everything before it
-    g.open = false;
+    lc.attrs = at; lc.numAttrs = plan.mode != lbk_pdl::NONE ? 1 : 0;
+    lbk_pdl::interrupt(c->pdl);                          // stays closed if the launch fails
     CU(c, cudaLaunchKernelExC(&lc, k, args));
-    if (mode != PDL_NONE) c->pdl_launches++;
+    if (plan.mode != lbk_pdl::NONE) c->pdl_launches++;
     KERNEL_CHECK(c);
-    bool full = false;
-    if (reduction) {            // what the group would be had this reduction released its dependents at once
-        lbk_ctx::PdlGroup &h = c->trig.hyp;
-        h = g;
-        bool hfull = false;
-        for (int i = 0; i < nrd; ++i) group_add(h.r, &h.nr, rd[i], rdn[i], &hfull);
-        for (int i = 0; i < nwr; ++i) group_add(h.w, &h.nw, wr[i], wrn[i], &hfull);
-        h.open = !hfull;
-    }
-    if (late) { g.nr = g.nw = 0; }      // released after its loads and its predecessors: only its result is still in flight
-    for (int i = 0; i < nrd && !late; ++i) group_add(g.r, &g.nr, rd[i], rdn[i], &full);
-    for (int i = 0; i < nwr; ++i) group_add(g.w, &g.nw, wr[i], wrn[i], &full);
-    g.open = !full;                                      // a full table ends the chain: the next launch is ordinary
+    lbk_pdl::commit(c->pdl, op, plan);
     return LBK_OK;
 }
 
@@ -887,17 +793,16 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
     F fc = f;
     unsigned fence_mask = 0;     // see map_unit_kernel: always 0, but only known at run time
     const i64 nb = n * (i64)sizeof(T);
-    const void *rd[2] = {nullptr, nullptr}; i64 rdn[2] = {0, 0}; int nrd = 0;
-    const void *wr[2] = {nullptr, nullptr}; i64 wrn[2] = {0, 0}; int nwr = 0;
-    if (F::RX) { rd[nrd] = xr; rdn[nrd++] = nb; }
-    if (F::RY) { rd[nrd] = yr; rdn[nrd++] = nb; }
-    if (F::WX) { wr[nwr] = xw; wrn[nwr++] = nb; }
-    if (F::WY) { wr[nwr] = yw; wrn[nwr++] = nb; }
-    const PdlMode mode = pdl_decide(c, rd, rdn, nrd, wr, wrn, nwr, false);
-    int wait_before_store = mode == PDL_WAIT_BEFORE_STORE ? 1 : 0;
+    lbk_pdl::Op op;
+    if (F::RX) { op.rd[op.nrd] = xr; op.rdn[op.nrd++] = nb; }
+    if (F::RY) { op.rd[op.nrd] = yr; op.rdn[op.nrd++] = nb; }
+    if (F::WX) { op.wr[op.nwr] = xw; op.wrn[op.nwr++] = nb; }
+    if (F::WY) { op.wr[op.nwr] = yw; op.wrn[op.nwr++] = nb; }
+    const lbk_pdl::Plan plan = lbk_pdl::plan(c->pdl, op);
+    int wait_before_store = plan.mode == lbk_pdl::WAIT_BEFORE_STORE ? 1 : 0;
     void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n,
                     (void *)&fence_mask, (void *)&wait_before_store};
-    return launch_stream_kernel(c, k, grid, threads, args, mode, rd, rdn, nrd, wr, wrn, nwr);
+    return launch_stream_kernel(c, k, grid, threads, args, op, plan);
 }
 
 extern "C" int lbk_vec_fill(lbk_vec *v, double value)
@@ -925,7 +830,7 @@ static int launch_map_strided(lbk_ctx *c, const F &f, const typename F::Scalar *
     const i64 ntiles = (n - i_begin + per_tile - 1) / per_tile;
     const i64 cap = cfg.blocks_per_sm > 0 ? (i64)c->sms * cfg.blocks_per_sm : (wide ? ntiles : (i64)c->sms * 256);
     const int grid = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(ntiles, cap), 0x7fffffff));
-    c->grp.open = false;
+    lbk_pdl::interrupt(c->pdl);
     if (cfg.variant == 0)
         lbk::map_strided_kernel<F, false><<<grid, threads, 0, c->stream>>>(f, xr, xw, incx_r, incx_w, kx0_r, kx0_w,
                                                                             yr, yw, incy_r, incy_w, ky0_r, ky0_w, i_begin, n, x_last, y_last, 0u);
@@ -966,11 +871,11 @@ static int map_dispatch(lbk_ctx *c, int rid, const F &f, i64 n, const Operand &X
     T *snap = (T *)c->snap;
     if (F::WX && incx == 0) {            // n sequential writes to x[0]: the last wins, all read the original
         x_last = 1;
-        if (F::RX) { c->grp.open = false; CU(c, cudaMemcpyAsync(snap, xr, sizeof(T), cudaMemcpyDeviceToDevice, c->stream)); xr = snap; kx0_r = 0; }
+        if (F::RX) { lbk_pdl::interrupt(c->pdl); CU(c, cudaMemcpyAsync(snap, xr, sizeof(T), cudaMemcpyDeviceToDevice, c->stream)); xr = snap; kx0_r = 0; }
     }
     if (F::WY && incy == 0) {
         y_last = 1;
-        if (F::RY) { c->grp.open = false; CU(c, cudaMemcpyAsync(snap + 1, yr, sizeof(T), cudaMemcpyDeviceToDevice, c->stream)); yr = snap + 1; ky0_r = 0; }
+        if (F::RY) { lbk_pdl::interrupt(c->pdl); CU(c, cudaMemcpyAsync(snap + 1, yr, sizeof(T), cudaMemcpyDeviceToDevice, c->stream)); yr = snap + 1; ky0_r = 0; }
     }
     const bool only_last = (!F::WX || x_last) && (!F::WY || y_last);
     return launch_map_strided<F>(c, f, xr, xw, incx, incx, kx0_r, kx0, yr, yw, incy, incy, ky0_r, ky0,
@@ -1026,7 +931,7 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
         const bool unit_cover = nl > 0 && (O.inc == 1 || O.inc == -1);
         const i64 from = unit_cover ? nl : 0;
         if (from < O.v->len) {
-            c->grp.open = false;
+            lbk_pdl::interrupt(c->pdl);
             CU(c, cudaMemcpyAsync(w + from, (const T *)O.v->ptr + from, sizeof(T) * (size_t)(O.v->len - from), cudaMemcpyDeviceToDevice, c->stream));
         }
         return LBK_OK;
@@ -1113,33 +1018,30 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid);
         if (s) return s;
         i64 nn = nl, ib = idx_base;
-        lbk_ctx::TriggerPredictor &tp = c->trig;
-        const int sl = lbk_ctx::TriggerPredictor::hash(rid, x, y);
-        lbk_ctx::TriggerPredictor::Slot &slot = tp.slot[sl];
-        if (slot.x != x || slot.y != y || slot.rid != rid) { slot.x = x; slot.y = y; slot.rid = rid; slot.late = false; }
-        int late_trigger = slot.late ? 1 : 0;
+        lbk_pdl::Op op;
+        op.reduction = true; op.rid = rid;
+        op.rd[0] = x; op.rdn[0] = nl * (i64)sizeof(T);
+        op.rd[1] = y; op.rdn[1] = y ? nl * (i64)sizeof(T) : 0;
+        op.nrd = 2;
+        op.wr[0] = out; op.wrn[0] = 8; op.nwr = 1;
+        const lbk_pdl::Plan plan = lbk_pdl::plan(c->pdl, op);
+        int late_trigger = plan.late ? 1 : 0;
         void *args[] = {(void *)&x, (void *)&y, (void *)&head, (void *)&nn, (void *)&ib, (void *)&c->partials, (void *)&c->ticket,
                         (void *)&fa, (void *)&late_trigger};
-        const void *rd[2] = {x, y};
-        const i64 rdn[2] = {nl * (i64)sizeof(T), y ? nl * (i64)sizeof(T) : 0};
-        const void *wr[1] = {out};
-        const i64 wrn[1] = {8};
-        // with the NCCL transport the all-gather and the finish kernel follow on the stream: no chain through them
-        const PdlMode mode = pdl_decide(c, rd, rdn, 2, wr, wrn, 1, true);
-        s = launch_stream_kernel(c, k, grid, threads, args, mode, rd, rdn, 2, wr, wrn, 1, true, late_trigger != 0);
+        s = launch_stream_kernel(c, k, grid, threads, args, op, plan);
         if (s) return s;
-        tp.pending = true; tp.pending_slot = sl;
-        if (exchange && !fused) c->grp.open = false;
+        // with the NCCL transport the all-gather and the finish kernel follow on the stream: no chain through them
+        if (exchange && !fused) lbk_pdl::interrupt(c->pdl);
     } else {
         const int threads = 256;
         const int grid = stream_grid(c, std::max<i64>(nl, 1), threads);
-        c->grp.open = false;
+        lbk_pdl::interrupt(c->pdl);
         lbk::reduce_strided_kernel<Op><<<grid, threads, 0, c->stream>>>(x, incx, first_index(nl, incx), y, incy,
                                                                           first_index(nl, incy), nl, idx_base, c->partials, c->ticket, fa);
         KERNEL_CHECK(c);
     }
     if (exchange && !fused) {
-        c->grp.open = false;
+        lbk_pdl::interrupt(c->pdl);
         NC(c, nccl_api()->AllGather(c->rec_send, c->rec_all, sizeof(Record), ncclChar, c->comm, c->stream));
         fa.mode = 0;
         lbk::finish_records_kernel<<<1, 32, 0, c->stream>>>(c->rec_all, c->nranks, fa);
@@ -1152,7 +1054,7 @@ template <class T>
 static int store_value(lbk_ctx *c, void *out, T v)
 {
     CU(c, cudaSetDevice(c->device));
-    c->grp.open = false;
+    lbk_pdl::interrupt(c->pdl);
     unsigned *flag = nullptr;
     if (out == c->result_dev) {
         if (++c->result_seq == 0) ++c->result_seq;
@@ -1303,7 +1205,7 @@ static int scal_common(lbk_ctx *c, const char *who, i64 n, T a, const lbk_vec *x
     }
     if (n_eff <= 0 && xout && xout->ptr != x->ptr) {      // nothing to scale: the pure result is a copy
         if (xout->ctx != c || xout->len != x->len || xout->dtype != x->dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
-        if (x->len) { c->grp.open = false; CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, (size_t)esz(x->dtype) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream)); }
+        if (x->len) { lbk_pdl::interrupt(c->pdl); CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, (size_t)esz(x->dtype) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream)); }
         return LBK_OK;
     }
     return map_entry(c, who, R_SCAL, lbk::ScalF<T>{a}, n_eff, x, inc_eff, nullptr, 1, xout, nullptr);
@@ -1323,7 +1225,7 @@ static int rotm_common(lbk_ctx *c, const char *who, i64 n, const lbk_vec *x, i64
         for (int i = 0; i < 2; ++i)
             if (dst[i] && src[i] && dst[i]->ptr != src[i]->ptr && src[i]->len) {
                 if (dst[i]->len != src[i]->len || dst[i]->dtype != src[i]->dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
-                c->grp.open = false;
+                lbk_pdl::interrupt(c->pdl);
                 CU(c, cudaMemcpyAsync(dst[i]->ptr, src[i]->ptr, (size_t)esz(src[i]->dtype) * (size_t)src[i]->len, cudaMemcpyDeviceToDevice, c->stream));
             }
         return LBK_OK;
@@ -1384,3 +1286,50 @@ extern "C" int lbk_combine_records(int kind, int is_f64, const lbk_record *recs,
     *fout = is_f64 ? v : (double)(float)v;
     return LBK_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// the launch planner of lbk_pdl.hpp on its own (no device needed): tests/test_pdl_plan.py
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbk_pdl_sim_create(void **sim)
+{
+    if (!sim) return fail(nullptr, LBK_ERR_ARG, "lbk_pdl_sim_create: null out pointer");
+    *sim = new (std::nothrow) lbk_pdl::State();
+    return *sim ? LBK_OK : fail(nullptr, LBK_ERR_NOMEM, "out of host memory");
+}
+extern "C" int lbk_pdl_sim_destroy(void *sim)
+{
+    delete static_cast<lbk_pdl::State *>(sim);
+    return LBK_OK;
+}
+extern "C" int lbk_pdl_sim_enable(void *sim, int enabled)
+{
+    if (!sim) return fail(nullptr, LBK_ERR_ARG, "lbk_pdl_sim_enable: null simulator");
+    static_cast<lbk_pdl::State *>(sim)->enabled = enabled != 0;
+    return LBK_OK;
+}
+extern "C" int lbk_pdl_sim_interrupt(void *sim)
+{
+    if (!sim) return fail(nullptr, LBK_ERR_ARG, "lbk_pdl_sim_interrupt: null simulator");
+    lbk_pdl::interrupt(*static_cast<lbk_pdl::State *>(sim));
+    return LBK_OK;
+}
+// rd / wr: (address, bytes) pairs of what the kernel reads / writes; mode: 0 ordinary launch, 1 PDL with the
+// wait at exit, 2 PDL with the wait before the first store; late: a reduction releases its dependents late
+extern "C" int lbk_pdl_sim_op(void *sim, int reduction, int rid, const int64_t *rd, int nrd, const int64_t *wr, int nwr,
+                              int *mode, int *late)
+{
+    if (!sim || nrd < 0 || nrd > 2 || nwr < 0 || nwr > 2 || (nrd && !rd) || (nwr && !wr) || !mode || !late)
+        return fail(nullptr, LBK_ERR_ARG, "lbk_pdl_sim_op: bad argument");
+    lbk_pdl::State &st = *static_cast<lbk_pdl::State *>(sim);
+    lbk_pdl::Op op;
+    op.reduction = reduction != 0; op.rid = rid;
+    op.nrd = nrd; op.nwr = nwr;
+    for (int i = 0; i < nrd; ++i) { op.rd[i] = reinterpret_cast<const void *>((uintptr_t)rd[2 * i]); op.rdn[i] = rd[2 * i + 1]; }
+    for (int i = 0; i < nwr; ++i) { op.wr[i] = reinterpret_cast<const void *>((uintptr_t)wr[2 * i]); op.wrn[i] = wr[2 * i + 1]; }
+    const lbk_pdl::Plan plan = lbk_pdl::plan(st, op);
+    lbk_pdl::commit(st, op, plan);
+    *mode = (int)plan.mode;
+    *late = plan.late ? 1 : 0;
+    return LBK_OK;
+}
+
