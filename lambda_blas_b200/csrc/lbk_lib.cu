@@ -302,6 +302,7 @@ extern "C" int lbk_set_pdl(lbk_ctx *c, int enabled)
 {
     if (!c) return fail(c, LBK_ERR_ARG, "lbk_set_pdl: null context");
     c->pdl.enabled = enabled != 0;
+    c->pdl.hold_stores = enabled != 2;      // 2: overlap only independent kernels (tools/, experiments)
     return LBK_OK;
 }
 

@@ -59,6 +59,7 @@ struct Plan {
 
 struct State {
     bool enabled = true;
+    bool hold_stores = true;         // false: an anti/output dependency gets an ordinary launch instead (experiments)
     Group grp;
     // the predictor: did the kernel that followed this call last time collide with it or its chain?
     static constexpr int kSlots = 64;
@@ -119,6 +120,7 @@ inline Plan plan(State &s, const Op &op)
         s.pending = false;
     }
     p.mode = s.enabled ? decide(s.grp, op) : NONE;
+    if (p.mode == WAIT_BEFORE_STORE && !s.hold_stores) p.mode = NONE;
     if (op.reduction) {
         p.slot = slot_of(op.rid, op.rd[0], op.rd[1]);
         State::Slot &sl = s.slot[p.slot];

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="Float or Double instance (same bytes: n is halved for f64)")
     a = ap.parse_args()
     ctx = lb.Context(0)
+    if os.environ.get("LBK_PDL"):
+        lb._ffi.check(lb._ffi.lib().lbk_set_pdl(ctx.handle, int(os.environ["LBK_PDL"])), ctx.handle)
     import numpy as np
     dt = np.float64 if a.dtype == "f64" else np.float32
     esz = 8 if a.dtype == "f64" else 4
