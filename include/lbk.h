@@ -51,7 +51,7 @@ enum lbk_status {
     LBK_ERR_ARG = 3,         /* null handle / pointer, negative length, handle of another context */
     LBK_ERR_RANGE = 4,       /* 1+(n-1)|inc| exceeds the vector (reference: undefined behaviour) */
     LBK_ERR_ALIAS = 5,       /* the two operands overlap in a way an in-place parallel update cannot honour */
-    LBK_ERR_UNSUPPORTED = 6, /* e.g. non-unit increment on a sharded vector */
+    LBK_ERR_UNSUPPORTED = 6, /* e.g. a negative, zero or unequal increment on sharded vectors */
     LBK_ERR_NOMEM = 7
 };
 
@@ -99,6 +99,11 @@ int lbk_comm_transport(lbk_ctx *ctx, int *fused);
 int lbk_set_fused_exchange(lbk_ctx *ctx, int enabled);
 /* Block partition of [0, global_len) used by lbk_vec_alloc_sharded: rank r owns [lo, hi). */
 int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t *lo, int64_t *hi);
+/* Sharded vectors take positive increments: logical element i of a call (n, inc) sits at global position i*inc.
+ * Which of them rank r holds: the first one, how many, and the offset of the first inside r's block.  (Two
+ * operands must have equal lengths and equal increments, so that every pairing stays on one rank; negative and
+ * zero increments on shards are LBK_ERR_UNSUPPORTED.) */
+int lbk_shard_span(int64_t global_len, int nranks, int rank, int64_t n, int64_t inc, int64_t *first, int64_t *count, int64_t *offset);
 
 /* ---- device vectors (the representation added beside Numerical.BLAS.Types, Types.hs:3) -----
  * The reference's routines are polymorphic with Float and Double instances (sdot/ddot, ..., Single.hs:83-87);

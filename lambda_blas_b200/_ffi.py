@@ -51,6 +51,7 @@ PROTOTYPES = {
     "lbk_comm_transport": (_int, [_vp, _pint]),
     "lbk_set_fused_exchange": (_int, [_vp, _int]),
     "lbk_shard_range": (_int, [_i64, _int, _int, _pi64, _pi64]),
+    "lbk_shard_span": (_int, [_i64, _int, _int, _i64, _i64, _pi64, _pi64, _pi64]),
     "lbk_vec_alloc": (_int, [_vp, _i64, _pvp]),
     "lbk_vec_alloc_f64": (_int, [_vp, _i64, _pvp]),
     "lbk_vec_alloc_sharded": (_int, [_vp, _i64, _pvp]),

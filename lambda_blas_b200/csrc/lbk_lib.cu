@@ -628,7 +628,33 @@ struct Operand {
     i64 inc;
     i64 n_local;   // logical elements of this call that live on this rank
     i64 i0;        // first logical element on this rank (0 unless sharded)
+    i64 base;      // where that element sits in this rank's buffer (0 unless sharded with an increment > 1)
+    const char *ptr() const { return v->ptr + base * (v->dtype ? 8 : 4); }
 };
+
+// Which logical elements i in [0, n), sitting at global positions i*inc (inc >= 1), fall into the block
+// [lo, hi) of positions: i0 = the first one, count of them, and where the first one sits inside the block.
+static void shard_span(i64 lo, i64 hi, i64 n, i64 inc, i64 *i0, i64 *count, i64 *base)
+{
+    const i64 i_lo = (lo + inc - 1) / inc, i_hi = std::min<i64>(n, (hi + inc - 1) / inc);
+    *count = i_hi > i_lo ? i_hi - i_lo : 0;
+    *i0 = i_lo;
+    *base = *count > 0 ? i_lo * inc - lo : 0;
+}
+
+extern "C" int lbk_shard_span(int64_t global_len, int nranks, int rank, int64_t n, int64_t inc,
+                              int64_t *first, int64_t *count, int64_t *offset)
+{
+    int64_t lo, hi;
+    int s = lbk_shard_range(global_len, nranks, rank, &lo, &hi);
+    if (s) return s;
+    if (n < 0 || inc < 1 || !first || !count || !offset) return fail(nullptr, LBK_ERR_ARG, "lbk_shard_span: bad argument");
+    if (n > 0 && 1 + (n - 1) * inc > global_len) return fail(nullptr, LBK_ERR_RANGE, "lbk_shard_span: 1+(n-1)*inc exceeds the vector");
+    i64 a = 0, b = 0, c2 = 0;
+    if (n > 0) shard_span(lo, hi, n, inc, &a, &b, &c2);
+    *first = a; *count = b; *offset = c2;
+    return LBK_OK;
+}
 
 // Validates one operand for a call over n logical elements and resolves sharding.
 static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, int dtype, i64 inc, i64 n, Operand *op)
@@ -636,14 +662,15 @@ static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, int dtyp
     if (!v) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
     if (v->ctx != c) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
     if (v->dtype != dtype) return fail(c, LBK_ERR_ARG, std::string(who) + (dtype ? ": needs a double-precision vector" : ": needs a single-precision vector"));
-    op->v = v; op->inc = inc; op->i0 = 0; op->n_local = n;
+    op->v = v; op->inc = inc; op->i0 = 0; op->n_local = n; op->base = 0;
     if (n <= 0) { op->n_local = 0; return LBK_OK; }
     if (v->sharded) {
-        if (inc != 1) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take unit increments only");
-        if (n > v->global_len) return fail(c, LBK_ERR_RANGE, std::string(who) + ": n exceeds the vector");
-        const i64 lo = v->shard_off, hi = std::min<i64>(n, v->shard_off + v->len);
-        op->n_local = hi > lo ? hi - lo : 0;
-        op->i0 = lo;
+        // Logical element i sits at global position i*inc; this rank holds positions [lo, hi).  Positive increments
+        // keep every pairing on one rank as long as both operands are partitioned alike (checked by the caller);
+        // negative ones pair x[i] with y[n-1-i] across devices and zero replicates one rank's element: refused.
+        if (inc < 1) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take positive increments only");
+        if (1 + (n - 1) * inc > v->global_len) return fail(c, LBK_ERR_RANGE, std::string(who) + ": 1+(n-1)*inc exceeds the vector");
+        shard_span(v->shard_off, v->shard_off + v->len, n, inc, &op->i0, &op->n_local, &op->base);
         return LBK_OK;
     }
     const i64 span = 1 + (n - 1) * iabs64(inc);
@@ -655,8 +682,8 @@ static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, int dtyp
 static void touched(const Operand &o, const char **lo, const char **hi)
 {
     const i64 n = o.n_local;
-    *lo = o.v->ptr;
-    *hi = o.v->ptr + (n > 0 ? 1 + (n - 1) * iabs64(o.inc) : 0) * esz(o.v->dtype);
+    *lo = o.ptr();
+    *hi = o.ptr() + (n > 0 ? 1 + (n - 1) * iabs64(o.inc) : 0) * esz(o.v->dtype);
 }
 template <class T> static inline int misalign(const T *p, int vec) { return (int)(((uintptr_t)p / sizeof(T)) % (uintptr_t)vec); }
 // elements per access of a variant for element type T: the table is in floats (4/16/32 bytes)
@@ -853,8 +880,10 @@ static int map_dispatch(lbk_ctx *c, int rid, const F &f, i64 n, const Operand &X
     if (n <= 0) return LBK_OK;
     CU(c, cudaSetDevice(c->device));
     const bool use_x = F::RX || F::WX, use_y = F::RY || F::WY;
-    const T *xr = use_x ? (const T *)X.v->ptr : nullptr;
-    const T *yr = use_y ? (const T *)Y.v->ptr : nullptr;
+    const T *xr = use_x ? (const T *)X.ptr() : nullptr;
+    const T *yr = use_y ? (const T *)Y.ptr() : nullptr;
+    if (xw) xw += X.base;       // the destinations are laid out like their sources
+    if (yw) yw += Y.base;
     const i64 incx = use_x ? X.inc : 1, incy = use_y ? Y.inc : 1;
     const i64 nl = use_x ? X.n_local : Y.n_local;   // sharded operands agree (checked by the caller)
     if (nl <= 0) return LBK_OK;
@@ -896,8 +925,8 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
     int s;
     if (use_x && (s = check_operand(c, who, x, dtype, incx, n, &X))) return s;
     if (use_y && (s = check_operand(c, who, y, dtype, incy, n, &Y))) return s;
-    if (use_x && use_y && (x->sharded != y->sharded || (x->sharded && (x->global_len != y->global_len))))
-        return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": operands must be sharded alike");
+    if (use_x && use_y && (x->sharded != y->sharded || (x->sharded && (x->global_len != y->global_len || (n > 0 && incx != incy)))))
+        return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded operands need equal lengths and equal increments");
     T *xw = nullptr, *yw = nullptr;
     if (F::WX) {
         lbk_vec *d = xo ? xo : const_cast<lbk_vec *>(x);
@@ -916,8 +945,8 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
         if (use_x) touched(X, &xl, &xh);
         if (use_y) touched(Y, &yl, &yh);
         auto hits = [](const char *al, const char *ah, const char *bl, const char *bh) { return al && bl && al < bh && bl < ah; };
-        const char *xwl = (const char *)xw, *xwh = xwl ? xwl + (xh - xl) : nullptr;
-        const char *ywl = (const char *)yw, *ywh = ywl ? ywl + (yh - yl) : nullptr;
+        const char *xwl = xw ? (const char *)(xw + X.base) : nullptr, *xwh = xwl ? xwl + (xh - xl) : nullptr;   // laid out like the sources
+        const char *ywl = yw ? (const char *)(yw + Y.base) : nullptr, *ywh = ywl ? ywl + (yh - yl) : nullptr;
         bool bad = false;
         if (F::WX) bad = bad || hits(xwl, xwh, yl, yh) || (xwl != xl && hits(xwl, xwh, xl, xh)) || (F::WY && hits(xwl, xwh, ywl, ywh));
         if (F::WY) bad = bad || hits(ywl, ywh, xl, xh) || (ywl != yl && hits(ywl, ywh, yl, yh));
@@ -973,7 +1002,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
     const bool exchange = c->nranks > 1 && X.v->sharded;
     const bool fused = exchange && c->fused_exchange;
     const i64 nl = X.n_local;
-    const T *x = (const T *)X.v->ptr, *y = Y ? (const T *)Y->v->ptr : nullptr;
+    const T *x = (const T *)X.ptr(), *y = Y ? (const T *)Y->ptr() : nullptr;
     const i64 incx = X.inc, incy = Y ? Y->inc : 1;
     FinishArgs fa;
     memset(&fa, 0, sizeof fa);
@@ -1084,8 +1113,8 @@ static int dot_common(lbk_ctx *c, const char *who, int rid, int kind, i64 n, flo
     int s;
     if ((s = check_operand(c, who, x, dtype, incx, n, &X))) return s;
     if ((s = check_operand(c, who, y, dtype, incy, n, &Y))) return s;
-    if (x->sharded != y->sharded || (x->sharded && x->global_len != y->global_len))
-        return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": operands must be sharded alike");
+    if (x->sharded != y->sharded || (x->sharded && (x->global_len != y->global_len || (n > 0 && incx != incy))))
+        return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded operands need equal lengths and equal increments");
     if (n <= 0) return store_value<T>(c, out_dev, kind == 3 ? (T)sb : (T)0);       // Single.hs:81 (empty fold), :239
     if constexpr (sizeof(T) == 4) {
         if (kind == 3) return reduce_dispatch<lbk::DsdotOp>(c, rid, 3, n, X, &Y, (double)sb, out_dev);
@@ -1202,7 +1231,7 @@ static int scal_common(lbk_ctx *c, const char *who, i64 n, T a, const lbk_vec *x
     if (n > 0 && incx <= 0) {
         if (incx == 0 || n == 1) { n_eff = 1; inc_eff = 1; }
         else n_eff = 0;
-        if (x->sharded) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take unit increments only");
+        if (x->sharded) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take positive increments only");
     }
     if (n_eff <= 0 && xout && xout->ptr != x->ptr) {      // nothing to scale: the pure result is a copy
         if (xout->ctx != c || xout->len != x->len || xout->dtype != x->dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");

@@ -22,6 +22,14 @@ def shard_range(global_len: int, nranks: int, rank: int) -> Tuple[int, int]:
     return lo.value, hi.value
 
 
+def shard_span(global_len: int, nranks: int, rank: int, n: int, inc: int) -> Tuple[int, int, int]:
+    """Of the logical elements i in [0, n) at global positions i*inc (inc >= 1): (first, count, offset) of those in
+    rank's block, offset being where the first one sits inside the block."""
+    a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+    _ffi.check(_ffi.lib().lbk_shard_span(global_len, nranks, rank, n, inc, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
 def attach_torch_distributed(ctx: Context) -> Context:
     """Give `ctx` an NCCL communicator spanning the initialised torch.distributed world."""
     import torch.distributed as dist

@@ -141,3 +141,26 @@ def test_haskell_shim_binds_declared_symbols_with_matching_arity():
               "axpy_oop", "scal_oop", "copy_oop", "swap_oop", "rot_oop", "rotm_oop"):
         assert f"lbk_s{r}" in names and f"lbk_d{r}" in names, r
     assert {"lbk_isamax", "lbk_idamax", "lbk_sdsdot", "lbk_vec_alloc", "lbk_vec_alloc_f64", "lbk_vec_free"} <= names
+
+
+def test_shard_span_partitions_the_logical_range(blas):
+    """Positive increments on shards: the ranks' (first, count) tile [0, n) in rank order and every element's
+    position i*inc falls inside the owning rank's block at the reported offset."""
+    from lambda_blas_b200 import sharded
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        world = int(rng.integers(1, 9)); inc = int(rng.integers(1, 9)); n = int(rng.integers(0, 200))
+        glen = (1 + (n - 1) * inc if n else 0) + int(rng.integers(0, 20))
+        nxt = 0
+        for r in range(world):
+            lo, hi = sharded.shard_range(glen, world, r)
+            first, count, off = sharded.shard_span(glen, world, r, n, inc)
+            if count:
+                assert first == nxt and lo <= first * inc < hi and first * inc - lo == off
+                assert lo <= (first + count - 1) * inc < hi
+                nxt = first + count
+            else:
+                assert not any(lo <= i * inc < hi for i in range(n))
+        assert nxt == n
+    with pytest.raises(blas.LbkError):
+        sharded.shard_span(10, 2, 0, 5, 3)          # 1+(n-1)*inc exceeds the vector

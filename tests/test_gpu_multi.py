@@ -70,14 +70,31 @@ def _worker(rank, world, port, q):
         ok &= bool(torch.equal(lo_t, hi_t))
         # elementwise: no communication, shard by shard
         ip.saxpy_(n, 1.000123, x, 1, y, 1)
-        want = oracle.saxpy(n, 1.000123, hx, 1, hy, 1)[lo:hi]
-        ok &= np.array_equal(y.to_host().view(bits), want.view(bits))
-        # non-unit increments on shards are refused, not silently wrong
-        try:
-            lb.sdot(max(n // 2, 1), x, 2, y, 2)
-            ok &= (world == 1)
-        except lb.LbkError as e:
-            ok &= e.status == 6
+        want_full = oracle.saxpy(n, 1.000123, hx, 1, hy, 1)
+        ok &= np.array_equal(y.to_host().view(bits), want_full[lo:hi].view(bits))
+        # equal positive increments on shards: logical element i sits at global position i*inc, so every pairing
+        # stays on one rank (y has just been updated: hy follows)
+        hy = want_full
+        for inc in (2, 3, 7):
+            m = (n - 1) // inc + 1
+            prod = float(np.sum(np.abs(hx[::inc][:m].astype(np.float64) * hy[::inc][:m])))
+            ok &= abs(float(lb.sdot(m, x, inc, y, inc)) - float(oracle.sdot(m, hx, inc, hy, inc))) <= 2 * m * u * prod
+            ok &= abs(float(lb.snrm2(m, x, inc)) - float(oracle.snrm2(m, hx, inc))) <= 2 * m * u * float(oracle.snrm2(m, hx, inc))
+            ok &= abs(float(lb.sasum(m, x, inc)) - float(oracle.sasum(m, hx, inc))) <= 2 * m * u * float(np.sum(np.abs(hx[::inc][:m])))
+            ok &= lb.isamax(m, x, inc) == oracle.isamax(m, hx, inc)
+            y2 = y.clone()
+            ip.saxpy_(m, -0.75, x, inc, y2, inc)
+            ok &= np.array_equal(y2.to_host().view(bits), oracle.saxpy(m, -0.75, hx, inc, hy, inc)[lo:hi].view(bits))
+            x2, y3 = lb.srot(m, x, inc, y, inc, np.cos(0.3), np.sin(0.3))          # the pure form: new sharded vectors
+            wx, wy = oracle.srot(m, hx, inc, hy, inc, np.cos(0.3), np.sin(0.3))
+            ok &= np.array_equal(x2.to_host().view(bits), wx[lo:hi].view(bits)) and np.array_equal(y3.to_host().view(bits), wy[lo:hi].view(bits))
+        # what would pair elements across devices is refused, not silently wrong
+        for incx, incy in ((2, 3), (-1, -1), (1, -1), (0, 1)):
+            try:
+                lb.sdot(max(n // 4, 1), x, incx, y, incy)
+                ok &= (world == 1)
+            except lb.LbkError as e:
+                ok &= e.status == 6
         notes.append((n, fused, np.dtype(dt).name, bool(ok)))
     notes.append(("fused_available", fused_available))
     t = torch.tensor([1 if ok else 0], device="cuda")
