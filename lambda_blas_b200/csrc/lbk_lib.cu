@@ -44,8 +44,8 @@ constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
 
 // launch shapes are per routine and shared by the Float and Double instances (they are in bytes per access)
-enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_FILL, R_MAPSTRIDED, R_COUNT };
-static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm", "fill", "mapstrided"};
+enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_FILL, R_MAPSTRIDED, R_REDSTRIDED, R_COUNT };
+static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm", "fill", "mapstrided", "redstrided"};
 struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
 // Defaults from the n = 2^28 sweeps on B200 (profiles/r01_tune_*.csv; tools/tune.py), reductions tuned
 // with their tails overlapped (PDL).  blocks_per_sm 0 = one resident wave (occupancy x SMs); larger
@@ -60,6 +60,7 @@ static const LaunchCfg kDefaultCfg[R_COUNT] = {
     /* rot  */ {22, 256, kOneTilePerBlock},  /* rotm */ {22, 256, kOneTilePerBlock},  /* fill */ {4, 256, 256},
     /* the general-stride map kernel: variant 0/1 = without/with the load fence (no measurable effect
        there); threads / blocks_per_sm 0 = chosen from the increments in launch_map_strided */ {0, 0, 0},
+    /* the general-stride reduce kernel: threads (<= 256) and blocks per SM of its grid-stride loop (0: from the increments) */ {0, 256, 0},
 };
 
 constexpr int kMaxGrid = 148 * 32 * 2;   // partial-record scratch (blocks)
@@ -1063,8 +1064,13 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         // with the NCCL transport the all-gather and the finish kernel follow on the stream: no chain through them
         if (exchange && !fused) lbk_pdl::interrupt(c->pdl);
     } else {
-        const int threads = 256;
-        const int grid = stream_grid(c, std::max<i64>(nl, 1), threads);
+        const LaunchCfg &scfg = c->cfg[R_REDSTRIDED];
+        const int threads = (scfg.threads > 0 && scfg.threads <= 256) ? scfg.threads : 256;
+        // config-4 sweep (profiles/r01_strided_launch_sweep.md): 8 blocks of 256 per SM for increments of 1-2,
+        // 32 when an increment of 4 or more puts every element in its own sector
+        const bool wide = std::max(iabs64(incx), Y ? iabs64(incy) : 0) >= 4;
+        const i64 cap = (i64)c->sms * (scfg.blocks_per_sm > 0 ? scfg.blocks_per_sm : (wide ? 32 : 8));
+        const int grid = (int)std::max<i64>(1, std::min<i64>(std::min<i64>((std::max<i64>(nl, 1) + threads - 1) / threads, cap), kMaxGrid));
         lbk_pdl::interrupt(c->pdl);
         lbk::reduce_strided_kernel<Op><<<grid, threads, 0, c->stream>>>(x, incx, first_index(nl, incx), y, incy,
                                                                           first_index(nl, incy), nl, idx_base, c->partials, c->ticket, fa);

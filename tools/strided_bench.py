@@ -21,7 +21,8 @@ x, y, out = ctx.alloc(span).fill_hash(1), ctx.alloc(span).fill_hash(2), ctx.allo
 c, s = math.cos(0.3), math.sin(0.3)
 B = {"sdot": 8, "saxpy": 12, "srot": 16}
 print("routine,incx,incy,us,GBps_algorithmic")
-for r in ("sdot", "saxpy", "srot"):
+ROUTINES = os.environ.get("ROUTINES", "sdot,saxpy,srot").split(",")
+for r in ROUTINES:
     for incx in incs:
         for incy in incs:
             f = {"sdot": lambda: ip.sdot_async(n, x, incx, y, incy, out),
