@@ -78,7 +78,7 @@ int lbk_launch_count(lbk_ctx *ctx, int64_t *launches);
 /* Programmatic dependent launch (on by default): consecutive unit-stride kernels overlap at their boundary --
  * the next kernel fills SMs while the previous one's last blocks (and a reduction's latency-bound tail)
  * drain.  The library tracks what the kernels still in flight read and write and launches the next one
- * the ordinary way, or makes it hold its stores, whenever the two depend on each other,
+ * holding its stores, or its loads, whenever the two depend on each other,
  * so results are unaffected.  lbk_pdl_count reports how many launches took that path. */
 int lbk_set_pdl(lbk_ctx *ctx, int enabled);
 int lbk_pdl_count(lbk_ctx *ctx, int64_t *launches);
@@ -239,7 +239,7 @@ int lbk_combine_records(int kind, int is_f64, const lbk_record *recs, int nranks
  * Feeds one unit-stride kernel at a time -- what it reads and writes as (address, bytes) pairs, whether it is a
  * reduction, its routine id -- to the planner the library uses (lambda_blas_b200/csrc/lbk_pdl.hpp) and reports
  * how it would be launched: mode 0 = ordinary launch, 1 = overlaps its predecessors, waits before it exits,
- * 2 = overlaps, but waits before its first store; late = 1: a reduction that releases its dependents only after
+ * 2 = overlaps, but waits before its first store, 3 = resident early, but waits before its first load; late = 1: a reduction that releases its dependents only after
  * its loads.  lbk_pdl_sim_interrupt = any other operation on the stream. */
 int lbk_pdl_sim_create(void **sim);
 int lbk_pdl_sim_destroy(void *sim);

@@ -279,10 +279,14 @@ __device__ __forceinline__ unsigned low_bits(double v) { return (unsigned)__doub
 template <class F, int VEC, int UNROLL, int POLICY, bool REV = false>
 __global__ void __launch_bounds__(kMaxThreads)
 map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr, typename F::Scalar *xw,
-                typename F::Scalar *yw, i64 head, i64 n, unsigned fence_mask, int wait_before_store)
+                typename F::Scalar *yw, i64 head, i64 n, unsigned fence_mask, int wait_mode)
 {
     using T = typename F::Scalar;
     constexpr bool FENCE = POLICY == 6 && (F::RX || F::RY);
+    // wait_mode (lbk_pdl.hpp): 0 wait for the predecessors only before exiting, 1 before the first store,
+    // 2 before the first load -- and in that case release the dependents only afterwards
+    const int wait_before_store = wait_mode == 1;
+    if (wait_mode == 2) pdl_wait();
     pdl_launch_dependents();
     const i64 body = n - head;
     const i64 npack = body / VEC;
@@ -853,7 +857,7 @@ __device__ __forceinline__ u64 apply_x0(typename Op::Partial &p, const FinishArg
 template <class Op, int VEC, int UNROLL, int POLICY, bool REV = false>
 __global__ void __launch_bounds__(kMaxThreads, reduce_min_blocks(VEC * UNROLL * (int)sizeof(typename Op::Scalar)))
 reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i64 head, i64 n, i64 idx_base,
-                   Record *partials, unsigned *ticket, FinishArgs fa, int late_trigger)
+                   Record *partials, unsigned *ticket, FinishArgs fa, int late_trigger, int wait_first)
 {
     using T = typename Op::Scalar;
     constexpr int YS = REV ? -1 : 1;     // REV: element i pairs x[i] with y[n-1-i] (see map_unit_kernel)
@@ -866,6 +870,7 @@ reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i
     // operands or with a kernel still running before it (lbk_lib.cu, TriggerPredictor): then each block releases
     // them after its last load AND after its predecessors have completed, so that the next kernel may read and
     // write anything but this kernel's result as soon as it runs, instead of being launched the ordinary way.
+    if (wait_first) pdl_wait();      // reads what a predecessor writes: an ordinary launch in effect, minus its latency
     if (!late_trigger) pdl_launch_dependents();
 
     typename Op::Acc acc = Op::zero();

@@ -303,7 +303,8 @@ extern "C" int lbk_set_pdl(lbk_ctx *c, int enabled)
 {
     if (!c) return fail(c, LBK_ERR_ARG, "lbk_set_pdl: null context");
     c->pdl.enabled = enabled != 0;
-    c->pdl.hold_stores = enabled != 2;      // 2: overlap only independent kernels (tools/, experiments)
+    c->pdl.hold_stores = enabled != 2 && enabled != 3;      // 2: dependent kernels (of any kind) wait before their first load
+    c->pdl.hold_loads = enabled != 3 && enabled != 4;       // 3: ... or get an ordinary launch; 4: only true dependencies do (tools/, experiments)
     return LBK_OK;
 }
 
@@ -828,9 +829,9 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
     if (F::WX) { op.wr[op.nwr] = xw; op.wrn[op.nwr++] = nb; }
     if (F::WY) { op.wr[op.nwr] = yw; op.wrn[op.nwr++] = nb; }
     const lbk_pdl::Plan plan = lbk_pdl::plan(c->pdl, op);
-    int wait_before_store = plan.mode == lbk_pdl::WAIT_BEFORE_STORE ? 1 : 0;
+    int wait_mode = plan.mode == lbk_pdl::WAIT_BEFORE_STORE ? 1 : plan.mode == lbk_pdl::WAIT_BEFORE_LOAD ? 2 : 0;
     void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n,
-                    (void *)&fence_mask, (void *)&wait_before_store};
+                    (void *)&fence_mask, (void *)&wait_mode};
     return launch_stream_kernel(c, k, grid, threads, args, op, plan);
 }
 
@@ -1056,9 +1057,9 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         op.nrd = 2;
         op.wr[0] = out; op.wrn[0] = 8; op.nwr = 1;
         const lbk_pdl::Plan plan = lbk_pdl::plan(c->pdl, op);
-        int late_trigger = plan.late ? 1 : 0;
+        int late_trigger = plan.late ? 1 : 0, wait_first = plan.mode == lbk_pdl::WAIT_BEFORE_LOAD ? 1 : 0;
         void *args[] = {(void *)&x, (void *)&y, (void *)&head, (void *)&nn, (void *)&ib, (void *)&c->partials, (void *)&c->ticket,
-                        (void *)&fa, (void *)&late_trigger};
+                        (void *)&fa, (void *)&late_trigger, (void *)&wait_first};
         s = launch_stream_kernel(c, k, grid, threads, args, op, plan);
         if (s) return s;
         // with the NCCL transport the all-gather and the finish kernel follow on the stream: no chain through them

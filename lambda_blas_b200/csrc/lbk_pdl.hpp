@@ -9,7 +9,10 @@
 // running when a kernel starts is the GROUP: the chain of PDL launches since the last ordinary launch (or
 // any other stream operation), with everything its members read and write.  A new kernel is planned
 // against the group:
-//   * it reads something the group writes          -> ordinary launch (true dependency);
+//   * it reads something the group writes          -> true dependency: PDL all the same, but the kernel
+//     executes griddepcontrol.wait before its first load and only then releases its own dependents --
+//     the semantics of an ordinary launch with the launch latency hidden (its blocks are resident and
+//     past their prologue when the predecessors finish);
 //   * it writes something the group reads or writes -> PDL, but it executes griddepcontrol.wait (all
 //     predecessors complete and visible) before its first store; its loads still overlap;
 //   * otherwise                                     -> PDL, griddepcontrol.wait only before it exits
@@ -28,7 +31,7 @@
 
 namespace lbk_pdl {
 
-enum Mode { NONE = 0, WAIT_AT_EXIT = 1, WAIT_BEFORE_STORE = 2 };
+enum Mode { NONE = 0, WAIT_AT_EXIT = 1, WAIT_BEFORE_STORE = 2, WAIT_BEFORE_LOAD = 3 };
 
 struct Range { const char *lo, *hi; };
 
@@ -59,7 +62,8 @@ struct Plan {
 
 struct State {
     bool enabled = true;
-    bool hold_stores = true;         // false: an anti/output dependency gets an ordinary launch instead (experiments)
+    bool hold_stores = true;         // false: an anti/output dependency is treated like a true one (experiments)
+    bool hold_loads = true;          // false: a true dependency gets an ordinary launch (experiments)
     Group grp;
     // the predictor: did the kernel that followed this call last time collide with it or its chain?
     static constexpr int kSlots = 64;
@@ -84,7 +88,7 @@ inline Mode decide(const Group &g, const Op &op)
 {
     if (!g.open) return NONE;
     for (int i = 0; i < op.nrd; ++i)
-        if (hits(g.w, g.nw, op.rd[i], op.rdn[i])) return NONE;               // reads what a predecessor writes
+        if (hits(g.w, g.nw, op.rd[i], op.rdn[i])) return WAIT_BEFORE_LOAD;   // reads what a predecessor writes
     if (op.reduction) return WAIT_AT_EXIT;
     for (int i = 0; i < op.nwr; ++i)
         if (hits(g.r, g.nr, op.wr[i], op.wrn[i]) || hits(g.w, g.nw, op.wr[i], op.wrn[i])) return WAIT_BEFORE_STORE;
@@ -120,7 +124,8 @@ inline Plan plan(State &s, const Op &op)
         s.pending = false;
     }
     p.mode = s.enabled ? decide(s.grp, op) : NONE;
-    if (p.mode == WAIT_BEFORE_STORE && !s.hold_stores) p.mode = NONE;
+    if (p.mode == WAIT_BEFORE_STORE && !s.hold_stores) p.mode = WAIT_BEFORE_LOAD;
+    if (p.mode == WAIT_BEFORE_LOAD && !s.hold_loads) p.mode = NONE;
     if (op.reduction) {
         p.slot = slot_of(op.rid, op.rd[0], op.rd[1]);
         State::Slot &sl = s.slot[p.slot];
@@ -134,7 +139,9 @@ inline Plan plan(State &s, const Op &op)
 inline void commit(State &s, const Op &op, const Plan &p)
 {
     Group &g = s.grp;
-    if (p.mode == NONE) { g.nr = g.nw = 0; }          // an ordinary launch starts after everything before it
+    // an ordinary launch, or one that waits before its first load and only then releases its dependents,
+    // starts (in effect) after everything before it
+    if (p.mode == NONE || p.mode == WAIT_BEFORE_LOAD) { g.nr = g.nw = 0; }
     bool full = false;
     if (op.reduction) {                                // the group had this reduction released its dependents at once
         Group &h = s.hyp;

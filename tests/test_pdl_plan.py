@@ -1,7 +1,8 @@
 """The launch planner (lambda_blas_b200/csrc/lbk_pdl.hpp) on the CPU: which consecutive kernels may overlap.
 
 Driven through lbk_pdl_sim_* (include/lbk.h): no device involved.  mode 0 = ordinary launch, 1 = programmatic
-dependent launch with the wait at exit, 2 = with the wait before the first store."""
+dependent launch with the wait for the predecessors at exit, 2 = before the first store, 3 = before the first load
+(a true dependency: ordinary-launch semantics with the launch latency hidden)."""
 import ctypes as C
 
 import pytest
@@ -51,11 +52,11 @@ def test_first_kernel_and_interrupts_are_ordinary(sim):
 
 def test_hazard_classes(sim):
     sim.op([X], [Y])                                # y = f(x)
-    assert sim.op([Y], [Z])[0] == 0                 # read after write: ordinary launch
+    assert sim.op([Y], [Z])[0] == 3                 # read after write: waits before its first load
     assert sim.op([X], [W])[0] == 1                 # reads x (only read so far), writes w: free
     assert sim.op([(X + 6 * N, N)], [X])[0] == 2    # write after read (x): hold the stores
     assert sim.op([(X + 6 * N, N)], [(X + N // 2, N)])[0] == 2   # write after write, partial overlap
-    assert sim.op([Z], [(Y + 6 * N, N)])[0] == 0    # z was written by a kernel of the chain: ordinary launch
+    assert sim.op([Z], [(Y + 6 * N, N)])[0] == 3    # z was written by a kernel of the chain
     assert sim.op([(X + 4 * N, N)], [(Y + 4 * N, N)])[0] == 1    # disjoint windows
 
 
@@ -63,13 +64,15 @@ def test_chain_is_checked_as_a_whole(sim):
     sim.op([X], [Y])                                # ordinary
     assert sim.op([Z], [W])[0] == 1                 # overlaps the first
     # the first kernel may still be running when a third starts: its write of y still counts
-    assert sim.op([Y], [(X + 8 * N, N)])[0] == 0
+    assert sim.op([Y], [(X + 8 * N, N)])[0] == 3
+    # ... and a kernel that waited before its first load restarts the chain: nothing older is in flight behind it
+    assert sim.op([W], [X])[0] == 1
 
 
 def test_reduction_reads_only(sim):
     sim.op([X], [Y])
     assert sim.red(NRM2, X)[0] == 1                 # reads what the map only read
-    assert sim.red(NRM2, Y)[0] == 0                 # reads what the map wrote
+    assert sim.red(NRM2, Y)[0] == 3                 # reads what the map wrote
     # a reduction writes its result after the wait: two reductions into the same slot still overlap
     assert sim.red(ASUM, X)[0] == 1
 
@@ -81,9 +84,9 @@ def test_predictor_learns_the_bench_step(sim):
         history.append((sim.red(DOT, X, Y), sim.op([X, Y], [Y]), sim.red(NRM2, X)))
     (d0, a0, n0), (d1, a1, n1) = history[0], history[1]
     assert d0 == (0, 0) and a0[0] == 2 and n0 == (1, 0)       # first pass: released at once, saxpy holds its stores
-    # second pass: sdot reads y that saxpy wrote and snrm2 was released at once -> ordinary launch, but both
-    # reductions have learnt to release late
-    assert d1 == (0, 1) and a1[0] == 1 and n1 == (1, 1)
+    # second pass: sdot reads y that saxpy wrote and snrm2 was released at once -> it waits before its first
+    # load, but both reductions have learnt to release late
+    assert d1 == (3, 1) and a1[0] == 1 and n1 == (1, 1)
     for d, a, n in history[2:]:
         assert d == (1, 1) and a[0] == 1 and n == (1, 1)       # steady state: all three overlap, no held stores
 
@@ -102,4 +105,4 @@ def test_full_table_ends_the_chain(sim):
 
 def test_disabled(sim):
     sim.L.lbk_pdl_sim_enable(sim.h, 0)
-    assert [sim.op([X], [Y])[0], sim.op([Z], [W])[0], sim.red(NRM2, X)[0]] == [0, 0, 0]
+    assert [sim.op([X], [Y])[0], sim.op([Z], [W])[0], sim.red(NRM2, X)[0], sim.op([Y], [Z])[0]] == [0, 0, 0, 0]
