@@ -45,18 +45,23 @@ int main()
             time_it("saxpy", "in place, enqueue only (lbk_saxpy)", n, [&] { ctx.check(lbk_saxpy(ctx.get(), n, 0.0f, x.get(), 1, y.get(), 1)); });
             ctx.sync();
         }
+        // what a pure result costs besides its kernel: one allocation and one release per call
+        for (long long n : {1024LL, 1LL << 20, 1LL << 24}) {
+            time_it("alloc+free", "lbk_vec_alloc + lbk_vec_free, stream busy (no sync)", n, [&] { DVector t(ctx, n); });
+            ctx.sync();
+            time_it("alloc+free", "lbk_vec_alloc + lbk_vec_free + lbk_sync", n, [&] { { DVector t(ctx, n); } ctx.sync(); });
+        }
         // Chains of DEPENDENT kernels (each call reads what the previous one wrote), enqueue only, one sync at the end:
         // microseconds per call.  pdl 0 = ordinary launches, 1 = the library's default (the next kernel is resident and
         // waits before its first load, so the launch latency is hidden).
         std::printf("chain,pdl,n,us_per_call\n");
-        const long long M = 1LL << 24;
-        DVector bx(ctx, M), by(ctx, M);
-        ctx.check(lbk_vec_fill(bx.get(), 0.25)); ctx.check(lbk_vec_fill(by.get(), 0.5));
         DVector res(ctx, 4);
         for (int pdl : {0, 1, 0, 1}) {
             ctx.check(lbk_set_pdl(ctx.get(), pdl));
             for (long long n : {1LL << 16, 1LL << 18, 1LL << 20, 1LL << 22, 1LL << 24}) {
                 const int K = 200;
+                DVector bx(ctx, n), by(ctx, n);
+                ctx.check(lbk_vec_fill(bx.get(), 0.25)); ctx.check(lbk_vec_fill(by.get(), 0.5));
                 auto run = [&](const char *name, const std::function<void()> &f) {
                     for (int i = 0; i < 20; ++i) f();
                     ctx.sync();
@@ -66,6 +71,7 @@ int main()
                     std::printf("%s,%d,%lld,%.2f\n", name, pdl, n, std::chrono::duration<double, std::micro>(clk::now() - t0).count() / K);
                 };
                 run("saxpy y+=a*x (in place)", [&] { ctx.check(lbk_saxpy(ctx.get(), n, 1e-3f, bx.get(), 1, by.get(), 1)); });
+                run("pure saxpy chain: w = saxpy(a, x, w), a new vector per call", [&] { by = saxpy(n, 1e-3f, bx, 1, by, 1); });
                 run("sscal then sdot_async", [&] { ctx.check(lbk_sscal(ctx.get(), n, 1.0f, bx.get(), 1));
                                                   ctx.check(lbk_sdot_async(ctx.get(), n, bx.get(), 1, by.get(), 1, res.get())); });
             }

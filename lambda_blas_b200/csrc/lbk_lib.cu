@@ -440,7 +440,8 @@ static int alloc_common(lbk_ctx *c, const char *who, i64 len, i64 glen, i64 off,
     CU(c, cudaSetDevice(c->device));
     void *p = nullptr;
     if (len > 0) {
-        lbk_pdl::interrupt(c->pdl);
+        // a stream-ordered allocation does not end the chain of overlapping kernels: hazards are tracked by address,
+        // so a block the pool hands out again while its previous user is still running is handled like any other
 #ifdef LBK_SYNC_MALLOC      // A/B builds only (profiles/r01_criterion_matrix*.csv): plain cudaMalloc / synchronise + cudaFree
         cudaError_t e = cudaMalloc(&p, (size_t)esz(dtype) * (size_t)len);
 #else
@@ -489,7 +490,6 @@ extern "C" int lbk_vec_free(lbk_vec *v)
     if (!v) return LBK_OK;
     if (v->owner && v->ptr) {      // released in stream order: everything enqueued so far may still use it
         cudaSetDevice(v->ctx->device);
-        lbk_pdl::interrupt(v->ctx->pdl);
 #ifdef LBK_SYNC_MALLOC
         cudaStreamSynchronize(v->ctx->stream);
         cudaFree(v->ptr);
