@@ -43,7 +43,7 @@ def run_sequence(blas, ctx, seed, pdl, dtype):
                 return a, b, m
 
     for step in range(48):
-        op = int(rng.integers(11))
+        op = int(rng.integers(13))
         slot = res.view(2 * int(rng.integers(30)), 2)
         if op == 0:
             a, b, m = two(); ip.sdot_async(m, a, 1, b, 1, slot)
@@ -65,8 +65,14 @@ def run_sequence(blas, ctx, seed, pdl, dtype):
             a, b, m = two(); ip.srot_(m, a, 1, b, 1, np.cos(0.3), np.sin(0.3))
         elif op == 9:
             a, b, m = two(); ip.saxpy_(m, 0.25, a, 1, b, -1)             # the reversed-pair kernel
-        else:
+        elif op == 10:
             a, m = window(); ip.sdot_async(m, a, 1, a, 1, slot)          # both operands the same vector
+        elif op == 11:                                                  # the pure forms: a NEW vector per call, the old one is
+            i, j = (int(v) for v in rng.choice(len(vecs), 2, replace=False))    # released in stream order and its block reused
+            vecs[j] = blas.saxpy(n, 0.125, vecs[i], 1, vecs[j], 1)
+        else:
+            j = int(rng.integers(len(vecs)))
+            vecs[j] = blas.sscal(n - 5, 0.75, vecs[j], 1)
     out = [v.to_host() for v in vecs] + [res.to_host()]
     return out, ctx.pdl_count() - before
 
