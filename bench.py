@@ -25,7 +25,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_ELEM = {"sdot": 8, "sasum": 4, "snrm2": 4, "isamax": 4, "saxpy": 12, "sscal": 8, "scopy": 8,
+BYTES_PER_ELEM = {"sdot": 8, "sdsdot": 8, "sasum": 4, "snrm2": 4, "isamax": 4, "saxpy": 12, "sscal": 8, "scopy": 8,
                   "sswap": 16, "srot": 16, "srotm": 16}
 STEP_ROUTINES = ("sdot", "saxpy", "snrm2")
 STEP_BYTES_PER_ELEM = sum(BYTES_PER_ELEM[r] for r in STEP_ROUTINES)   # 24
@@ -220,6 +220,7 @@ def run_ours(args) -> None:
         "sdot": lambda: ip.sdot_async(ng, x, 1, y, 1, res),
         "saxpy": lambda: ip.saxpy_(ng, SAXPY_A, x, 1, y, 1),
         "snrm2": lambda: ip.snrm2_async(ng, x, 1, res),
+        "sdsdot": lambda: ip.sdsdot_async(ng, 0.5, x, 1, y, 1, res),
         "sasum": lambda: ip.sasum_async(ng, x, 1, res),
         "isamax": lambda: ip.isamax_async(ng, x, 1, res),
         "sscal": lambda: ip.sscal_(ng, SAXPY_A, x, 1),
@@ -281,7 +282,7 @@ def run_ours(args) -> None:
 
     # ---- every routine alone (K launches back to back), for the per-routine table ----
     routines = {}
-    order = ["sdot", "saxpy", "snrm2", "sasum", "isamax", "sscal", "scopy", "sswap", "srot", "srotm"]
+    order = ["sdot", "saxpy", "snrm2", "sasum", "isamax", "sscal", "scopy", "sswap", "srot", "srotm", "sdsdot"]
     times = []
     for r in order:
         x.fill_hash(1); y.fill_hash(2)

@@ -154,6 +154,7 @@ int lbk_sdot(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_
 int lbk_ddot(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, double *out);
 /* sdsdot, Single.hs:231-262 ("sdsdot_", Foreign.hs:52): sb + sum in double, rounded once to float. */
 int lbk_sdsdot(lbk_ctx *ctx, int64_t n, float sb, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out);
+int lbk_sdsdot_async(lbk_ctx *ctx, int64_t n, float sb, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *out);
 /* asum / sasum / dasum, Single.hs:155-168 ("sasum_"/"dasum_", Foreign.hs:36,38): 0 when incx < 1. */
 int lbk_sasum(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, float *out);
 int lbk_dasum(lbk_ctx *ctx, int64_t n, const lbk_vec *x, int64_t incx, double *out);

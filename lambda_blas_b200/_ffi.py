@@ -78,6 +78,7 @@ PROTOTYPES = {
     "lbk_wait_event": (_int, [_vp, _vp]),
     "lbk_event_destroy": (_int, [_vp]),
     "lbk_sdsdot": (_int, [_vp, _i64, _f32, _vp, _i64, _vp, _i64, _pf32]),
+    "lbk_sdsdot_async": (_int, [_vp, _i64, _f32, _vp, _i64, _vp, _i64, _vp]),
     "lbk_srotg": (_int, [_f32, _f32, _pf32]),
     "lbk_drotg": (_int, [_f64, _f64, _pf64]),
     "lbk_srotmg": (_int, [_f32, _f32, _f32, _f32, _pf32, _pf32]),

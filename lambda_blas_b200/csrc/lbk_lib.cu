@@ -1224,6 +1224,13 @@ extern "C" int lbk_sdsdot(lbk_ctx *c, int64_t n, float sb, const lbk_vec *x, int
     return finish_sync(c, dot_common<float>(c, "lbk_sdsdot", R_SDSDOT, 3, n, sb, x, incx, y, incy, c->result_dev), out);
 }
 
+extern "C" int lbk_sdsdot_async(lbk_ctx *c, int64_t n, float sb, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *o)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_sdsdot_async: null context");
+    int s = check_out_vec(c, "lbk_sdsdot_async", o, 0, sizeof(float));
+    return s ? s : dot_common<float>(c, "lbk_sdsdot_async", R_SDSDOT, 3, n, sb, x, incx, y, incy, o->ptr);
+}
+
 // ------------------------------------------------------------------------------------------------
 // elementwise entry points
 // ------------------------------------------------------------------------------------------------

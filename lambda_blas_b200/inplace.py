@@ -61,6 +61,10 @@ def sdot_async(n: int, x: DVector, incx: int, y: DVector, incy: int, out: DVecto
     _ffi.check(_fn(x, "dot_async")(x.ctx.handle, n, x.handle, incx, y.handle, incy, out.handle), x.ctx.handle)
 
 
+def sdsdot_async(n: int, sb, x: DVector, incx: int, y: DVector, incy: int, out: DVector) -> None:
+    _ffi.check(_L().lbk_sdsdot_async(x.ctx.handle, n, float(np.float32(sb)), x.handle, incx, y.handle, incy, out.handle), x.ctx.handle)
+
+
 def sasum_async(n: int, x: DVector, incx: int, out: DVector) -> None:
     _ffi.check(_fn(x, "asum_async")(x.ctx.handle, n, x.handle, incx, out.handle), x.ctx.handle)
 

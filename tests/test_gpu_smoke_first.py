@@ -192,3 +192,18 @@ def test_guard_bands_stay_untouched(blas, ctx, oracle, n, incs, dtype):
         assert np.all(gx[:G] == sent) and np.all(gx[G + lx:] == sent), (name, "x guard")
         assert np.all(gy[:G] == sent) and np.all(gy[G + ly:] == sent), (name, "y guard")
         P.assert_same(gx[G:G + lx], wx, name); P.assert_same(gy[G:G + ly], wy, name)
+
+
+def test_sdsdot_async_matches_the_blocking_call(blas, ctx, oracle):
+    """lbk_sdsdot_async (result left on the device) and lbk_sdsdot (Single.hs:231-262) are the same reduction."""
+    from lambda_blas_b200 import inplace as ip
+    rng = np.random.default_rng(5)
+    n = 123457
+    hx, hy = gen_unit(rng, n), gen_unit(rng, n)
+    x, y, r = ctx.to_device(hx), ctx.to_device(hy), ctx.alloc(4)
+    for incx, incy, m in ((1, 1, n), (2, -3, n // 3), (-1, 1, n)):
+        ip.sdsdot_async(m, 0.625, x, incx, y, incy, r)
+        got = r.to_host()[:1]
+        P.assert_same(got, np.array([blas.sdsdot(m, 0.625, x, incx, y, incy)], dtype=np.float32))
+        want = float(oracle.sdsdot(m, 0.625, hx, incx, hy, incy))
+        assert abs(float(got[0]) - want) <= 2.0 ** -23 * abs(want) + 1e-30       # double accumulation: one float rounding

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lambda_blas_b200 as lb  # noqa: E402
 from lambda_blas_b200 import inplace as ip  # noqa: E402
 
-BYTES = {"sdot": 8, "sasum": 4, "snrm2": 4, "isamax": 4, "saxpy": 12, "sscal": 8, "scopy": 8, "sswap": 16, "srot": 16, "srotm": 16, "fill": 4}
+BYTES = {"sdot": 8, "sdsdot": 8, "sasum": 4, "snrm2": 4, "isamax": 4, "saxpy": 12, "sscal": 8, "scopy": 8, "sswap": 16, "srot": 16, "srotm": 16, "fill": 4}
 
 
 def main():
@@ -39,6 +39,7 @@ def main():
     calls = {
         "sdot": lambda: ip.sdot_async(n, x, 1, y, 1, out),
         "sasum": lambda: ip.sasum_async(n, x, 1, out),
+        "sdsdot": lambda: ip.sdsdot_async(n, 0.5, x, 1, y, 1, out),
         "snrm2": lambda: ip.snrm2_async(n, x, 1, out),
         "isamax": lambda: ip.isamax_async(n, x, 1, out),
         "saxpy": lambda: ip.saxpy_(n, 1.000123, x, 1, y, 1),
