@@ -170,6 +170,10 @@ static int fail(lbk_ctx *ctx, int code, const std::string &msg)
     } while (0)
 
 static inline i64 first_index(i64 n, i64 inc) { return inc > 0 ? 0 : (1 - n) * inc; }   // Single.hs:91-96
+
+// Device-to-device copy of whole elements on the context's stream with the copy kernel (scopy's): faster than
+// cudaMemcpyAsync on this part (7.0 vs 6.4 TB/s) and, unlike it, a member of the chain of overlapping kernels.
+static int device_copy(lbk_ctx *c, void *dst, const void *src, i64 count, int dtype);
 static inline i64 iabs64(i64 v) { return v < 0 ? -v : v; }
 
 // ------------------------------------------------------------------------------------------------
@@ -543,9 +547,8 @@ extern "C" int lbk_vec_clone(const lbk_vec *v, lbk_vec **out)
     if (s) return s;
     w->global_len = v->global_len; w->shard_off = v->shard_off; w->sharded = v->sharded;
     if (v->len) {
-        lbk_pdl::interrupt(v->ctx->pdl);
-        cudaError_t e = cudaMemcpyAsync(w->ptr, v->ptr, (size_t)esz(v->dtype) * (size_t)v->len, cudaMemcpyDeviceToDevice, v->ctx->stream);
-        if (e != cudaSuccess) { lbk_vec_free(w); return fail(v->ctx, LBK_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e)); }
+        s = device_copy(v->ctx, w->ptr, v->ptr, v->len, v->dtype);
+        if (s) { lbk_vec_free(w); return s; }
     }
     *out = w;
     return LBK_OK;
@@ -845,6 +848,14 @@ extern "C" int lbk_vec_fill(lbk_vec *v, double value)
     return launch_map_unit(c, R_FILL, lbk::FillF<float>{(float)value}, (const float *)nullptr, (const float *)nullptr, (float *)v->ptr, (float *)nullptr, v->len);
 }
 
+static int device_copy(lbk_ctx *c, void *dst, const void *src, i64 count, int dtype)
+{
+    if (count <= 0) return LBK_OK;
+    CU(c, cudaSetDevice(c->device));
+    if (dtype) return launch_map_unit(c, R_COPY, lbk::CopyF<double>{}, (const double *)src, (const double *)nullptr, (double *)nullptr, (double *)dst, count);
+    return launch_map_unit(c, R_COPY, lbk::CopyF<float>{}, (const float *)src, (const float *)nullptr, (float *)nullptr, (float *)dst, count);
+}
+
 template <class F>
 static int launch_map_strided(lbk_ctx *c, const F &f, const typename F::Scalar *xr, typename F::Scalar *xw, i64 incx_r, i64 incx_w,
                               i64 kx0_r, i64 kx0_w, const typename F::Scalar *yr, typename F::Scalar *yw, i64 incy_r, i64 incy_w,
@@ -962,10 +973,7 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
         const i64 nl = n > 0 ? O.n_local : 0;
         const bool unit_cover = nl > 0 && (O.inc == 1 || O.inc == -1);
         const i64 from = unit_cover ? nl : 0;
-        if (from < O.v->len) {
-            lbk_pdl::interrupt(c->pdl);
-            CU(c, cudaMemcpyAsync(w + from, (const T *)O.v->ptr + from, sizeof(T) * (size_t)(O.v->len - from), cudaMemcpyDeviceToDevice, c->stream));
-        }
+        if (from < O.v->len) return device_copy(c, w + from, (const T *)O.v->ptr + from, O.v->len - from, dtype);
         return LBK_OK;
     };
     if ((s = prepare(X, xw, F::WX))) return s;
@@ -1249,8 +1257,7 @@ static int scal_common(lbk_ctx *c, const char *who, i64 n, T a, const lbk_vec *x
     }
     if (n_eff <= 0 && xout && xout->ptr != x->ptr) {      // nothing to scale: the pure result is a copy
         if (xout->ctx != c || xout->len != x->len || xout->dtype != x->dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
-        if (x->len) { lbk_pdl::interrupt(c->pdl); CU(c, cudaMemcpyAsync(xout->ptr, x->ptr, (size_t)esz(x->dtype) * (size_t)x->len, cudaMemcpyDeviceToDevice, c->stream)); }
-        return LBK_OK;
+        return x->len ? device_copy(c, xout->ptr, x->ptr, x->len, x->dtype) : LBK_OK;
     }
     return map_entry(c, who, R_SCAL, lbk::ScalF<T>{a}, n_eff, x, inc_eff, nullptr, 1, xout, nullptr);
 }
@@ -1269,8 +1276,8 @@ static int rotm_common(lbk_ctx *c, const char *who, i64 n, const lbk_vec *x, i64
         for (int i = 0; i < 2; ++i)
             if (dst[i] && src[i] && dst[i]->ptr != src[i]->ptr && src[i]->len) {
                 if (dst[i]->len != src[i]->len || dst[i]->dtype != src[i]->dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
-                lbk_pdl::interrupt(c->pdl);
-                CU(c, cudaMemcpyAsync(dst[i]->ptr, src[i]->ptr, (size_t)esz(src[i]->dtype) * (size_t)src[i]->len, cudaMemcpyDeviceToDevice, c->stream));
+                int s = device_copy(c, dst[i]->ptr, src[i]->ptr, src[i]->len, src[i]->dtype);
+                if (s) return s;
             }
         return LBK_OK;
     }
