@@ -276,8 +276,16 @@ template <class T> struct Rotm1F {      // Single.hs:481-482   h11*x + y ; -x + 
 __device__ __forceinline__ unsigned low_bits(float v) { return __float_as_uint(v); }
 __device__ __forceinline__ unsigned low_bits(double v) { return (unsigned)__double2loint(v); }
 
+// The shapes that hold at most 32 bytes of loaded data per thread live on occupancy (2048 threads per SM):
+// they are compiled for 4 resident 512-thread blocks, i.e. 32 registers -- two registers more cost a quarter of
+// the resident threads and 5% of the bandwidth (dcopy 7020 -> 6540, drot 6900 -> 6600 GB/s when ptxas chose 34 / 40).
+// Up to 128 bytes they are compiled for 2 such blocks (64 registers): left alone, ptxas has given saxpy's default
+// shape anything from 58 to 72 registers from one build to the next, and 72 halves its resident threads
+// (7130 -> 6590 GB/s).
+constexpr int map_min_blocks(int loaded_bytes_per_thread) { return loaded_bytes_per_thread <= 32 ? 4 : loaded_bytes_per_thread <= 128 ? 2 : 1; }
+
 template <class F, int VEC, int UNROLL, int POLICY, bool REV = false>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(kMaxThreads, map_min_blocks(VEC * UNROLL * (int)sizeof(typename F::Scalar) * ((F::RX ? 1 : 0) + (F::RY ? 1 : 0))))
 map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr, typename F::Scalar *xw,
                 typename F::Scalar *yw, i64 head, i64 n, unsigned fence_mask, int wait_mode)
 {
