@@ -204,6 +204,9 @@ def run_ours(args) -> None:
         sharded.attach_torch_distributed(ctx)
         if args.exchange != "auto":
             ctx.set_fused_exchange(args.exchange == "fused")
+    for spec in args.launch:
+        name, v, t, b = spec.split(":")
+        ctx.set_launch(name, int(v), int(t), int(b))
     exchange = ("fused: record pushed into every peer's mailbox over NVLink inside the reduction kernel" if ctx.fused_exchange()
                 else "ncclAllGather of one 48-byte record + finish kernel") if world > 1 else "none (1 rank)"
 
@@ -530,6 +533,8 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks per vector in the end-to-end pipeline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-f64", action="store_true", help="skip the table of the Double instances")
+    ap.add_argument("--launch", action="append", default=[], metavar="ROUTINE:VARIANT:THREADS:BLOCKS_PER_SM",
+                    help="override a routine's launch shape (lbk_set_launch), for A/B runs; the default shapes are the product")
     ap.add_argument("--criterion", action="store_true", help="print the reference's criterion matrix (test/Bench.hs) for the CPU port and the B200 path as CSV")
     ap.add_argument("--quick", action="store_true", help="--criterion: six sizes per routine instead of the full list")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],

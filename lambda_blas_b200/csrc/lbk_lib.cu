@@ -52,6 +52,8 @@ struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: de
 // values oversubscribe the SMs and let the hardware block scheduler balance the load; kOneTilePerBlock
 // makes the grid as large as the tile count, so blocks retire front to back through the vector -- the
 // shape every writer prefers (with the load fence of POLICY 6 and 32-64 bytes per thread per operand).
+// (saxpy: 16-byte packs x 4 are 1% faster back to back, 32-byte packs x 2 are 1% faster inside the bench step,
+// where saxpy runs under sdot's tail and snrm2 under saxpy's -- profiles/README.md; the step decides.)
 constexpr int kOneTilePerBlock = 1 << 20;
 static const LaunchCfg kDefaultCfg[R_COUNT] = {
     /* dot  */ {4, 256, 16},   /* sdsdot */ {3, 512, 8},    /* asum */ {3, 256, 16},
