@@ -69,6 +69,19 @@ def _worker(rank, world, port, seed, out):
         if n >= 101:                             # a tie that straddles the shard boundary, and a NaN that must lose
             x[n // 2 - 1] = 5.0; x[n // 2 + 3] = -5.0; x[7] = np.nan
         lo, hi = sharded.shard_range(n, world, rank)
+        # positive increments on shards (lbk_shard_span): logical element i sits at global position i*inc; this rank
+        # reduces the ones inside its block, and the fold over ranks must give the oracle's answer on the whole vector
+        for inc in (2, 3, 7):
+            m = (n - 1) // inc + 1
+            first, count, off = sharded.shard_span(n, world, rank, m, inc)
+            xs, ys = x[lo:hi][off::inc][:count], y[lo:hi][off::inc][:count]
+            ok &= np.array_equal(xs, x[::inc][first:first + count], equal_nan=True)
+            mine = _local_record(2, xs, ys, first)
+            buf = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8)
+            gathered = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(gathered, buf)
+            recs = [Record.from_buffer_copy(bytes(g.numpy().tobytes())) for g in gathered]
+            ok &= sharded.combine_records(2, recs, dt == np.float64) == oracle.iamax(m, x, inc)
         for kind in (0, 1, 2):
             mine = _local_record(kind, x[lo:hi], y[lo:hi], lo)
             buf = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8)
