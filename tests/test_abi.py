@@ -164,3 +164,20 @@ def test_shard_span_partitions_the_logical_range(blas):
         assert nxt == n
     with pytest.raises(blas.LbkError):
         sharded.shard_span(10, 2, 0, 5, 3)          # 1+(n-1)*inc exceeds the vector
+
+
+@pytest.mark.parametrize("src", ["example.cpp", "latency.cpp"])
+def test_cpp_mirror_compiles_against_the_header(src, tmp_path):
+    """cpp/lambda_blas.hpp (the compiled host layer) and its programs build and link against liblbk.so; running them
+    needs a GPU and is tests/test_gpu_smoke_first.py::test_cpp_mirror_example."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    lib = os.path.join(ROOT, "lambda_blas_b200")
+    if not os.path.exists(os.path.join(lib, "liblbk.so")):
+        pytest.skip("liblbk.so not built")
+    exe = str(tmp_path / "prog")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", os.path.join(ROOT, "cpp", src), "-o", exe, "-L" + lib, "-llbk",
+                        "-Wl,-rpath," + lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
