@@ -80,6 +80,9 @@ int lbk_launch_count(lbk_ctx *ctx, int64_t *launches);
  * drain.  The library tracks what the kernels still in flight read and write and launches the next one
  * holding its stores, or its loads, whenever the two depend on each other,
  * so results are unaffected.  lbk_pdl_count reports how many launches took that path. */
+/* enabled: 0 off, 1 on (default).  For experiments (tools/, cpp/latency.cpp): 2 = a kernel that overwrites what its
+ * predecessors use waits before its first LOAD instead of before its first store, 3 = dependent kernels of any kind
+ * are launched the ordinary way (only independent ones overlap), 4 = only true dependencies are. */
 int lbk_set_pdl(lbk_ctx *ctx, int enabled);
 int lbk_pdl_count(lbk_ctx *ctx, int64_t *launches);
 
