@@ -204,6 +204,8 @@ def run_ours(args) -> None:
         sharded.attach_torch_distributed(ctx)
         if args.exchange != "auto":
             ctx.set_fused_exchange(args.exchange == "fused")
+    if args.pdl != 1:
+        lb._ffi.check(lb._ffi.lib().lbk_set_pdl(ctx.handle, args.pdl), ctx.handle)
     for spec in args.launch:
         name, v, t, b = spec.split(":")
         ctx.set_launch(name, int(v), int(t), int(b))
@@ -535,6 +537,7 @@ def main():
     ap.add_argument("--no-f64", action="store_true", help="skip the table of the Double instances")
     ap.add_argument("--launch", action="append", default=[], metavar="ROUTINE:VARIANT:THREADS:BLOCKS_PER_SM",
                     help="override a routine's launch shape (lbk_set_launch), for A/B runs; the default shapes are the product")
+    ap.add_argument("--pdl", type=int, default=1, help="lbk_set_pdl value (1 = the product's default; 0 = every kernel launched the ordinary way, for A/B runs)")
     ap.add_argument("--criterion", action="store_true", help="print the reference's criterion matrix (test/Bench.hs) for the CPU port and the B200 path as CSV")
     ap.add_argument("--quick", action="store_true", help="--criterion: six sizes per routine instead of the full list")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
