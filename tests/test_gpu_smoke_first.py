@@ -207,3 +207,32 @@ def test_sdsdot_async_matches_the_blocking_call(blas, ctx, oracle):
         P.assert_same(got, np.array([blas.sdsdot(m, 0.625, x, incx, y, incy)], dtype=np.float32))
         want = float(oracle.sdsdot(m, 0.625, hx, incx, hy, incy))
         assert abs(float(got[0]) - want) <= 2.0 ** -23 * abs(want) + 1e-30       # double accumulation: one float rounding
+
+
+@pytest.mark.parametrize("fenced,threads,bps", [(0, 128, 8), (1, 256, 0), (1, 128, 100000)])
+def test_general_stride_kernels_under_every_launch_shape(blas, ctx, oracle, fenced, threads, bps):
+    """The general-stride map / reduce kernels give the oracle's bits whatever their launch shape (the fenced form of
+    the map kernel is not a default: it made no difference on B200, profiles/r01_strided_launch_sweep.md)."""
+    from lambda_blas_b200 import inplace as ip
+    rng = np.random.default_rng(11)
+    n = 40003
+    ctx.set_launch("mapstrided", fenced, threads, bps)
+    ctx.set_launch("redstrided", 0, threads, max(bps, 0) if bps < 1000 else 64)
+    try:
+        for incx, incy in ((2, 3), (-2, 5), (7, -1), (3, 3)):
+            hx, hy = gen_unit(rng, 1 + (n - 1) * abs(incx)), gen_unit(rng, 1 + (n - 1) * abs(incy))
+            x, y = ctx.to_device(hx), ctx.to_device(hy)
+            ip.saxpy_(n, 0.75, x, incx, y, incy)
+            want = oracle.saxpy(n, 0.75, hx, incx, hy, incy)
+            P.assert_same(y.to_host(), want)
+            ip.srot_(n, x, incx, y, incy, np.cos(0.3), np.sin(0.3))
+            wx, wy = oracle.srot(n, hx, incx, want, incy, np.cos(0.3), np.sin(0.3))
+            P.assert_same(x.to_host(), wx); P.assert_same(y.to_host(), wy)
+            got = float(blas.sdot(n, x, incx, y, incy))
+            ref = float(oracle.sdot(n, wx, incx, wy, incy))
+            assert abs(got - ref) <= 2 * n * 2.0 ** -24 * float(np.sum(np.abs(P.sample(wx, n, incx) * P.sample(wy, n, incy))))
+            if incx > 0:
+                assert blas.isamax(n, x, incx) == oracle.isamax(n, wx, incx)
+    finally:
+        ctx.set_launch("mapstrided", -1, 0, 0)
+        ctx.set_launch("redstrided", -1, 0, 0)
