@@ -106,3 +106,49 @@ def test_full_table_ends_the_chain(sim):
 def test_disabled(sim):
     sim.L.lbk_pdl_sim_enable(sim.h, 0)
     assert [sim.op([X], [Y])[0], sim.op([Z], [W])[0], sim.red(NRM2, X)[0], sim.op([Y], [Z])[0]] == [0, 0, 0, 0]
+
+
+def _overlap(a, b):
+    return a[0] < b[0] + b[1] and b[0] < a[0] + a[1]
+
+
+def test_random_sequences_never_admit_a_hazard(blas):
+    """Model check: replay random kernel sequences through the planner and, from the MODES it hands out alone, keep the
+    set of kernels that may physically still be running when the next one starts.  Whatever the planner's own
+    bookkeeping (capacity, predictor, late release), no kernel may then read what a running kernel writes, nor
+    write -- before its wait -- what a running kernel reads or writes."""
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    bases = [0x1000000 * (k + 1) for k in range(6)]
+    for trial in range(200):
+        sim = Sim(blas)
+        flight = []                               # (reads, writes) of kernels that may still be running
+        for step in range(int(rng.integers(5, 80))):
+            if rng.random() < 0.08:
+                sim.interrupt(); flight = None    # any other stream operation: the next launch must be ordinary
+                continue
+            def rng_range():
+                b = bases[int(rng.integers(len(bases)))]
+                off = int(rng.integers(0, 4)) * (N // 4)
+                return (b + off, int(rng.integers(1, 5)) * (N // 4))
+            reduction = rng.random() < 0.4
+            reads = [rng_range() for _ in range(int(rng.integers(1, 3)))]
+            writes = [(OUT + 16 * int(rng.integers(4)), 8)] if reduction else [rng_range() for _ in range(int(rng.integers(1, 3)))]
+            if not reduction and rng.random() < 0.5:
+                reads[0] = writes[0]              # an in-place update
+            mode, late = sim.op(reads, writes, reduction, int(rng.integers(3)))
+            if flight is None:
+                assert mode == 0                  # after an interruption nothing may overlap
+                flight = []
+            if mode in (0, 3):
+                flight = []                       # starts (in effect) after everything before it
+            for fr, fw in flight:
+                assert not any(_overlap(r, w) for r in reads for w in fw), "reads what a running kernel writes"
+                if mode == 1 and not reduction:
+                    assert not any(_overlap(w, o) for w in writes for o in fr + fw), "stores over a running kernel's operands"
+            if late:
+                assert reduction
+                flight = [([], writes)]           # released after its loads and its predecessors: only its result is pending
+            else:
+                flight.append((reads, writes))
+        sim.close()
