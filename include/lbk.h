@@ -31,7 +31,13 @@
  *     Util.hs:134-142) are obtained by the host layer with lbk_vec_clone + the
  *     in-place routine, or in one pass with the *_oop ("out of place") variants;
  *   - one context per host thread, or calls on a context serialised by the caller.
- *     There is no CPU fallback: without a CUDA device lbk_init fails.
+ *     There is no CPU fallback: without a CUDA device lbk_init fails;
+ *   - the library leaves the process as it found it: every call runs with the context's device current and
+ *     restores the caller's current device before it returns, and vectors come from the context's OWN
+ *     stream-ordered memory pool (the device's default pool and its release threshold are not touched);
+ *   - handles keep their context alive: lbk_shutdown on a context that still has vectors or events only closes
+ *     it (every further call fails with LBK_ERR_ARG), and the last lbk_vec_free / lbk_event_destroy -- e.g. a
+ *     finaliser run by a garbage collector after the scope that closed the context -- releases it.
  */
 #ifndef LBK_H
 #define LBK_H
@@ -42,7 +48,7 @@
 extern "C" {
 #endif
 
-#define LBK_VERSION 100 /* 0.1.0 */
+#define LBK_VERSION 200 /* 0.2.0 */
 
 enum lbk_status {
     LBK_OK = 0,
@@ -63,6 +69,25 @@ typedef struct lbk_event lbk_event; /* CUDA event on the context's stream (timin
 int lbk_version(void);
 int lbk_device_count(int *count);
 int lbk_init(int device, lbk_ctx **ctx);
+/* ONE host thread, many GPUs (the reference is a single-threaded library: lambda-blas.cabal:36-48, call surface
+ * Single.hs:84-85).  Rank r of the context is device devs[r].  lbk_vec_alloc_sharded then makes block shards over
+ * the ranks and EVERY routine of this header fans out over per-device streams -- from one launcher thread per
+ * device (lbk_set_multi_threads, the default) or one after the other from the calling thread; lbk_vec_upload /
+ * _download scatter / gather ONE host buffer, each rank moving its block over its own PCIe link.  Elementwise
+ * routines need no communication; a reduction ends inside its kernel: the last block of every rank writes its
+ * 48-byte record into every other rank's mailbox through plain peer pointers (cudaDeviceEnablePeerAccess over
+ * NVLink; mapped host memory when the devices are not peers) and folds what it received in rank order, so all
+ * ranks hold the same bits and the caller reads rank 0's.  lbk_vec_alloc / lbk_vec_wrap make UNSHARDED vectors:
+ * whole on devs[0], with the full increment semantics of a one-device context; the vectors of one call are all
+ * sharded or all unsharded.  The same device may appear more than once in devs[] (ranks then share a GPU, each
+ * with its own stream, and run without programmatic dependent launch): the sharded path on a one-GPU box. */
+int lbk_init_multi(int ndev, const int *devs, lbk_ctx **ctx);
+/* The rank context of rank r (borrowed; it goes with the multi-device context): a one-device context with
+ * nranks = ndev whose sharded vectors are that rank's blocks -- for callers that drive the ranks themselves. */
+int lbk_multi_rank(lbk_ctx *ctx, int rank, lbk_ctx **rank_ctx);
+/* enabled = 1: one launcher thread per device (they spin for 200 us after a call, then sleep); 0: the calling
+ * thread launches rank after rank (each launch costs 2-3 us, so the last of 8 GPUs starts ~20 us late). */
+int lbk_set_multi_threads(lbk_ctx *ctx, int enabled);
 int lbk_shutdown(lbk_ctx *ctx);
 int lbk_sync(lbk_ctx *ctx);                 /* wait for everything enqueued on the context */
 const char *lbk_last_error(lbk_ctx *ctx);   /* text of the last failure ("" if none); ctx may be NULL */
@@ -100,6 +125,10 @@ int lbk_comm_info(lbk_ctx *ctx, int *nranks, int *rank);
  * every rank could map every mailbox; lbk_set_fused_exchange overrides it (all ranks must agree). */
 int lbk_comm_transport(lbk_ctx *ctx, int *fused);
 int lbk_set_fused_exchange(lbk_ctx *ctx, int enabled);
+/* How long a reduction kernel's last block waits for the peers' records before it gives up and the call (or the
+ * next lbk_sync) returns LBK_ERR_NCCL: a rank that never makes the matching call must not hang the others.
+ * Default 5000 ms, or LBK_EXCHANGE_TIMEOUT_MS from the environment. */
+int lbk_set_exchange_timeout(lbk_ctx *ctx, int64_t milliseconds);
 /* Block partition of [0, global_len) used by lbk_vec_alloc_sharded: rank r owns [lo, hi). */
 int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t *lo, int64_t *hi);
 /* Sharded vectors take positive increments: logical element i of a call (n, inc) sits at global position i*inc.
@@ -122,8 +151,13 @@ int lbk_vec_alloc_sharded_f64(lbk_ctx *ctx, int64_t global_len, lbk_vec **v);
 int lbk_vec_wrap(lbk_ctx *ctx, void *device_ptr, int64_t len, lbk_vec **v);     /* non-owning */
 int lbk_vec_wrap_f64(lbk_ctx *ctx, void *device_ptr, int64_t len, lbk_vec **v);
 int lbk_vec_view(const lbk_vec *v, int64_t offset, int64_t len, lbk_vec **view); /* non-owning */
+/* An uninitialised vector with v's length, element type and shard layout: what a pure routine's result is made of. */
+int lbk_vec_alloc_like(const lbk_vec *v, lbk_vec **out);
+/* Rank r's block of a multi-device context's vector, as a (borrowed, non-owning) handle of that rank's context. */
+int lbk_vec_part(const lbk_vec *v, int rank, lbk_vec **part);
 int lbk_vec_free(lbk_vec *v);
 int lbk_vec_len(const lbk_vec *v, int64_t *local_len, int64_t *global_len, int64_t *shard_offset);
+int lbk_vec_is_sharded(const lbk_vec *v);                                       /* 1: a block shard / sharded over ranks */
 int lbk_vec_elem_size(const lbk_vec *v);                                        /* 4 or 8 */
 void *lbk_vec_ptr(const lbk_vec *v);
 int lbk_vec_upload(lbk_vec *v, const void *host, int64_t len);        /* host -> device, synchronous */
@@ -136,9 +170,13 @@ int lbk_vec_clone(const lbk_vec *v, lbk_vec **out);
  * vector's own precision. */
 int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, double lo, double hi);
 int lbk_vec_fill(lbk_vec *v, double value);
-/* Pinned host memory for the transfers above. */
+/* Pinned host memory for the transfers above: lbk_host_alloc makes some; lbk_host_register page-locks memory
+ * the caller already owns (a Data.Vector.Storable buffer, Single.hs:67) until lbk_host_unregister, so that
+ * uploads from it run at the rate of a pinned copy instead of through the driver's staging buffer. */
 int lbk_host_alloc(int64_t nbytes, void **host);
 int lbk_host_free(void *host);
+int lbk_host_register(void *host, int64_t nbytes);
+int lbk_host_unregister(void *host);
 
 /* ---- timing on the context's stream ---------------------------------------------------------- */
 int lbk_event_create(lbk_ctx *ctx, lbk_event **ev);
@@ -238,6 +276,11 @@ int lbk_drotmg(double sd1, double sd2, double sx1, double sy1, double out[8], do
 typedef struct lbk_record { double f[3]; uint64_t key; int64_t idx; int64_t pad; } lbk_record;
 enum lbk_reduce_kind { LBK_RED_SUM = 0, LBK_RED_NRM2 = 1, LBK_RED_IAMAX = 2 };
 int lbk_combine_records(int kind, int is_f64, const lbk_record *recs, int nranks, double *fout, int64_t *iout);
+
+/* ---- the launcher threads of a multi-device context on their own (CPU tests; lambda_blas_b200/csrc/lbk_team.hpp) ----
+ * `jobs` jobs on a team of `nranks`; job j makes rank r add (j+1)*(r+1) to its counter and report status 100+r when
+ * j == fail_at; *sum = total of the counters, *first_status = what the failing job returned. */
+int lbk_team_selftest(int nranks, int jobs, int fail_at, int pause_us, int64_t *sum, int *first_status);
 
 /* ---- the launch planner on its own (CPU tests of the programmatic-dependent-launch rules) ------------------
  * Feeds one unit-stride kernel at a time -- what it reads and writes as (address, bytes) pairs, whether it is a

@@ -36,6 +36,10 @@ PROTOTYPES = {
     "lbk_version": (_int, []),
     "lbk_device_count": (_int, [_pint]),
     "lbk_init": (_int, [_int, _pvp]),
+    "lbk_init_multi": (_int, [_int, _pint, _pvp]),
+    "lbk_multi_rank": (_int, [_vp, _int, _pvp]),
+    "lbk_set_multi_threads": (_int, [_vp, _int]),
+    "lbk_set_exchange_timeout": (_int, [_vp, _i64]),
     "lbk_shutdown": (_int, [_vp]),
     "lbk_sync": (_int, [_vp]),
     "lbk_last_error": (C.c_char_p, [_vp]),
@@ -59,6 +63,9 @@ PROTOTYPES = {
     "lbk_vec_wrap": (_int, [_vp, _vp, _i64, _pvp]),
     "lbk_vec_wrap_f64": (_int, [_vp, _vp, _i64, _pvp]),
     "lbk_vec_view": (_int, [_vp, _i64, _i64, _pvp]),
+    "lbk_vec_alloc_like": (_int, [_vp, _pvp]),
+    "lbk_vec_part": (_int, [_vp, _int, _pvp]),
+    "lbk_vec_is_sharded": (_int, [_vp]),
     "lbk_vec_free": (_int, [_vp]),
     "lbk_vec_len": (_int, [_vp, _pi64, _pi64, _pi64]),
     "lbk_vec_elem_size": (_int, [_vp]),
@@ -72,6 +79,9 @@ PROTOTYPES = {
     "lbk_vec_fill": (_int, [_vp, _f64]),
     "lbk_host_alloc": (_int, [_i64, _pvp]),
     "lbk_host_free": (_int, [_vp]),
+    "lbk_host_register": (_int, [_vp, _i64]),
+    "lbk_host_unregister": (_int, [_vp]),
+    "lbk_team_selftest": (_int, [_int, _int, _int, _int, _pi64, _pint]),
     "lbk_event_create": (_int, [_vp, _pvp]),
     "lbk_event_record": (_int, [_vp]),
     "lbk_event_elapsed_ms": (_int, [_vp, _vp, _pf32]),

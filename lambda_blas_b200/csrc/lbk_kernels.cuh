@@ -72,7 +72,12 @@ template <> __device__ __forceinline__ double from_abs_bits<double>(u64 b) { ret
 // ------------------------------------------------------------------------------------------------
 // 128/256-bit global memory access.  A Pack is VEC elements = 4/8 (scalar), 16 or 32 bytes.
 // POLICY 0: default caching.  POLICY >= 1: streaming -- do not allocate in L1 (each byte is touched
-// once), read-only operands through the non-coherent path.  POLICY 2..5 add L2 hints on 256-bit
+// once).  Read-only operands do NOT go through the non-coherent path (ld.global.nc): every unit-stride
+// kernel can be a programmatic-dependent-launch secondary that is resident while its predecessor is
+// still writing what it will read after griddepcontrol.wait, and PTX defines .nc only for data that
+// stays read-only for the kernel's whole lifetime.  A plain ld.global.L1::no_allocate is served from L2
+// at the same rate (profiles/r02_nc_ab.md); LBK_USE_NC=1 rebuilds the old qualifier for A/B runs only.
+// POLICY 2..5 add L2 hints on 256-bit
 // accesses (2/3: evict-first loads, 3/5: evict-first stores, 4: 256-byte L2 prefetch + st.cs); they were
 // measured to make no difference (profiles/r01_tune_l2policy_writers.csv) and exist for tools/tune.py.
 // POLICY 6 = POLICY 1 plus, in the map kernel, a data dependency that holds a thread's stores back until
@@ -97,15 +102,23 @@ template <class T, int VEC> struct alignas(VEC * sizeof(T)) Pack { T v[VEC]; };
 #define LBK_LD_F64x2(Q) asm volatile("ld.global" Q ".v2.f64 {%0,%1}, [%2];" : "=d"(p.v[0]), "=d"(p.v[1]) : "l"(ptr) : "memory")
 #define LBK_LD_F64x4(Q) asm volatile("ld.global" Q ".v4.f64 {%0,%1,%2,%3}, [%4];"                   \
                                      : "=d"(p.v[0]), "=d"(p.v[1]), "=d"(p.v[2]), "=d"(p.v[3]) : "l"(ptr) : "memory")
+#ifndef LBK_USE_NC
+#define LBK_USE_NC 0
+#endif
+#if LBK_USE_NC
+#define LBK_NC ".nc"
+#else
+#define LBK_NC ""
+#endif
 #define LBK_LD_DISPATCH(SHAPE)                                                                      \
     do {                                                                                            \
         constexpr int q = LBK_LDQ(POLICY, RO, sizeof(T) * VEC == 32);                               \
         if constexpr (q == 0) SHAPE("");                                                            \
-        else if constexpr (q == 1) SHAPE(".nc.L1::no_allocate");                                    \
+        else if constexpr (q == 1) SHAPE(LBK_NC ".L1::no_allocate");                                \
         else if constexpr (q == 2) SHAPE(".L1::no_allocate");                                       \
-        else if constexpr (q == 3) SHAPE(".nc.L1::no_allocate.L2::evict_first");                    \
+        else if constexpr (q == 3) SHAPE(LBK_NC ".L1::no_allocate.L2::evict_first");                \
         else if constexpr (q == 4) SHAPE(".L1::no_allocate.L2::evict_first");                       \
-        else if constexpr (q == 5) SHAPE(".nc.L1::no_allocate.L2::256B");                           \
+        else if constexpr (q == 5) SHAPE(LBK_NC ".L1::no_allocate.L2::256B");                       \
         else SHAPE(".L1::no_allocate.L2::256B");                                                    \
     } while (0)
 
@@ -668,6 +681,7 @@ struct FinishArgs {
     int nranks, rank;
     unsigned seq;         // number of this exchange, identical on every rank, never 0
     int *error_flag;      // host-mapped: set to 1 if a peer's record never arrived
+    u64 timeout_ns;       // how long the last block waits for the peers' records (lbk_set_exchange_timeout)
     // synchronous calls: `out` is host-mapped and the host polls done_flag (next to it) for done_seq instead
     // of synchronising the stream -- the scalar is back 5-7 us sooner (profiles/r01_call_latency.csv)
     unsigned *done_flag;
@@ -690,7 +704,7 @@ __device__ __forceinline__ void signal_done(unsigned *done_flag, unsigned done_s
 constexpr int kMaxRanks = 64;
 constexpr int kMailboxSlot = 16;                               // words reserved per sender (>= kRecordWords)
 constexpr int kMailboxWords = 2 * kMaxRanks * kMailboxSlot;
-constexpr u64 kExchangeTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;
+constexpr u64 kExchangeTimeoutNs = 5ull * 1000ull * 1000ull * 1000ull;   // default; lbk_set_exchange_timeout
 static_assert(kRecordWords <= kMailboxSlot, "a record fits its mailbox slot");
 
 __device__ __forceinline__ u64 global_timer_ns()
@@ -823,7 +837,7 @@ __device__ __forceinline__ void grid_finish(typename Op::Partial p, Record *part
         for (;;) {
             asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
             if ((unsigned)(v >> 32) == fa.seq) break;
-            if (global_timer_ns() - t_start > kExchangeTimeoutNs) { timed_out = 1; v = 0; break; }
+            if (global_timer_ns() - t_start > fa.timeout_ns) { timed_out = 1; v = 0; break; }
         }
         reinterpret_cast<unsigned *>(&all[src])[w] = (unsigned)v;
     }

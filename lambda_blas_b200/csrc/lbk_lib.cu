@@ -8,6 +8,7 @@
 #include "../../include/lbk.h"
 #include "lbk_kernels.cuh"
 #include "lbk_pdl.hpp"
+#include "lbk_team.hpp"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -17,7 +18,10 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -71,6 +75,20 @@ struct lbk_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;     // this context's own stream-ordered pool (the device's default pool is left alone)
+    // Handles (vectors, events) keep their context alive: lbk_shutdown on a context that still has handles
+    // only closes it, and the last lbk_vec_free / lbk_event_destroy releases it (a garbage-collected host
+    // language runs finalisers after the scope that closed the context).
+    std::atomic<int> refs{0};
+    bool closed = false;
+    // ---- single-process multi-device context (lbk_init_multi): `subs` are the rank contexts, one per entry of
+    // devs[]; every routine fans out over them.  A rank context points back through `parent`.
+    std::vector<lbk_ctx *> subs;
+    lbk_ctx *parent = nullptr;
+    std::unique_ptr<lbk_team::Team> team;   // launcher threads (rank >= 1), when threaded
+    bool threaded = false;
+    bool host_mailbox = false;        // the mailboxes live in mapped host memory (no peer access between the devices)
+    void *sink = nullptr;             // 64 device bytes: where ranks >= 1 put the scalar of an enqueue-only reduction
     Record *partials = nullptr;
     unsigned *ticket = nullptr;
     double *snap = nullptr;           // two slots: snapshots of x[0], y[0] for zero output increments
@@ -88,6 +106,7 @@ struct lbk_ctx {
     bool fused_exchange = false;
     unsigned exchange_seq = 0;
     int *error_flag_host = nullptr, *error_flag_dev = nullptr;   // mapped: a kernel reports an exchange timeout
+    unsigned long long exchange_timeout_ns = lbk::kExchangeTimeoutNs;
     LaunchCfg cfg[R_COUNT];
     lbk_pdl::State pdl;               // which kernels of the stream may overlap: see lbk_pdl.hpp
     int64_t launches = 0;
@@ -104,10 +123,14 @@ struct lbk_vec {
     bool owner;
     bool sharded;
     int dtype;        // 0: float (Vector Float), 1: double (Vector Double)
+    // a vector of a multi-device context: its parts on the rank contexts, in rank order -- every rank's block
+    // shard when `sharded`, otherwise ONE part on rank 0 (the whole vector on devs[0]).  ptr is then part 0's.
+    std::vector<lbk_vec *> parts;
+    bool borrowed = false;   // a handle lbk_vec_part gave out: freeing it must not free the part
 };
 static inline int esz(int dtype) { return dtype ? 8 : 4; }
 
-struct lbk_event { lbk_ctx *ctx; cudaEvent_t ev; };
+struct lbk_event { lbk_ctx *ctx; cudaEvent_t ev; std::vector<lbk_event *> parts; };
 
 static thread_local std::string g_err;   // failures before a context exists
 
@@ -122,6 +145,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t *) = nullptr;   // optional
     std::string error;
 };
 static NcclApi *nccl_api()
@@ -138,6 +162,7 @@ static NcclApi *nccl_api()
         api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
         api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+        api.CommGetAsyncError = (decltype(api.CommGetAsyncError))dlsym(h, "ncclCommGetAsyncError");
         if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) {
             api.error = "libnccl.so.2 lacks a required symbol";
             api.handle = nullptr;
@@ -171,12 +196,48 @@ static int fail(lbk_ctx *ctx, int code, const std::string &msg)
             return fail((ctx), LBK_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
     } while (0)
 
+// Every entry point that launches or allocates runs with the context's device current and puts the caller's
+// device back afterwards: the host application (torch, another library) keeps its own current device.
+struct DevGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err;
+    explicit DevGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            changed = err == cudaSuccess;
+        }
+    }
+    ~DevGuard() { if (changed) cudaSetDevice(prev); }
+    DevGuard(const DevGuard &) = delete;
+    DevGuard &operator=(const DevGuard &) = delete;
+};
+#define ON_DEVICE(ctx)                                                                             \
+    DevGuard dev_guard_((ctx)->device);                                                            \
+    if (dev_guard_.err != cudaSuccess)                                                             \
+        return fail((ctx), LBK_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(dev_guard_.err))
+
+static inline bool is_multi(const lbk_ctx *c) { return c && !c->subs.empty(); }
+#define LIVE(ctx, who)                                                                             \
+    if ((ctx)->closed) return fail((ctx), LBK_ERR_ARG, std::string(who) + ": the context has been shut down")
+
 static inline i64 first_index(i64 n, i64 inc) { return inc > 0 ? 0 : (1 - n) * inc; }   // Single.hs:91-96
 
 // Device-to-device copy of whole elements on the context's stream with the copy kernel (scopy's): faster than
 // cudaMemcpyAsync on this part (7.0 vs 6.4 TB/s) and, unlike it, a member of the chain of overlapping kernels.
 static int device_copy(lbk_ctx *c, void *dst, const void *src, i64 count, int dtype);
 static inline i64 iabs64(i64 v) { return v < 0 ? -v : v; }
+// Does the span 1 + (n-1)*|inc| of n >= 1 logical elements exceed `len` elements?  Stated without the product,
+// which overflows int64 for large n x inc (and |INT64_MIN| does not exist).
+static inline bool span_exceeds(i64 n, i64 inc, i64 len)
+{
+    if (len < 1) return true;
+    if (inc == INT64_MIN) return n > 1;
+    const i64 a = iabs64(inc);
+    return a != 0 && n - 1 > (len - 1) / a;
+}
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -190,9 +251,11 @@ extern "C" int lbk_device_count(int *count)
     return LBK_OK;
 }
 
-extern "C" int lbk_init(int device, lbk_ctx **out)
+static void destroy_one(lbk_ctx *c);
+
+// One rank context: a device, a stream, a private memory pool and the reduction scratch.
+static int init_one(int device, lbk_ctx **out)
 {
-    if (!out) return fail(nullptr, LBK_ERR_ARG, "lbk_init: null out pointer");
     *out = nullptr;
     int count = 0;
     CU(nullptr, cudaGetDeviceCount(&count));
@@ -202,26 +265,39 @@ extern "C" int lbk_init(int device, lbk_ctx **out)
     if (!c) return fail(nullptr, LBK_ERR_NOMEM, "lbk_init: out of host memory");
     c->device = device;
     for (int r = 0; r < R_COUNT; ++r) c->cfg[r] = kDefaultCfg[r];
-    cudaError_t e;
-#define INIT(call) if ((e = (call)) != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e); delete c; return fail(nullptr, LBK_ERR_CUDA, m); }
-    INIT(cudaSetDevice(device));
+    if (const char *t = getenv("LBK_EXCHANGE_TIMEOUT_MS")) {
+        const long ms = atol(t);
+        if (ms > 0) c->exchange_timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
+    DevGuard guard(device);
+    cudaError_t e = guard.err;
+    if (e != cudaSuccess) { delete c; return fail(nullptr, LBK_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+#define INIT(call) if ((e = (call)) != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e); cudaGetLastError(); destroy_one(c); return fail(nullptr, LBK_ERR_CUDA, m); }
     INIT(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
     INIT(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    {   // vectors come from the device's stream-ordered pool: the reference's pure routines allocate a result
-        // per call (Util.hs:134-142), which must not cost a cudaMalloc + a device-wide synchronise each time
-        cudaMemPool_t pool;
-        INIT(cudaDeviceGetDefaultMemPool(&pool, device));
-        unsigned long long keep = ~0ull;      // freed blocks stay cached in the pool
-        INIT(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    {   // vectors come from a stream-ordered pool: the reference's pure routines allocate a result per call
+        // (Util.hs:134-142), which must not cost a cudaMalloc + a device-wide synchronise each time.  The pool is
+        // this context's own: the device's default pool (and whoever else uses it in the process) is untouched.
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        INIT(cudaMemPoolCreate(&c->pool, &props));
+        unsigned long long keep = ~0ull;      // freed blocks stay cached in the pool until the context goes
+        INIT(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     INIT(cudaMalloc(&c->partials, sizeof(Record) * kMaxGrid));
     INIT(cudaMalloc(&c->ticket, sizeof(unsigned)));
     INIT(cudaMemset(c->ticket, 0, sizeof(unsigned)));
     INIT(cudaMalloc(&c->snap, 2 * sizeof(double)));
+    INIT(cudaMalloc(&c->sink, 64));
     INIT(cudaHostAlloc(&c->result_host, 64, cudaHostAllocMapped));
+    if (c->result_host) memset(c->result_host, 0, 64);     // the tag the host polls starts from a known value
     INIT(cudaHostGetDevicePointer(&c->result_dev, c->result_host, 0));
     INIT(cudaHostAlloc((void **)&c->error_flag_host, sizeof(int), cudaHostAllocMapped));
-    *c->error_flag_host = 0;
+    if (c->error_flag_host) *c->error_flag_host = 0;
     INIT(cudaHostGetDevicePointer((void **)&c->error_flag_dev, c->error_flag_host, 0));
     INIT(cudaMalloc(&c->rec_send, sizeof(Record)));
     INIT(cudaMalloc(&c->rec_all, sizeof(Record) * 64));
@@ -231,21 +307,195 @@ extern "C" int lbk_init(int device, lbk_ctx **out)
     return LBK_OK;
 }
 
+// Releases everything a rank context owns (the stream has been synchronised by the caller when it matters).
+static void destroy_one(lbk_ctx *c)
+{
+    if (!c) return;
+    {
+        DevGuard guard(c->device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        if (c->comm) {
+            for (int r = 0; r < c->nranks; ++r)
+                if (r != c->rank && c->peer_ptrs[r]) cudaIpcCloseMemHandle(c->peer_ptrs[r]);
+            nccl_api()->CommDestroy(c->comm);
+        }
+        if (c->mailbox) { if (c->host_mailbox) cudaFreeHost(c->mailbox); else cudaFree(c->mailbox); }
+        cudaFree(c->peers_dev);
+        if (c->error_flag_host) cudaFreeHost(c->error_flag_host);
+        cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->snap); cudaFree(c->sink);
+        cudaFree(c->rec_send); cudaFree(c->rec_all);
+        if (c->result_host) cudaFreeHost(c->result_host);
+        if (c->pool) cudaMemPoolDestroy(c->pool);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        cudaGetLastError();
+    }
+    delete c;
+}
+
+static std::mutex g_life;      // context lifetime: shutdown and the last handle's release may come from different threads
+static inline lbk_ctx *root_of(lbk_ctx *c) { return c->parent ? c->parent : c; }
+static int live_handles(lbk_ctx *root)
+{
+    int n = root->refs.load();
+    for (lbk_ctx *s : root->subs) n += s->refs.load();
+    return n;
+}
+static void destroy_tree(lbk_ctx *root)
+{
+    root->team.reset();
+    for (lbk_ctx *s : root->subs) destroy_one(s);
+    root->subs.clear();
+    if (root->stream || root->pool) destroy_one(root); else delete root;
+}
+static inline void ctx_ref(lbk_ctx *c) { c->refs.fetch_add(1); }
+// A handle of `c` is gone; a context that was shut down while handles were alive goes with its last handle.
+static void ctx_unref(lbk_ctx *c)
+{
+    std::lock_guard<std::mutex> lk(g_life);
+    c->refs.fetch_sub(1);
+    lbk_ctx *root = root_of(c);
+    if (root->closed && live_handles(root) == 0) destroy_tree(root);
+}
+
+extern "C" int lbk_init(int device, lbk_ctx **out)
+{
+    if (!out) return fail(nullptr, LBK_ERR_ARG, "lbk_init: null out pointer");
+    return init_one(device, out);
+}
+
+// Runs fn(rank context, rank) for the first `count` ranks of a multi-device context: on the launcher threads
+// when all ranks take part and the context is threaded, otherwise one after the other on the calling thread.
+static int fan_out(lbk_ctx *m, int count, const std::function<int(lbk_ctx *, int)> &fn)
+{
+    const int n = (int)m->subs.size();
+    for (int r = 0; r < n; ++r) m->subs[r]->err.clear();
+    int status = LBK_OK;
+    if (count == n && n > 1 && m->threaded && m->team) {
+        status = m->team->run([&](int r) { return fn(m->subs[r], r); });
+    } else {
+        for (int r = 0; r < count && !status; ++r) status = fn(m->subs[r], r);
+    }
+    if (status)
+        for (int r = 0; r < n; ++r)
+            if (!m->subs[r]->err.empty()) { m->err = "rank " + std::to_string(r) + " (device " + std::to_string(m->subs[r]->device) + "): " + m->subs[r]->err; break; }
+    return status;
+}
+static inline int all_ranks(lbk_ctx *m, const std::function<int(lbk_ctx *, int)> &fn) { return fan_out(m, (int)m->subs.size(), fn); }
+
+static void make_team(lbk_ctx *m)
+{
+    if (m->team || m->subs.size() < 2) return;
+    std::vector<int> devs;
+    for (lbk_ctx *s : m->subs) devs.push_back(s->device);
+    m->team.reset(new lbk_team::Team((int)devs.size(), [devs](int r) { cudaSetDevice(devs[r]); }));
+}
+
+// lbk_init_multi: ONE host thread drives the GPUs devs[0..ndev).  Rank r of the context is devs[r]; vectors made
+// with lbk_vec_alloc_sharded are block shards over the ranks, every routine fans out over per-device streams,
+// and a reduction ends inside its kernel: the last block of every rank pushes its 48-byte record into every
+// other rank's mailbox -- plain peer pointers (cudaDeviceEnablePeerAccess; no IPC, no NCCL) -- and folds what
+// it received in rank order.  The same device may appear more than once (two ranks then share a GPU, each with
+// its own stream): that is how the 2-shard path is exercised on a one-GPU box.
+extern "C" int lbk_init_multi(int ndev, const int *devs, lbk_ctx **out)
+{
+    if (!out) return fail(nullptr, LBK_ERR_ARG, "lbk_init_multi: null out pointer");
+    *out = nullptr;
+    if (ndev < 1 || ndev > lbk::kMaxRanks || !devs) return fail(nullptr, LBK_ERR_ARG, "lbk_init_multi: needs 1..64 devices");
+    lbk_ctx *m = new (std::nothrow) lbk_ctx();
+    if (!m) return fail(nullptr, LBK_ERR_NOMEM, "lbk_init_multi: out of host memory");
+    auto bail = [&](int code, const std::string &msg) { destroy_tree(m); return fail(nullptr, code, msg); };
+    bool dup = false;
+    for (int r = 0; r < ndev; ++r) {
+        lbk_ctx *s = nullptr;
+        int st = init_one(devs[r], &s);
+        if (st) { std::string msg = g_err; return bail(st, msg); }
+        s->parent = m; s->nranks = ndev; s->rank = r;
+        m->subs.push_back(s);
+        for (int q = 0; q < r; ++q) dup = dup || devs[q] == devs[r];
+    }
+    m->device = devs[0]; m->sms = m->subs[0]->sms; m->nranks = ndev; m->rank = 0;
+    for (int r = 0; r < R_COUNT; ++r) m->cfg[r] = kDefaultCfg[r];
+    if (ndev > 1) {
+        // peer access between every pair of distinct devices; without it the mailboxes live in mapped host memory
+        bool peer = true;
+        for (int a = 0; a < ndev && peer; ++a)
+            for (int b = 0; b < ndev && peer; ++b) {
+                if (devs[a] == devs[b]) continue;
+                int ok = 0;
+                if (cudaDeviceCanAccessPeer(&ok, devs[a], devs[b]) != cudaSuccess || !ok) { cudaGetLastError(); peer = false; }
+            }
+        for (int a = 0; a < ndev && peer; ++a) {
+            DevGuard g(devs[a]);
+            for (int b = 0; b < ndev; ++b) {
+                if (devs[a] == devs[b]) continue;
+                cudaError_t e = cudaDeviceEnablePeerAccess(devs[b], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peer = false;
+                cudaGetLastError();
+            }
+        }
+        const size_t mb = sizeof(unsigned long long) * lbk::kMailboxWords;
+        for (int r = 0; r < ndev; ++r) {
+            lbk_ctx *s = m->subs[r];
+            DevGuard g(s->device);
+            cudaError_t e;
+            s->host_mailbox = !peer;
+            if (peer) { e = cudaMalloc(&s->mailbox, mb); if (e == cudaSuccess) e = cudaMemset(s->mailbox, 0, mb); }
+            else { e = cudaHostAlloc((void **)&s->mailbox, mb, cudaHostAllocPortable | cudaHostAllocMapped); if (e == cudaSuccess) memset(s->mailbox, 0, mb); }
+            if (e == cudaSuccess) e = cudaMalloc(&s->peers_dev, sizeof(void *) * lbk::kMaxRanks);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) return bail(LBK_ERR_CUDA, std::string("lbk_init_multi: mailbox: ") + cudaGetErrorString(e));
+        }
+        for (int r = 0; r < ndev; ++r) {
+            lbk_ctx *s = m->subs[r];
+            DevGuard g(s->device);
+            for (int q = 0; q < ndev; ++q) s->peer_ptrs[q] = m->subs[q]->mailbox;     // unified addressing: the same pointer on every device
+            cudaError_t e = cudaMemcpy(s->peers_dev, s->peer_ptrs, sizeof(void *) * lbk::kMaxRanks, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return bail(LBK_ERR_CUDA, std::string("lbk_init_multi: peer table: ") + cudaGetErrorString(e));
+            s->fused_exchange = true;
+            s->exchange_seq = 0;
+            // Two ranks on ONE device: a kernel's last block waits in the exchange for the other rank's kernel, which
+            // needs SM slots -- slots that this rank's NEXT kernel, resident early under programmatic dependent launch
+            // and parked at its griddepcontrol.wait, could be holding.  No early residency on a shared device.
+            if (dup) { s->pdl.enabled = false; }
+        }
+        m->host_mailbox = !peer;
+        m->fused_exchange = true;
+        const char *t = getenv("LBK_MULTI_THREADS");
+        m->threaded = t ? atoi(t) != 0 : !dup;
+        if (m->threaded) make_team(m);
+    }
+    *out = m;
+    return LBK_OK;
+}
+
+extern "C" int lbk_multi_rank(lbk_ctx *c, int rank, lbk_ctx **out)
+{
+    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_multi_rank: null argument");
+    if (!is_multi(c) || rank < 0 || rank >= (int)c->subs.size()) return fail(c, LBK_ERR_ARG, "lbk_multi_rank: not a multi-device context, or no such rank");
+    *out = c->subs[rank];
+    return LBK_OK;
+}
+
+extern "C" int lbk_set_multi_threads(lbk_ctx *c, int enabled)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_set_multi_threads: null context");
+    if (!is_multi(c)) return fail(c, LBK_ERR_ARG, "lbk_set_multi_threads: not a multi-device context");
+    c->threaded = enabled != 0;
+    if (c->threaded) make_team(c);
+    return LBK_OK;
+}
+
 extern "C" int lbk_shutdown(lbk_ctx *c)
 {
     if (!c) return LBK_OK;
-    cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    for (int r = 0; r < c->nranks; ++r)
-        if (r != c->rank && c->peer_ptrs[r]) cudaIpcCloseMemHandle(c->peer_ptrs[r]);
-    if (c->comm) nccl_api()->CommDestroy(c->comm);
-    cudaFree(c->mailbox); cudaFree(c->peers_dev);
-    if (c->error_flag_host) cudaFreeHost(c->error_flag_host);
-    cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->snap);
-    cudaFree(c->rec_send); cudaFree(c->rec_all);
-    if (c->result_host) cudaFreeHost(c->result_host);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    delete c;
+    if (c->parent) return fail(c, LBK_ERR_ARG, "lbk_shutdown: a rank context goes with its multi-device context");
+    std::lock_guard<std::mutex> lk(g_life);
+    if (c->closed) return LBK_OK;
+    for (lbk_ctx *s : c->subs) { DevGuard g(s->device); if (s->stream) cudaStreamSynchronize(s->stream); s->closed = true; }
+    if (c->stream) { DevGuard g(c->device); cudaStreamSynchronize(c->stream); }
+    c->team.reset();
+    c->closed = true;
+    if (live_handles(c) == 0) destroy_tree(c);      // otherwise the last lbk_vec_free / lbk_event_destroy does it
     return LBK_OK;
 }
 
@@ -255,18 +505,25 @@ static int check_exchange_error(lbk_ctx *c)
         *c->error_flag_host = 0;
         return fail(c, LBK_ERR_NCCL, "peer exchange timed out: a rank never delivered its record (did every rank make the same call?)");
     }
+    if (c->comm && nccl_api()->CommGetAsyncError) {      // a failure NCCL noticed on its own threads
+        ncclResult_t async = ncclSuccess;
+        if (nccl_api()->CommGetAsyncError(c->comm, &async) == ncclSuccess && async != ncclSuccess && async != ncclInProgress)
+            return fail(c, LBK_ERR_NCCL, std::string("NCCL asynchronous error: ") + nccl_api()->GetErrorString(async));
+    }
     return LBK_OK;
 }
 
 extern "C" int lbk_sync(lbk_ctx *c)
 {
     if (!c) return fail(nullptr, LBK_ERR_ARG, "lbk_sync: null context");
+    LIVE(c, "lbk_sync");
+    if (is_multi(c)) return all_ranks(c, [](lbk_ctx *s, int) { return lbk_sync(s); });
     CU(c, cudaStreamSynchronize(c->stream));
     return check_exchange_error(c);
 }
 
 extern "C" const char *lbk_last_error(lbk_ctx *c) { return c ? c->err.c_str() : g_err.c_str(); }
-extern "C" void *lbk_stream(lbk_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" void *lbk_stream(lbk_ctx *c) { return !c ? nullptr : is_multi(c) ? (void *)c->subs[0]->stream : (void *)c->stream; }
 
 extern "C" int lbk_sm_count(lbk_ctx *c, int *sms)
 {
@@ -278,6 +535,10 @@ extern "C" int lbk_sm_count(lbk_ctx *c, int *sms)
 extern "C" int lbk_set_launch(lbk_ctx *c, const char *routine, int variant, int threads, int blocks_per_sm)
 {
     if (!c || !routine) return fail(c, LBK_ERR_ARG, "lbk_set_launch: null argument");
+    if (is_multi(c)) {
+        for (lbk_ctx *s : c->subs) { int st = lbk_set_launch(s, routine, variant, threads, blocks_per_sm); if (st) { c->err = s->err; return st; } }
+        return LBK_OK;
+    }
     if (variant >= kNumVariants) return fail(c, LBK_ERR_ARG, "lbk_set_launch: no such variant");
     if (threads > lbk::kMaxThreads || (threads > 0 && threads % 32 != 0))
         return fail(c, LBK_ERR_ARG, "lbk_set_launch: threads must be a multiple of 32, at most 512");
@@ -302,12 +563,14 @@ extern "C" int lbk_launch_count(lbk_ctx *c, int64_t *launches)
 {
     if (!c || !launches) return fail(c, LBK_ERR_ARG, "lbk_launch_count: null argument");
     *launches = c->launches;
+    for (lbk_ctx *s : c->subs) *launches += s->launches;
     return LBK_OK;
 }
 
 extern "C" int lbk_set_pdl(lbk_ctx *c, int enabled)
 {
     if (!c) return fail(c, LBK_ERR_ARG, "lbk_set_pdl: null context");
+    for (lbk_ctx *s : c->subs) lbk_set_pdl(s, enabled);
     c->pdl.enabled = enabled != 0;
     c->pdl.hold_stores = enabled != 2 && enabled != 3;      // 2: dependent kernels (of any kind) wait before their first load
     c->pdl.hold_loads = enabled != 3 && enabled != 4;       // 3: ... or get an ordinary launch; 4: only true dependencies do (tools/, experiments)
@@ -318,8 +581,18 @@ extern "C" int lbk_pdl_count(lbk_ctx *c, int64_t *launches)
 {
     if (!c || !launches) return fail(c, LBK_ERR_ARG, "lbk_pdl_count: null argument");
     *launches = c->pdl_launches;
+    for (lbk_ctx *s : c->subs) *launches += s->pdl_launches;
     return LBK_OK;
 }
+
+extern "C" int lbk_set_exchange_timeout(lbk_ctx *c, int64_t milliseconds)
+{
+    if (!c || milliseconds <= 0) return fail(c, LBK_ERR_ARG, "lbk_set_exchange_timeout: needs a context and a positive time");
+    for (lbk_ctx *s : c->subs) s->exchange_timeout_ns = (unsigned long long)milliseconds * 1000000ull;
+    c->exchange_timeout_ns = (unsigned long long)milliseconds * 1000000ull;
+    return LBK_OK;
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // communicator
@@ -385,9 +658,11 @@ extern "C" int lbk_comm_init(lbk_ctx *c, int nranks, int rank, const char id[128
 {
     if (!c || !id) return fail(c, LBK_ERR_ARG, "lbk_comm_init: null argument");
     if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return fail(c, LBK_ERR_ARG, "lbk_comm_init: bad rank / world size");
+    LIVE(c, "lbk_comm_init");
+    if (is_multi(c) || c->parent) return fail(c, LBK_ERR_UNSUPPORTED, "lbk_comm_init: a multi-device context already spans its ranks (one process); NCCL joins one-device contexts");
     if (c->comm) return fail(c, LBK_ERR_ARG, "lbk_comm_init: communicator already attached");
     if (!nccl_api()->handle) return fail(c, LBK_ERR_NCCL, nccl_api()->error);
-    CU(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     ncclUniqueId u;
     memcpy(&u, id, 128);
     NC(c, nccl_api()->CommInitRank(&c->comm, nranks, u, rank));
@@ -406,6 +681,10 @@ extern "C" int lbk_comm_transport(lbk_ctx *c, int *fused)
 extern "C" int lbk_set_fused_exchange(lbk_ctx *c, int enabled)
 {
     if (!c) return fail(c, LBK_ERR_ARG, "lbk_set_fused_exchange: null context");
+    if (is_multi(c) || c->parent) {
+        if (!enabled && c->nranks > 1) return fail(c, LBK_ERR_UNSUPPORTED, "lbk_set_fused_exchange: a multi-device context has no NCCL communicator; its exchange is always in-kernel");
+        return LBK_OK;
+    }
     if (enabled && !c->mailbox) return fail(c, LBK_ERR_UNSUPPORTED, "lbk_set_fused_exchange: peer mailboxes were not mapped on this communicator");
     c->fused_exchange = enabled != 0;
     return LBK_OK;
@@ -435,37 +714,70 @@ extern "C" int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t
 // ------------------------------------------------------------------------------------------------
 static int make_vec(lbk_ctx *c, void *ptr, i64 len, i64 glen, i64 off, bool owner, bool sharded, int dtype, lbk_vec **out)
 {
-    lbk_vec *v = new (std::nothrow) lbk_vec{c, (char *)ptr, len, glen, off, owner, sharded, dtype};
+    lbk_vec *v = new (std::nothrow) lbk_vec{c, (char *)ptr, len, glen, off, owner, sharded, dtype, {}, false};
     if (!v) return fail(c, LBK_ERR_NOMEM, "out of host memory");
+    ctx_ref(c);
     *out = v;
     return LBK_OK;
 }
 
 static int alloc_common(lbk_ctx *c, const char *who, i64 len, i64 glen, i64 off, bool sharded, int dtype, lbk_vec **out)
 {
-    CU(c, cudaSetDevice(c->device));
+    LIVE(c, who);
+    ON_DEVICE(c);
     void *p = nullptr;
     if (len > 0) {
+        if ((unsigned long long)len > (~0ull >> 4)) return fail(c, LBK_ERR_NOMEM, std::string(who) + ": length overflows the address space");
         // a stream-ordered allocation does not end the chain of overlapping kernels: hazards are tracked by address,
         // so a block the pool hands out again while its previous user is still running is handled like any other
 #ifdef LBK_SYNC_MALLOC      // A/B builds only (profiles/r01_criterion_matrix*.csv): plain cudaMalloc / synchronise + cudaFree
         cudaError_t e = cudaMalloc(&p, (size_t)esz(dtype) * (size_t)len);
 #else
-        cudaError_t e = cudaMallocAsync(&p, (size_t)esz(dtype) * (size_t)len, c->stream);
+        cudaError_t e = cudaMallocFromPoolAsync(&p, (size_t)esz(dtype) * (size_t)len, c->pool, c->stream);
 #endif
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, LBK_ERR_NOMEM, std::string(who) + ": cudaMallocAsync: " + cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, LBK_ERR_NOMEM, std::string(who) + ": cudaMallocFromPoolAsync: " + cudaGetErrorString(e)); }
     }
     return make_vec(c, p, len, glen, off, true, sharded, dtype, out);
+}
+
+// The handle of a multi-device context's vector: `parts` on the rank contexts (all ranks when sharded, rank 0 only
+// otherwise).  It takes the geometry of the logical vector; ptr is part 0's buffer.
+static int make_multi_vec(lbk_ctx *m, std::vector<lbk_vec *> &&parts, i64 glen, bool sharded, int dtype, bool owner, lbk_vec **out)
+{
+    lbk_vec *v = new (std::nothrow) lbk_vec{m, parts.empty() ? nullptr : parts[0]->ptr, sharded ? glen : parts[0]->len, glen, 0, owner, sharded, dtype, {}, false};
+    if (!v) { for (lbk_vec *p : parts) lbk_vec_free(p); return fail(m, LBK_ERR_NOMEM, "out of host memory"); }
+    v->parts = std::move(parts);
+    ctx_ref(m);
+    *out = v;
+    return LBK_OK;
+}
+// part of a multi-device vector on rank r (a vector that is not sharded lives on rank 0 alone)
+static inline lbk_vec *part(const lbk_vec *v, int r) { return !v ? nullptr : v->sharded ? v->parts[r] : v->parts[0]; }
+
+static int multi_alloc(lbk_ctx *m, const char *who, i64 len, bool sharded, int dtype, lbk_vec **out)
+{
+    LIVE(m, who);
+    const int n = sharded ? (int)m->subs.size() : 1;
+    std::vector<lbk_vec *> parts(n, nullptr);
+    int s = fan_out(m, n, [&](lbk_ctx *sc, int r) {
+        int64_t lo = 0, hi = len;
+        if (sharded) lbk_shard_range(len, sc->nranks, r, &lo, &hi);
+        return alloc_common(sc, who, hi - lo, len, lo, sharded && sc->nranks > 1, dtype, &parts[r]);
+    });
+    if (s) { for (lbk_vec *p : parts) lbk_vec_free(p); return s; }
+    return make_multi_vec(m, std::move(parts), len, sharded, dtype, true, out);
 }
 
 static int vec_alloc(lbk_ctx *c, int64_t len, int dtype, lbk_vec **out)
 {
     if (!c || !out || len < 0) return fail(c, LBK_ERR_ARG, "lbk_vec_alloc: bad argument");
+    if (is_multi(c)) return multi_alloc(c, "lbk_vec_alloc", len, false, dtype, out);
     return alloc_common(c, "lbk_vec_alloc", len, len, 0, false, dtype, out);
 }
 static int vec_alloc_sharded(lbk_ctx *c, int64_t global_len, int dtype, lbk_vec **out)
 {
     if (!c || !out || global_len < 0) return fail(c, LBK_ERR_ARG, "lbk_vec_alloc_sharded: bad argument");
+    if (is_multi(c)) return multi_alloc(c, "lbk_vec_alloc_sharded", global_len, true, dtype, out);
     int64_t lo, hi;
     lbk_shard_range(global_len, c->nranks, c->rank, &lo, &hi);
     return alloc_common(c, "lbk_vec_alloc_sharded", hi - lo, global_len, lo, c->nranks > 1, dtype, out);
@@ -474,6 +786,13 @@ static int vec_wrap(lbk_ctx *c, void *device_ptr, int64_t len, int dtype, lbk_ve
 {
     if (!c || !out || len < 0 || (len > 0 && !device_ptr) || ((uintptr_t)device_ptr & (uintptr_t)(esz(dtype) - 1)))
         return fail(c, LBK_ERR_ARG, "lbk_vec_wrap: bad argument (null, negative or not element aligned)");
+    LIVE(c, "lbk_vec_wrap");
+    if (is_multi(c)) {      // foreign memory is one device's: the wrapped vector lives on rank 0 (devs[0])
+        std::vector<lbk_vec *> parts(1, nullptr);
+        int s = vec_wrap(c->subs[0], device_ptr, len, dtype, &parts[0]);
+        if (s) { c->err = c->subs[0]->err; return s; }
+        return make_multi_vec(c, std::move(parts), len, false, dtype, false, out);
+    }
     return make_vec(c, device_ptr, len, len, 0, false, false, dtype, out);
 }
 extern "C" int lbk_vec_alloc(lbk_ctx *c, int64_t len, lbk_vec **out) { return vec_alloc(c, len, 0, out); }
@@ -483,27 +802,59 @@ extern "C" int lbk_vec_alloc_sharded_f64(lbk_ctx *c, int64_t glen, lbk_vec **out
 extern "C" int lbk_vec_wrap(lbk_ctx *c, void *p, int64_t len, lbk_vec **out) { return vec_wrap(c, p, len, 0, out); }
 extern "C" int lbk_vec_wrap_f64(lbk_ctx *c, void *p, int64_t len, lbk_vec **out) { return vec_wrap(c, p, len, 1, out); }
 
+// An uninitialised vector with v's length, element type and layout (sharded like v, on the same ranks): what a
+// pure routine's result is made of.
+extern "C" int lbk_vec_alloc_like(const lbk_vec *v, lbk_vec **out)
+{
+    if (!v || !out) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_alloc_like: null argument");
+    lbk_ctx *c = v->ctx;
+    if (is_multi(c)) return multi_alloc(c, "lbk_vec_alloc_like", v->global_len, v->sharded, v->dtype, out);
+    return alloc_common(c, "lbk_vec_alloc_like", v->len, v->global_len, v->shard_off, v->sharded, v->dtype, out);
+}
+
 extern "C" int lbk_vec_view(const lbk_vec *v, int64_t offset, int64_t len, lbk_vec **out)
 {
-    if (!v || !out || offset < 0 || len < 0 || offset + len > v->len)
+    if (!v || !out || offset < 0 || len < 0 || offset > v->len || len > v->len - offset)
         return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_view: window outside the vector");
     if (v->sharded) return fail(v->ctx, LBK_ERR_UNSUPPORTED, "lbk_vec_view: views of sharded vectors are not supported");
+    LIVE(v->ctx, "lbk_vec_view");
+    if (is_multi(v->ctx)) {
+        std::vector<lbk_vec *> parts(1, nullptr);
+        int s = lbk_vec_view(v->parts[0], offset, len, &parts[0]);
+        if (s) { v->ctx->err = v->parts[0]->ctx->err; return s; }
+        return make_multi_vec(v->ctx, std::move(parts), len, false, v->dtype, false, out);
+    }
     return make_vec(v->ctx, v->ptr + offset * esz(v->dtype), len, len, 0, false, false, v->dtype, out);
+}
+
+// Rank r's part of a multi-device vector, as a handle of that rank's context (lbk_multi_rank): borrowed -- it
+// stays valid as long as `v` and freeing it releases only the handle.
+extern "C" int lbk_vec_part(const lbk_vec *v, int rank, lbk_vec **out)
+{
+    if (!v || !out) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_part: null argument");
+    if (!is_multi(v->ctx) || rank < 0 || rank >= (int)v->parts.size()) return fail(v->ctx, LBK_ERR_ARG, "lbk_vec_part: not a multi-device vector, or no such part");
+    const lbk_vec *p = v->parts[rank];
+    int s = make_vec(p->ctx, p->ptr, p->len, p->global_len, p->shard_off, false, p->sharded, p->dtype, out);
+    if (!s) (*out)->borrowed = true;
+    return s;
 }
 
 extern "C" int lbk_vec_free(lbk_vec *v)
 {
     if (!v) return LBK_OK;
-    if (v->owner && v->ptr) {      // released in stream order: everything enqueued so far may still use it
-        cudaSetDevice(v->ctx->device);
+    lbk_ctx *c = v->ctx;
+    for (lbk_vec *p : v->parts) lbk_vec_free(p);
+    if (v->parts.empty() && v->owner && v->ptr) {      // released in stream order: everything enqueued so far may still use it
+        DevGuard guard(c->device);
 #ifdef LBK_SYNC_MALLOC
-        cudaStreamSynchronize(v->ctx->stream);
+        cudaStreamSynchronize(c->stream);
         cudaFree(v->ptr);
 #else
-        cudaFreeAsync(v->ptr, v->ctx->stream);
+        cudaFreeAsync(v->ptr, c->stream);
 #endif
     }
     delete v;
+    ctx_unref(c);          // the last handle of a context that was shut down takes the context with it
     return LBK_OK;
 }
 
@@ -515,12 +866,29 @@ extern "C" int lbk_vec_len(const lbk_vec *v, int64_t *local_len, int64_t *global
     if (shard_offset) *shard_offset = v->shard_off;
     return LBK_OK;
 }
+extern "C" int lbk_vec_is_sharded(const lbk_vec *v) { return v && v->sharded ? 1 : 0; }
 extern "C" int lbk_vec_elem_size(const lbk_vec *v) { return v ? esz(v->dtype) : 0; }
 extern "C" void *lbk_vec_ptr(const lbk_vec *v) { return v ? (void *)v->ptr : nullptr; }
 
+// A multi-device vector's transfers scatter / gather one host buffer: every rank moves its own block on its own
+// stream (N copy engines, N PCIe links), `len` counting logical elements from the start of the vector.
+static int multi_transfer(lbk_vec *v, const char *host_c, char *host, int64_t len, bool up)
+{
+    lbk_ctx *m = v->ctx;
+    const int n = v->sharded ? (int)m->subs.size() : 1;
+    return fan_out(m, n, [&](lbk_ctx *, int r) {
+        lbk_vec *p = v->parts[r];
+        const i64 lo = p->shard_off, cnt = std::max<i64>(0, std::min<i64>(len, lo + p->len) - lo);
+        if (cnt <= 0) return (int)LBK_OK;
+        return up ? lbk_vec_upload_async(p, host_c + lo * esz(v->dtype), cnt) : lbk_vec_download_async(p, host + lo * esz(v->dtype), cnt);
+    });
+}
+
 extern "C" int lbk_vec_upload_async(lbk_vec *v, const void *host, int64_t len)
 {
-    if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_upload: bad argument");
+    if (!v || len < 0 || len > (is_multi(v->ctx) ? v->global_len : v->len) || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_upload: bad argument");
+    LIVE(v->ctx, "lbk_vec_upload");
+    if (is_multi(v->ctx)) return multi_transfer(v, (const char *)host, nullptr, len, true);
     if (len) { lbk_pdl::interrupt(v->ctx->pdl); CU(v->ctx, cudaMemcpyAsync(v->ptr, host, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream)); }
     return LBK_OK;
 }
@@ -531,7 +899,9 @@ extern "C" int lbk_vec_upload(lbk_vec *v, const void *host, int64_t len)
 }
 extern "C" int lbk_vec_download_async(const lbk_vec *v, void *host, int64_t len)
 {
-    if (!v || len < 0 || len > v->len || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_download: bad argument");
+    if (!v || len < 0 || len > (is_multi(v->ctx) ? v->global_len : v->len) || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_download: bad argument");
+    LIVE(v->ctx, "lbk_vec_download");
+    if (is_multi(v->ctx)) return multi_transfer(const_cast<lbk_vec *>(v), nullptr, (char *)host, len, false);
     if (len) { lbk_pdl::interrupt(v->ctx->pdl); CU(v->ctx, cudaMemcpyAsync(host, v->ptr, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyDeviceToHost, v->ctx->stream)); }
     return LBK_OK;
 }
@@ -544,10 +914,17 @@ extern "C" int lbk_vec_download(const lbk_vec *v, void *host, int64_t len)
 extern "C" int lbk_vec_clone(const lbk_vec *v, lbk_vec **out)
 {
     if (!v || !out) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_clone: null argument");
+    LIVE(v->ctx, "lbk_vec_clone");
+    if (is_multi(v->ctx)) {
+        lbk_ctx *m = v->ctx;
+        std::vector<lbk_vec *> parts(v->parts.size(), nullptr);
+        int s = fan_out(m, (int)parts.size(), [&](lbk_ctx *, int r) { return lbk_vec_clone(v->parts[r], &parts[r]); });
+        if (s) { for (lbk_vec *p : parts) lbk_vec_free(p); return s; }
+        return make_multi_vec(m, std::move(parts), v->global_len, v->sharded, v->dtype, true, out);
+    }
     lbk_vec *w = nullptr;
-    int s = vec_alloc(v->ctx, v->len, v->dtype, &w);
+    int s = alloc_common(v->ctx, "lbk_vec_clone", v->len, v->global_len, v->shard_off, v->sharded, v->dtype, &w);
     if (s) return s;
-    w->global_len = v->global_len; w->shard_off = v->shard_off; w->sharded = v->sharded;
     if (v->len) {
         s = device_copy(v->ctx, w->ptr, v->ptr, v->len, v->dtype);
         if (s) { lbk_vec_free(w); return s; }
@@ -561,9 +938,11 @@ static int stream_grid(lbk_ctx *c, i64 n, int threads) { return (int)std::max<i6
 extern "C" int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, double lo, double hi)
 {
     if (!v) return fail(nullptr, LBK_ERR_ARG, "lbk_vec_fill_hash: null vector");
-    if (!v->len) return LBK_OK;
     lbk_ctx *c = v->ctx;
-    CU(c, cudaSetDevice(c->device));
+    LIVE(c, "lbk_vec_fill_hash");
+    if (is_multi(c)) return fan_out(c, (int)v->parts.size(), [&](lbk_ctx *, int r) { return lbk_vec_fill_hash(v->parts[r], seed, lo, hi); });
+    if (!v->len) return LBK_OK;
+    ON_DEVICE(c);
     lbk_pdl::interrupt(c->pdl);
     const int grid = stream_grid(c, v->len, 256);
     if (v->dtype) lbk::fill_hash_kernel<double><<<grid, 256, 0, c->stream>>>((double *)v->ptr, v->len, v->shard_off, seed, lo, hi - lo);
@@ -572,18 +951,34 @@ extern "C" int lbk_vec_fill_hash(lbk_vec *v, uint64_t seed, double lo, double hi
     return LBK_OK;
 }
 
+// Page-locked host memory for the transfers above: lbk_host_alloc makes some, lbk_host_register pins memory the
+// caller already owns (a Data.Vector.Storable buffer, a numpy array) for the lifetime of the registration, so an
+// upload from it runs at the rate of a pinned copy instead of being staged through the driver's bounce buffer.
 extern "C" int lbk_host_alloc(int64_t nbytes, void **host)
 {
     if (!host || nbytes < 0) return fail(nullptr, LBK_ERR_ARG, "lbk_host_alloc: bad argument");
     *host = nullptr;
     if (nbytes == 0) return LBK_OK;
-    cudaError_t e = cudaHostAlloc(host, (size_t)nbytes, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(host, (size_t)nbytes, cudaHostAllocPortable);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, LBK_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
     return LBK_OK;
 }
 extern "C" int lbk_host_free(void *host)
 {
     if (host) CU(nullptr, cudaFreeHost(host));
+    return LBK_OK;
+}
+extern "C" int lbk_host_register(void *host, int64_t nbytes)
+{
+    if (!host || nbytes <= 0) return fail(nullptr, LBK_ERR_ARG, "lbk_host_register: bad argument");
+    cudaError_t e = cudaHostRegister(host, (size_t)nbytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, e == cudaErrorMemoryAllocation ? LBK_ERR_NOMEM : LBK_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    return LBK_OK;
+}
+extern "C" int lbk_host_unregister(void *host)
+{
+    if (!host) return fail(nullptr, LBK_ERR_ARG, "lbk_host_unregister: null pointer");
+    CU(nullptr, cudaHostUnregister(host));
     return LBK_OK;
 }
 
@@ -593,37 +988,77 @@ extern "C" int lbk_host_free(void *host)
 extern "C" int lbk_event_create(lbk_ctx *c, lbk_event **out)
 {
     if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_event_create: null argument");
-    lbk_event *e = new (std::nothrow) lbk_event{c, nullptr};
+    LIVE(c, "lbk_event_create");
+    lbk_event *e = new (std::nothrow) lbk_event{c, nullptr, {}};
     if (!e) return fail(c, LBK_ERR_NOMEM, "out of host memory");
-    cudaError_t ce = cudaEventCreate(&e->ev);
-    if (ce != cudaSuccess) { delete e; return fail(c, LBK_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(ce)); }
+    if (is_multi(c)) {         // one event per rank, each on its own device's stream
+        for (lbk_ctx *s : c->subs) {
+            lbk_event *pe = nullptr;
+            int st = lbk_event_create(s, &pe);
+            if (st) { c->err = s->err; for (lbk_event *q : e->parts) lbk_event_destroy(q); delete e; return st; }
+            e->parts.push_back(pe);
+        }
+    } else {
+        DevGuard guard(c->device);
+        cudaError_t ce = guard.err == cudaSuccess ? cudaEventCreate(&e->ev) : guard.err;
+        if (ce != cudaSuccess) { delete e; return fail(c, LBK_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(ce)); }
+    }
+    ctx_ref(c);
     *out = e;
     return LBK_OK;
 }
 extern "C" int lbk_event_record(lbk_event *e)
 {
     if (!e) return fail(nullptr, LBK_ERR_ARG, "lbk_event_record: null event");
+    LIVE(e->ctx, "lbk_event_record");
+    if (!e->parts.empty()) return all_ranks(e->ctx, [&](lbk_ctx *, int r) { return lbk_event_record(e->parts[r]); });
+    ON_DEVICE(e->ctx);
     lbk_pdl::interrupt(e->ctx->pdl);
     CU(e->ctx, cudaEventRecord(e->ev, e->ctx->stream));
     return LBK_OK;
 }
+// Everything enqueued on `c` after this call waits for `e`.  With multi-device contexts rank r waits for the
+// event's rank-r part (both sides must then be multi-device contexts over the same devices).
 extern "C" int lbk_wait_event(lbk_ctx *c, lbk_event *e)
 {
     if (!c || !e) return fail(c, LBK_ERR_ARG, "lbk_wait_event: null argument");
+    LIVE(c, "lbk_wait_event");
+    if (is_multi(c) != !e->parts.empty() || (is_multi(c) && c->subs.size() != e->parts.size()))
+        return fail(c, LBK_ERR_ARG, "lbk_wait_event: context and event must both be single-device, or multi-device over the same ranks");
+    if (is_multi(c)) return all_ranks(c, [&](lbk_ctx *s, int r) { return lbk_wait_event(s, e->parts[r]); });
+    ON_DEVICE(c);
     lbk_pdl::interrupt(c->pdl);
     CU(c, cudaStreamWaitEvent(c->stream, e->ev, 0));
     return LBK_OK;
 }
+// Multi-device events: the LONGEST of the ranks' own device times (every rank's pair brackets the same calls).
 extern "C" int lbk_event_elapsed_ms(lbk_event *a, lbk_event *b, float *ms)
 {
     if (!a || !b || !ms) return fail(nullptr, LBK_ERR_ARG, "lbk_event_elapsed_ms: null argument");
+    if (a->parts.size() != b->parts.size()) return fail(b->ctx, LBK_ERR_ARG, "lbk_event_elapsed_ms: events of different contexts");
+    if (!a->parts.empty()) {
+        float worst = 0.f;
+        for (size_t r = 0; r < a->parts.size(); ++r) {
+            float t = 0.f;
+            int s = lbk_event_elapsed_ms(a->parts[r], b->parts[r], &t);
+            if (s) { b->ctx->err = b->parts[r]->ctx->err; return s; }
+            worst = std::max(worst, t);
+        }
+        *ms = worst;
+        return LBK_OK;
+    }
     CU(b->ctx, cudaEventSynchronize(b->ev));
     CU(b->ctx, cudaEventElapsedTime(ms, a->ev, b->ev));
     return LBK_OK;
 }
 extern "C" int lbk_event_destroy(lbk_event *e)
 {
-    if (e) { cudaEventDestroy(e->ev); delete e; }
+    if (!e) return LBK_OK;
+    lbk_ctx *c = e->ctx;
+    for (lbk_event *p : e->parts) lbk_event_destroy(p);
+    if (e->ev) cudaEventDestroy(e->ev);
+    delete e;
+    ctx_unref(c);
     return LBK_OK;
 }
 
@@ -656,7 +1091,7 @@ extern "C" int lbk_shard_span(int64_t global_len, int nranks, int rank, int64_t 
     int s = lbk_shard_range(global_len, nranks, rank, &lo, &hi);
     if (s) return s;
     if (n < 0 || inc < 1 || !first || !count || !offset) return fail(nullptr, LBK_ERR_ARG, "lbk_shard_span: bad argument");
-    if (n > 0 && 1 + (n - 1) * inc > global_len) return fail(nullptr, LBK_ERR_RANGE, "lbk_shard_span: 1+(n-1)*inc exceeds the vector");
+    if (n > 0 && span_exceeds(n, inc, global_len)) return fail(nullptr, LBK_ERR_RANGE, "lbk_shard_span: 1+(n-1)*inc exceeds the vector");
     i64 a = 0, b = 0, c2 = 0;
     if (n > 0) shard_span(lo, hi, n, inc, &a, &b, &c2);
     *first = a; *count = b; *offset = c2;
@@ -669,6 +1104,7 @@ static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, int dtyp
     if (!v) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
     if (v->ctx != c) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
     if (v->dtype != dtype) return fail(c, LBK_ERR_ARG, std::string(who) + (dtype ? ": needs a double-precision vector" : ": needs a single-precision vector"));
+    LIVE(c, who);
     op->v = v; op->inc = inc; op->i0 = 0; op->n_local = n; op->base = 0;
     if (n <= 0) { op->n_local = 0; return LBK_OK; }
     if (v->sharded) {
@@ -676,12 +1112,27 @@ static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, int dtyp
         // keep every pairing on one rank as long as both operands are partitioned alike (checked by the caller);
         // negative ones pair x[i] with y[n-1-i] across devices and zero replicates one rank's element: refused.
         if (inc < 1) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take positive increments only");
-        if (1 + (n - 1) * inc > v->global_len) return fail(c, LBK_ERR_RANGE, std::string(who) + ": 1+(n-1)*inc exceeds the vector");
-        shard_span(v->shard_off, v->shard_off + v->len, n, inc, &op->i0, &op->n_local, &op->base);
+        if (span_exceeds(n, inc, v->global_len)) return fail(c, LBK_ERR_RANGE, std::string(who) + ": 1+(n-1)*inc exceeds the vector");
+        shard_span(v->shard_off, v->shard_off + v->len, n, n == 1 ? 1 : inc, &op->i0, &op->n_local, &op->base);   // n == 1: the increment is never applied
         return LBK_OK;
     }
-    const i64 span = 1 + (n - 1) * iabs64(inc);
-    if (span > v->len) return fail(c, LBK_ERR_RANGE, std::string(who) + ": 1+(n-1)|inc| exceeds the vector");
+    if (span_exceeds(n, inc, v->len)) return fail(c, LBK_ERR_RANGE, std::string(who) + ": 1+(n-1)|inc| exceeds the vector");
+    return LBK_OK;
+}
+
+// A call on a multi-device context: its vectors must all be that context's, and all sharded (the call runs on
+// every rank) or all whole (it runs on rank 0, with the full increment semantics of a single device).
+static int multi_count(lbk_ctx *m, const char *who, std::initializer_list<const lbk_vec *> vs, int *count)
+{
+    LIVE(m, who);
+    int sharded = 0, whole = 0;
+    for (const lbk_vec *v : vs) {
+        if (!v) continue;
+        if (v->ctx != m) return fail(m, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
+        (v->sharded ? sharded : whole)++;
+    }
+    if (sharded && whole) return fail(m, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded and unsharded vectors cannot be mixed in one call");
+    *count = sharded ? (int)m->subs.size() : 1;
     return LBK_OK;
 }
 
@@ -843,9 +1294,11 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
 extern "C" int lbk_vec_fill(lbk_vec *v, double value)
 {
     if (!v) return fail(nullptr, LBK_ERR_ARG, "lbk_vec_fill: null vector");
-    if (!v->len) return LBK_OK;
     lbk_ctx *c = v->ctx;
-    CU(c, cudaSetDevice(c->device));
+    LIVE(c, "lbk_vec_fill");
+    if (is_multi(c)) return fan_out(c, (int)v->parts.size(), [&](lbk_ctx *, int r) { return lbk_vec_fill(v->parts[r], value); });
+    if (!v->len) return LBK_OK;
+    ON_DEVICE(c);
     if (v->dtype) return launch_map_unit(c, R_FILL, lbk::FillF<double>{value}, (const double *)nullptr, (const double *)nullptr, (double *)v->ptr, (double *)nullptr, v->len);
     return launch_map_unit(c, R_FILL, lbk::FillF<float>{(float)value}, (const float *)nullptr, (const float *)nullptr, (float *)v->ptr, (float *)nullptr, v->len);
 }
@@ -853,7 +1306,7 @@ extern "C" int lbk_vec_fill(lbk_vec *v, double value)
 static int device_copy(lbk_ctx *c, void *dst, const void *src, i64 count, int dtype)
 {
     if (count <= 0) return LBK_OK;
-    CU(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     if (dtype) return launch_map_unit(c, R_COPY, lbk::CopyF<double>{}, (const double *)src, (const double *)nullptr, (double *)nullptr, (double *)dst, count);
     return launch_map_unit(c, R_COPY, lbk::CopyF<float>{}, (const float *)src, (const float *)nullptr, (float *)nullptr, (float *)dst, count);
 }
@@ -893,7 +1346,7 @@ static int map_dispatch(lbk_ctx *c, int rid, const F &f, i64 n, const Operand &X
 {
     using T = typename F::Scalar;
     if (n <= 0) return LBK_OK;
-    CU(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     const bool use_x = F::RX || F::WX, use_y = F::RY || F::WY;
     const T *xr = use_x ? (const T *)X.ptr() : nullptr;
     const T *yr = use_y ? (const T *)Y.ptr() : nullptr;
@@ -936,6 +1389,12 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
     constexpr int dtype = sizeof(T) == 8 ? 1 : 0;
     if (!c) return fail(nullptr, LBK_ERR_ARG, std::string(who) + ": null context");
     const bool use_x = F::RX || F::WX, use_y = F::RY || F::WY;
+    if (is_multi(c)) {
+        int count, st = multi_count(c, who, {use_x ? x : nullptr, use_y ? y : nullptr, xo, yo}, &count);
+        if (st) return st;
+        if ((use_x && !x) || (use_y && !y)) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
+        return fan_out(c, count, [&](lbk_ctx *sc, int r) { return map_entry<F>(sc, who, rid, f, n, part(x, r), incx, part(y, r), incy, part(xo, r), part(yo, r)); });
+    }
     Operand X{}, Y{};
     int s;
     if (use_x && (s = check_operand(c, who, x, dtype, incx, n, &X))) return s;
@@ -945,12 +1404,14 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
     T *xw = nullptr, *yw = nullptr;
     if (F::WX) {
         lbk_vec *d = xo ? xo : const_cast<lbk_vec *>(x);
-        if (d->ctx != c || d->len != x->len || d->dtype != dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
+        if (d->ctx != c || d->len != x->len || d->dtype != dtype || d->sharded != x->sharded || d->shard_off != x->shard_off)
+            return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length, type and shard layout");
         xw = (T *)d->ptr;
     }
     if (F::WY) {
         lbk_vec *d = yo ? yo : const_cast<lbk_vec *>(y);
-        if (d->ctx != c || d->len != y->len || d->dtype != dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
+        if (d->ctx != c || d->len != y->len || d->dtype != dtype || d->sharded != y->sharded || d->shard_off != y->shard_off)
+            return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length, type and shard layout");
         yw = (T *)d->ptr;
     }
     // A written span must not overlap any OTHER span this call touches (reads may alias each other freely,
@@ -1010,7 +1471,7 @@ template <class Op>
 static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &X, const Operand *Y, double sb, void *out)
 {
     using T = typename Op::Scalar;
-    CU(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     const bool exchange = c->nranks > 1 && X.v->sharded;
     const bool fused = exchange && c->fused_exchange;
     const i64 nl = X.n_local;
@@ -1025,7 +1486,9 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         if (++c->exchange_seq == 0) ++c->exchange_seq;    // tag 0 means "empty slot"
         fa.peers = c->peers_dev; fa.nranks = c->nranks; fa.rank = c->rank; fa.seq = c->exchange_seq;
         fa.error_flag = c->error_flag_dev;
+        fa.timeout_ns = c->exchange_timeout_ns;
     }
+    if (exchange && !fused && !c->comm) return fail(c, LBK_ERR_UNSUPPORTED, "sharded reduction: this context has neither peer mailboxes nor an NCCL communicator");
     fa.n_global = n;
     fa.sb = sb;
     fa.out = out;
@@ -1100,7 +1563,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
 template <class T>
 static int store_value(lbk_ctx *c, void *out, T v)
 {
-    CU(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     lbk_pdl::interrupt(c->pdl);
     unsigned *flag = nullptr;
     if (out == c->result_dev) {
@@ -1126,6 +1589,7 @@ static int dot_common(lbk_ctx *c, const char *who, int rid, int kind, i64 n, flo
                       const lbk_vec *y, i64 incy, void *out_dev)
 {
     constexpr int dtype = sizeof(T) == 8 ? 1 : 0;
+    LIVE(c, who);
     Operand X{}, Y{};
     int s;
     if ((s = check_operand(c, who, x, dtype, incx, n, &X))) return s;
@@ -1167,6 +1631,7 @@ template <class T>
 static int ivi_common(lbk_ctx *c, const char *who, int rid, i64 n, const lbk_vec *x, i64 incx, void *out_dev)
 {
     constexpr int dtype = sizeof(T) == 8 ? 1 : 0;
+    LIVE(c, who);
     if (!x) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
     if (x->ctx != c) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
     if (x->dtype != dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector has the wrong element type");
@@ -1180,50 +1645,67 @@ static int ivi_common(lbk_ctx *c, const char *who, int rid, i64 n, const lbk_vec
     return reduce_dispatch<lbk::IamaxOp<T>>(c, rid, 2, n, X, nullptr, 0.0, out_dev);
 }
 
+// A reduction on a multi-device context.  call(rank context, rank, out) enqueues the routine on one rank with
+// `out` as the device-visible address of its scalar: every rank computes the same bits (the records are folded
+// in rank order everywhere); the caller gets rank 0's -- through rank 0's mapped result slot (synchronous
+// forms, `out_host`) or in out_vec[0] (enqueue-only forms; out_vec is an unsharded vector, i.e. on rank 0,
+// and the other ranks park their copy in a private sink).
+template <class R, class Call>
+static int multi_reduce(lbk_ctx *m, const char *who, std::initializer_list<const lbk_vec *> vs, lbk_vec *out_vec, int out_dtype,
+                        i64 out_bytes, R *out_host, Call call)
+{
+    int count, s = multi_count(m, who, vs, &count);
+    if (s) return s;
+    for (const lbk_vec *v : vs)
+        if (!v) return fail(m, LBK_ERR_ARG, std::string(who) + ": null vector");
+    void *out0 = nullptr;
+    if (!out_host) {
+        if (!out_vec || out_vec->ctx != m || out_vec->sharded) return fail(m, LBK_ERR_ARG, std::string(who) + ": the result vector must be an unsharded vector of this context");
+        if ((s = check_out_vec(m->subs[0], who, out_vec->parts[0], out_dtype, out_bytes))) { m->err = m->subs[0]->err; return s; }
+        out0 = out_vec->parts[0]->ptr;
+    }
+    s = fan_out(m, count, [&](lbk_ctx *sc, int r) { return call(sc, r, out_host ? sc->result_dev : (r == 0 ? out0 : sc->sink)); });
+    if (!out_host) return s;
+    s = finish_sync(m->subs[0], s, out_host);
+    if (s && m->err.empty()) m->err = m->subs[0]->err;
+    return s;
+}
+
 #define LBK_REDUCTIONS(P, T, DT, IPFX)                                                                                         \
     extern "C" int lbk_##P##dot(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, T *out)  \
     {                                                                                                                          \
         if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_" #P "dot: null argument");                                           \
+        if (is_multi(c)) return multi_reduce<T>(c, "lbk_" #P "dot", {x, y}, nullptr, DT, sizeof(T), out, [&](lbk_ctx *sc, int r, void *o) { \
+            return dot_common<T>(sc, "lbk_" #P "dot", R_DOT, 0, n, 0.f, part(x, r), incx, part(y, r), incy, o); });             \
         return finish_sync(c, dot_common<T>(c, "lbk_" #P "dot", R_DOT, 0, n, 0.f, x, incx, y, incy, c->result_dev), out);       \
     }                                                                                                                          \
     extern "C" int lbk_##P##dot_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *o) \
     {                                                                                                                          \
         if (!c) return fail(c, LBK_ERR_ARG, "lbk_" #P "dot_async: null context");                                              \
+        if (is_multi(c)) return multi_reduce<T>(c, "lbk_" #P "dot_async", {x, y}, o, DT, sizeof(T), nullptr, [&](lbk_ctx *sc, int r, void *od) { \
+            return dot_common<T>(sc, "lbk_" #P "dot_async", R_DOT, 0, n, 0.f, part(x, r), incx, part(y, r), incy, od); });      \
         int s = check_out_vec(c, "lbk_" #P "dot_async", o, DT, sizeof(T));                                                     \
         return s ? s : dot_common<T>(c, "lbk_" #P "dot_async", R_DOT, 0, n, 0.f, x, incx, y, incy, o->ptr);                     \
     }                                                                                                                          \
-    extern "C" int lbk_##P##asum(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, T *out)                                 \
+    LBK_IVI(P##asum, T, T, DT, sizeof(T), R_ASUM)                                                                              \
+    LBK_IVI(P##nrm2, T, T, DT, sizeof(T), R_NRM2)                                                                              \
+    LBK_IVI(IPFX##amax, T, int64_t, DT, 8, R_IAMAX)
+// one-vector reductions: NAME(ctx, n, x, incx, &out) and NAME_async(ctx, n, x, incx, out_vec)
+#define LBK_IVI(NAME, T, RT, DT, OUTBYTES, RID)                                                                                \
+    extern "C" int lbk_##NAME(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, RT *out)                                   \
     {                                                                                                                          \
-        if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_" #P "asum: null argument");                                          \
-        return finish_sync(c, ivi_common<T>(c, "lbk_" #P "asum", R_ASUM, n, x, incx, c->result_dev), out);                      \
+        if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_" #NAME ": null argument");                                           \
+        if (is_multi(c)) return multi_reduce<RT>(c, "lbk_" #NAME, {x}, nullptr, DT, OUTBYTES, out, [&](lbk_ctx *sc, int r, void *o) { \
+            return ivi_common<T>(sc, "lbk_" #NAME, RID, n, part(x, r), incx, o); });                                           \
+        return finish_sync(c, ivi_common<T>(c, "lbk_" #NAME, RID, n, x, incx, c->result_dev), out);                             \
     }                                                                                                                          \
-    extern "C" int lbk_##P##nrm2(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, T *out)                                 \
+    extern "C" int lbk_##NAME##_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)                        \
     {                                                                                                                          \
-        if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_" #P "nrm2: null argument");                                          \
-        return finish_sync(c, ivi_common<T>(c, "lbk_" #P "nrm2", R_NRM2, n, x, incx, c->result_dev), out);                      \
-    }                                                                                                                          \
-    extern "C" int lbk_##IPFX##amax(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, int64_t *out)                        \
-    {                                                                                                                          \
-        if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_" #IPFX "amax: null argument");                                       \
-        return finish_sync(c, ivi_common<T>(c, "lbk_" #IPFX "amax", R_IAMAX, n, x, incx, c->result_dev), out);                  \
-    }                                                                                                                          \
-    extern "C" int lbk_##P##asum_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)                       \
-    {                                                                                                                          \
-        if (!c) return fail(c, LBK_ERR_ARG, "lbk_" #P "asum_async: null context");                                             \
-        int s = check_out_vec(c, "lbk_" #P "asum_async", o, DT, sizeof(T));                                                    \
-        return s ? s : ivi_common<T>(c, "lbk_" #P "asum_async", R_ASUM, n, x, incx, o->ptr);                                    \
-    }                                                                                                                          \
-    extern "C" int lbk_##P##nrm2_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)                       \
-    {                                                                                                                          \
-        if (!c) return fail(c, LBK_ERR_ARG, "lbk_" #P "nrm2_async: null context");                                             \
-        int s = check_out_vec(c, "lbk_" #P "nrm2_async", o, DT, sizeof(T));                                                    \
-        return s ? s : ivi_common<T>(c, "lbk_" #P "nrm2_async", R_NRM2, n, x, incx, o->ptr);                                    \
-    }                                                                                                                          \
-    extern "C" int lbk_##IPFX##amax_async(lbk_ctx *c, int64_t n, const lbk_vec *x, int64_t incx, lbk_vec *o)                    \
-    {                                                                                                                          \
-        if (!c) return fail(c, LBK_ERR_ARG, "lbk_" #IPFX "amax_async: null context");                                          \
-        int s = check_out_vec(c, "lbk_" #IPFX "amax_async", o, DT, 8);                                                         \
-        return s ? s : ivi_common<T>(c, "lbk_" #IPFX "amax_async", R_IAMAX, n, x, incx, o->ptr);                                \
+        if (!c) return fail(c, LBK_ERR_ARG, "lbk_" #NAME "_async: null context");                                              \
+        if (is_multi(c)) return multi_reduce<RT>(c, "lbk_" #NAME "_async", {x}, o, DT, OUTBYTES, nullptr, [&](lbk_ctx *sc, int r, void *od) { \
+            return ivi_common<T>(sc, "lbk_" #NAME "_async", RID, n, part(x, r), incx, od); });                                 \
+        int s = check_out_vec(c, "lbk_" #NAME "_async", o, DT, OUTBYTES);                                                      \
+        return s ? s : ivi_common<T>(c, "lbk_" #NAME "_async", RID, n, x, incx, o->ptr);                                        \
     }
 LBK_REDUCTIONS(s, float, 0, is)
 LBK_REDUCTIONS(d, double, 1, id)
@@ -1231,12 +1713,16 @@ LBK_REDUCTIONS(d, double, 1, id)
 extern "C" int lbk_sdsdot(lbk_ctx *c, int64_t n, float sb, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, float *out)
 {
     if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_sdsdot: null argument");
+    if (is_multi(c)) return multi_reduce<float>(c, "lbk_sdsdot", {x, y}, nullptr, 0, sizeof(float), out, [&](lbk_ctx *sc, int r, void *o) {
+        return dot_common<float>(sc, "lbk_sdsdot", R_SDSDOT, 3, n, sb, part(x, r), incx, part(y, r), incy, o); });
     return finish_sync(c, dot_common<float>(c, "lbk_sdsdot", R_SDSDOT, 3, n, sb, x, incx, y, incy, c->result_dev), out);
 }
 
 extern "C" int lbk_sdsdot_async(lbk_ctx *c, int64_t n, float sb, const lbk_vec *x, int64_t incx, const lbk_vec *y, int64_t incy, lbk_vec *o)
 {
     if (!c) return fail(c, LBK_ERR_ARG, "lbk_sdsdot_async: null context");
+    if (is_multi(c)) return multi_reduce<float>(c, "lbk_sdsdot_async", {x, y}, o, 0, sizeof(float), nullptr, [&](lbk_ctx *sc, int r, void *od) {
+        return dot_common<float>(sc, "lbk_sdsdot_async", R_SDSDOT, 3, n, sb, part(x, r), incx, part(y, r), incy, od); });
     int s = check_out_vec(c, "lbk_sdsdot_async", o, 0, sizeof(float));
     return s ? s : dot_common<float>(c, "lbk_sdsdot_async", R_SDSDOT, 3, n, sb, x, incx, y, incy, o->ptr);
 }
@@ -1251,6 +1737,13 @@ static int scal_common(lbk_ctx *c, const char *who, i64 n, T a, const lbk_vec *x
 {
     if (!c) return fail(nullptr, LBK_ERR_ARG, std::string(who) + ": null context");
     if (!x) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
+    if (is_multi(c)) {
+        int count, st = multi_count(c, who, {x, xout}, &count);
+        if (st) return st;
+        return fan_out(c, count, [&](lbk_ctx *sc, int r) { return scal_common<T>(sc, who, n, a, part(x, r), incx, part(xout, r)); });
+    }
+    LIVE(c, who);
+    if (x->ctx != c || (xout && xout->ctx != c)) return fail(c, LBK_ERR_ARG, std::string(who) + ": vector belongs to another context");
     i64 n_eff = n, inc_eff = incx;
     if (n > 0 && incx <= 0) {
         if (incx == 0 || n == 1) { n_eff = 1; inc_eff = 1; }
@@ -1271,13 +1764,20 @@ static int rotm_common(lbk_ctx *c, const char *who, i64 n, const lbk_vec *x, i64
 {
     if (!c) return fail(nullptr, LBK_ERR_ARG, std::string(who) + ": null context");
     if (!p) return fail(c, LBK_ERR_ARG, std::string(who) + ": null param");
+    if (is_multi(c)) {
+        int count, st = multi_count(c, who, {x, y, xout, yout}, &count);
+        if (st) return st;
+        if (!x || !y) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
+        return fan_out(c, count, [&](lbk_ctx *sc, int r) { return rotm_common<T>(sc, who, n, part(x, r), incx, part(y, r), incy, p, part(xout, r), part(yout, r)); });
+    }
+    LIVE(c, who);
     const T flag = p[0];
     if (flag == (T)-2) {          // FLAGNEG2: the inputs come back as they are (Single.hs:473)
         const lbk_vec *src[2] = {x, y};
         lbk_vec *dst[2] = {xout, yout};
         for (int i = 0; i < 2; ++i)
             if (dst[i] && src[i] && dst[i]->ptr != src[i]->ptr && src[i]->len) {
-                if (dst[i]->len != src[i]->len || dst[i]->dtype != src[i]->dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
+                if (dst[i]->ctx != c || src[i]->ctx != c || dst[i]->len != src[i]->len || dst[i]->dtype != src[i]->dtype) return fail(c, LBK_ERR_ARG, std::string(who) + ": output vector must match the input's length and type");
                 int s = device_copy(c, dst[i]->ptr, src[i]->ptr, src[i]->len, src[i]->dtype);
                 if (s) return s;
             }
@@ -1337,6 +1837,37 @@ extern "C" int lbk_combine_records(int kind, int is_f64, const lbk_record *recs,
         v = is_f64 ? lbk::nrm2_finish(a.f[0], a.f[1], a.f[2], (double)lbk::Blue<double>::sbig, (double)lbk::Blue<double>::ssml)
                    : lbk::nrm2_finish(a.f[0], a.f[1], a.f[2], (double)lbk::Blue<float>::sbig, (double)lbk::Blue<float>::ssml);
     *fout = is_f64 ? v : (double)(float)v;
+    return LBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the launcher threads of lbk_team.hpp on their own (no device needed): tests/test_team.py
+// ------------------------------------------------------------------------------------------------
+// Runs `jobs` jobs on a team of `nranks`; job j makes rank r add (j+1)*(r+1) to its own counter and fail with
+// status 100+r when j == fail_at (-1: never).  Returns through *sum the total of all counters, through
+// *first_status the status the failing job reported (0 if none), and checks that every job ran exactly once
+// per rank (LBK_ERR_ARG otherwise).  pause_us > 0 idles between jobs so that the members go to sleep and
+// have to be woken.
+extern "C" int lbk_team_selftest(int nranks, int jobs, int fail_at, int pause_us, int64_t *sum, int *first_status)
+{
+    if (nranks < 1 || nranks > 64 || jobs < 0 || !sum || !first_status) return fail(nullptr, LBK_ERR_ARG, "lbk_team_selftest: bad argument");
+    std::vector<int64_t> counter(nranks, 0), runs(nranks, 0);
+    std::atomic<int> started{0};
+    *first_status = 0;
+    {
+        lbk_team::Team team(nranks, [&](int) { started.fetch_add(1); });
+        for (int j = 0; j < jobs; ++j) {
+            const int st = team.run([&](int r) { counter[r] += (int64_t)(j + 1) * (r + 1); runs[r]++; return j == fail_at ? 100 + r : 0; });
+            if (st && !*first_status) *first_status = st;
+            if (pause_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(pause_us));
+        }
+    }
+    *sum = 0;
+    for (int r = 0; r < nranks; ++r) {
+        *sum += counter[r];
+        if (runs[r] != jobs) return fail(nullptr, LBK_ERR_ARG, "lbk_team_selftest: a rank missed or repeated a job");
+    }
+    if (started.load() != nranks - 1) return fail(nullptr, LBK_ERR_ARG, "lbk_team_selftest: on_start did not run once per member");
     return LBK_OK;
 }
 

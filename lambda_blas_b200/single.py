@@ -40,8 +40,7 @@ def _r(v: DVector):
 
 def _like(v: DVector) -> DVector:
     """An uninitialised vector with v's length, type and shard layout."""
-    c = v.ctx
-    return c.alloc_sharded(v.global_len, v.dtype) if v.global_len != len(v) or v.shard_offset else c.alloc(len(v), v.dtype)
+    return v.like()
 
 
 def _fn(v: DVector, name: str):

@@ -42,9 +42,15 @@ class Context:
         return self._h
 
     def close(self) -> None:
+        """lbk_shutdown: vectors and events that are still alive keep the native context until they are freed."""
         if getattr(self, "_h", None) is not None:
-            _ffi.lib().lbk_shutdown(self._h)
+            if getattr(self, "_borrowed", None) is None:      # a rank context goes with its multi-device context
+                _ffi.lib().lbk_shutdown(self._h)
             self._h = None
+
+    def set_exchange_timeout(self, milliseconds: int) -> None:
+        """How long a sharded reduction waits for its peers' records before LBK_ERR_NCCL."""
+        _ffi.check(_ffi.lib().lbk_set_exchange_timeout(self.handle, int(milliseconds)), self.handle)
 
     def sync(self) -> None:
         _ffi.check(_ffi.lib().lbk_sync(self.handle), self.handle)
@@ -142,6 +148,53 @@ class Context:
         self.close()
 
 
+class MultiContext(Context):
+    """ONE host thread, many GPUs (lbk_init_multi): rank r is devices[r].  `alloc_sharded` / `to_device_sharded` make
+    vectors block-sharded over the ranks; every routine of `single` / `inplace` then fans out over the devices, and a
+    reduction returns the scalar all ranks agree on.  `alloc` / `to_device` make unsharded vectors (whole on devices[0]).
+    The same device may be listed more than once (the sharded path on a one-GPU box)."""
+
+    def __init__(self, devices, threads: Optional[bool] = None):
+        L = _ffi.lib()
+        devices = [int(d) for d in devices]
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _ffi.check(L.lbk_init_multi(len(devices), arr, C.byref(h)))
+        self._h = h
+        self.device = devices[0]
+        self.devices = devices
+        self.nranks, self.rank = len(devices), 0
+        if threads is not None:
+            self.set_threads(threads)
+
+    def set_threads(self, enabled: bool) -> None:
+        """One launcher thread per device (True) or rank after rank from the calling thread (False)."""
+        _ffi.check(_ffi.lib().lbk_set_multi_threads(self.handle, int(enabled)), self.handle)
+
+    def rank_context(self, rank: int) -> "Context":
+        """The borrowed one-device context of `rank` (for callers that drive the ranks themselves)."""
+        cache = self.__dict__.setdefault("_ranks", {})
+        if rank not in cache:
+            h = C.c_void_p()
+            _ffi.check(_ffi.lib().lbk_multi_rank(self.handle, rank, C.byref(h)), self.handle)
+            c = Context.__new__(Context)
+            c._h, c.device, c.nranks, c.rank, c._borrowed = h, self.devices[rank], self.nranks, rank, self
+            cache[rank] = c
+        return cache[rank]
+
+    def to_device_sharded(self, host, dtype=None) -> "DVector":
+        """Explicit host -> devices transfer of ONE host buffer into a vector sharded over the ranks."""
+        if dtype is None:
+            dtype = np.float64 if getattr(host, "dtype", None) == np.float64 else np.float32
+        a = np.ascontiguousarray(host, dtype=dtype)
+        if a.ndim != 1:
+            raise ValueError("vectors are one-dimensional")
+        v = self.alloc_sharded(a.size, dtype)
+        if a.size:
+            _ffi.check(_ffi.lib().lbk_vec_upload(v.handle, a.ctypes.data_as(C.c_void_p), a.size), self.handle)
+        return v
+
+
 class Event:
     def __init__(self, ctx: Context):
         h = C.c_void_p()
@@ -159,10 +212,11 @@ class Event:
 
     def __del__(self):
         try:
-            if self._h is not None and self.ctx._h is not None:
+            if self._h is not None:       # safe after ctx.close(): handles keep the native context alive
                 _ffi.lib().lbk_event_destroy(self._h)
         except Exception:
             pass
+        self._h = None
 
 
 class DVector:
@@ -177,6 +231,7 @@ class DVector:
         self._len, self._glen, self._off = a.value, b.value, c.value
         self._ptr = int(L.lbk_vec_ptr(handle) or 0)
         self._dtype = np.dtype(np.float64 if L.lbk_vec_elem_size(handle) == 8 else np.float32)
+        self._sharded = bool(L.lbk_vec_is_sharded(handle))
 
     @property
     def handle(self):
@@ -201,6 +256,22 @@ class DVector:
     def dtype(self):
         return self._dtype
 
+    @property
+    def is_sharded(self) -> bool:
+        return self._sharded
+
+    def like(self) -> "DVector":
+        """An uninitialised vector with this one's length, element type and shard layout (lbk_vec_alloc_like)."""
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().lbk_vec_alloc_like(self._h, C.byref(h)), self.ctx.handle)
+        return DVector(self.ctx, h)
+
+    def part(self, rank: int) -> "DVector":
+        """Rank `rank`'s block of a multi-device context's vector, as a vector of that rank's context (borrowed)."""
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().lbk_vec_part(self._h, rank, C.byref(h)), self.ctx.handle)
+        return DVector(self.ctx.rank_context(rank), h, parent=self)
+
     def clone(self) -> "DVector":
         h = C.c_void_p()
         _ffi.check(_ffi.lib().lbk_vec_clone(self._h, C.byref(h)), self.ctx.handle)
@@ -212,6 +283,7 @@ class DVector:
         return DVector(self.ctx, h, parent=self)
 
     def to_host(self) -> np.ndarray:
+        """Explicit device -> host transfer (of this rank's shard; of the WHOLE vector on a multi-device context)."""
         n = len(self)
         out = np.empty(n, dtype=self.dtype)
         if n:
@@ -245,7 +317,7 @@ class DVector:
 
     def __del__(self):
         try:
-            if self._h is not None and self.ctx._h is not None:
+            if self._h is not None:       # safe after ctx.close(): handles keep the native context alive
                 _ffi.lib().lbk_vec_free(self._h)
         except Exception:
             pass
@@ -285,6 +357,24 @@ class _PinnedArray(np.ndarray):
     def __array_finalize__(self, obj):
         if obj is not None:
             self._owner = getattr(obj, "_owner", None)
+
+
+class registered:
+    """Context manager: page-lock a numpy array the caller already owns for the duration of the block
+    (lbk_host_register / lbk_host_unregister), so uploads from it run at the rate of a pinned copy."""
+
+    def __init__(self, array: np.ndarray):
+        assert array.flags.c_contiguous
+        self.a = array
+
+    def __enter__(self):
+        if self.a.nbytes:
+            _ffi.check(_ffi.lib().lbk_host_register(self.a.ctypes.data_as(C.c_void_p), self.a.nbytes))
+        return self.a
+
+    def __exit__(self, *exc):
+        if self.a.nbytes:
+            _ffi.check(_ffi.lib().lbk_host_unregister(self.a.ctypes.data_as(C.c_void_p)))
 
 
 def hash_fill_reference(n: int, seed: int, lo: float = -1.0, hi: float = 1.0, offset: int = 0, dtype=np.float32) -> np.ndarray:

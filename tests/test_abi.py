@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(blas):
     for n in names:
         assert hasattr(L, n), f"liblbk.so does not export {n}"
     assert sorted(_ffi.PROTOTYPES) == names, "the ctypes binding and the header disagree"
-    assert L.lbk_version() == 100
+    assert L.lbk_version() == 200
 
 
 def test_no_cpu_fallback(blas):
