@@ -4,11 +4,17 @@
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle port) on host cores
 
-One "step" = one pass of the hot path over one batch of synthetic fp32 data: sdot, saxpy, snrm2 at
-n = 2^28 per GPU, unit stride (BASELINE.json's metric: "sdot/saxpy/snrm2 achieved HBM GB/s at n=2^28").
-Algorithmic bytes per element: sdot 8 + saxpy 12 + snrm2 4 = 24.  Weak scaling: every
-rank holds a 2^28-element block shard of each vector; saxpy needs no communication, each reduction ends
-with one 48-byte record exchange.  Rank 0 prints ONE JSON line.
+One "step" = PASSES (default 12) passes of the hot path over one batch of synthetic fp32 data, a pass being
+sdot, saxpy, snrm2 at n = 2^28 per GPU, unit stride (BASELINE.json's metric: "sdot/saxpy/snrm2 achieved HBM
+GB/s at n=2^28"); twelve passes make a step ~10.7 ms, so the K = 20 timed steps cover > 0.2 s of device time.
+Algorithmic bytes per element and pass: sdot 8 + saxpy 12 + snrm2 4 = 24.  `value` is WEAK
+scaling: every rank holds a 2^28-element block shard of each vector; saxpy needs no communication, each
+reduction ends with one 48-byte record exchange.  With more than one rank the line also carries
+  strong         the metric's n as the GLOBAL n: n_global = 2^28 and 2^30 (BASELINE.json configs[2]),
+                 sdot/saxpy/snrm2/sasum/isamax, with the speed-up over ONE GPU of the same box on the same n;
+  parity_check   an untimed block comparing the sharded path with the oracle / exact properties on this very job;
+  single_process the same step driven from ONE host thread through lbk_init_multi (rank 0 alone, all GPUs).
+Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -138,6 +144,13 @@ def cpu_info():
     return model, os.cpu_count()
 
 
+def reference_toolchain() -> dict:
+    """if the reference's toolchain ever shows up on the box, say so (and `__graft_entry__.build()`
+    then builds oracle/_ref from /root/reference).  On this image every entry is None."""
+    import shutil
+    return {t: shutil.which(t) for t in ("stack", "ghc", "cabal", "gfortran")}
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,16 +158,18 @@ def run_reference(args) -> None:
     n = 1 << args.ref_log2n
     dt, gbs = time_cpu(n, args.steps, args.warmup)
     model, ncpu = cpu_info()
-    sample = (f"each step = sdot+saxpy(pure: clone+update)+snrm2 on a 2^{args.ref_log2n}-element sample of the 2^{args.log2n} workload, "
-              f"U(-1,1) fp32, unit stride; C port of Single.hs/Util.hs (gcc -O2, no FMA), 1 thread: the reference is single-threaded "
-              f"pure Haskell (no ghc/stack in this image, so `stack bench` itself cannot run); host = {model}, {ncpu} logical CPUs")
+    tools = reference_toolchain()
+    sample = (f"each step = sdot+saxpy(pure: clone+update)+snrm2 on a 2^{args.ref_log2n}-element sample of the 2^{args.log2n} workload "
+              f"(the metric is a rate, so the sample carries), U(-1,1) fp32, unit stride; C port of Single.hs/Util.hs (gcc -O2, no FMA), "
+              f"1 thread: the reference is single-threaded pure Haskell; toolchain probe {tools} -> `stack bench` cannot run here; "
+              f"host = {model}, {ncpu} logical CPUs")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "reference_toolchain": tools,
     }
     emit(line)
 
@@ -172,19 +187,146 @@ METRIC = "sdot+saxpy+snrm2 achieved HBM GB/s at n=2^28 per GPU (algorithmic byte
 
 
 def workload_config(args, world: int) -> dict:
+    """Identical in both arms (it depends on the command line only), so the driver can tell they ran the same workload."""
     n = 1 << args.log2n
     return {
         "workload": (f"sdot, saxpy, snrm2 fp32, unit stride, n=2^{args.log2n} per GPU, in place on device-resident block shards "
                      f"(BASELINE.json metric; configs[1]-[2] class); all ten routines are reported under `routines`"),
-        "n_per_gpu": n, "n_global": n * world, "bytes_per_elem_step": STEP_BYTES_PER_ELEM,
-        "l2": "each vector is 1 GiB per GPU, far larger than the 126 MB L2, so no flush between iterations",
+        "n_per_gpu": n, "n_global": n * world, "bytes_per_elem_pass": STEP_BYTES_PER_ELEM,
+        "passes_per_step": args.passes,
+        "l2": f"each vector is {4 * n >> 20} MiB per GPU, far larger than the 126 MB L2, so no flush between iterations",
         "parallelism": f"{world} rank(s), one per GPU; saxpy: no communication; sdot/snrm2: one 48-byte record exchange per call",
+        "cpu_sample": (f"the reference arm (and cpu_baseline) time the same three routines on a 2^{args.ref_log2n}-element sample per step, "
+                       f"one pass per step, on one host core"),
     }
 
 
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def time_calls(ctx, barrier, f, k: int, warm: int = 3) -> float:
+    """ms per call of f(i) over k back-to-back calls on the library's stream (CUDA events), after `warm` untimed ones."""
+    for i in range(warm):
+        f(i)
+    barrier()
+    a = ctx.event().record()
+    for i in range(k):
+        f(i)
+    b = ctx.event().record()
+    barrier()
+    return a.elapsed_ms(b) / k
+
+
+def planted(lb, np, ctx, n_global: int, world: int, rank: int, seed: int, plant: dict):
+    """A sharded hash-filled vector with `plant` = {global index: value} written over it (each rank writes what falls into its block)."""
+    from lambda_blas_b200 import sharded
+    v = ctx.alloc_sharded(n_global).fill_hash(seed)
+    lo, hi = sharded.shard_range(n_global, world, rank)
+    for k, val in plant.items():
+        if lo <= k < hi:
+            ctx.wrap(v.ptr + 4 * (k - lo), 1, keepalive=v).upload(np.array([val], dtype=np.float32))
+    return v
+
+
+def parity_block(lb, np, ctx, world: int, rank: int, agree, log2_big: int) -> dict:
+    """Untimed: the sharded path of THIS job against the oracle (moderate n) and against exact / double-precision properties at
+    the full size of BASELINE.json configs[2].  `agree(values)` -> True when every rank passed the same numbers (all-ranks-same-bits,
+    test/Main.hs:37-42 is the property the tests replay; here across GPUs).  Returns {"status": "ok" | "FAILED: ...", ...}."""
+    from lambda_blas_b200 import inplace as ip, sharded
+    from oracle import oracle
+    oracle.build()
+    fails, checks = [], 0
+
+    def check(name, cond):
+        nonlocal checks
+        checks += 1
+        if not cond:
+            fails.append(name)
+
+    # ---- moderate n: the whole (unsharded) vector through the oracle on every rank
+    n = (1 << 22) + 3
+    lo, hi = sharded.shard_range(n, world, rank)
+    edge = sharded.shard_range(n, world, 0)[1]                 # first element of shard 1 (== n when there is one rank)
+    e1 = min(edge, n - 1)
+    cases = {
+        "max at the end of shard 0": {edge - 1: -9.0},
+        "max at the start of shard 1": {e1: 9.0},
+        "tie across the shard boundary": {edge - 1: 7.0, e1: -7.0, n - 1: 7.0},
+        "NaN at index 0": {0: float("nan"), e1: 5.0},
+        "NaN elsewhere": {e1: float("nan"), edge - 1: 3.0},
+    }
+    u = 2.0 ** -24
+    hy = lb.hash_fill_reference(n, 12)
+    y = ctx.alloc_sharded(n).fill_hash(12)
+    for name, plant in cases.items():
+        hx = lb.hash_fill_reference(n, 11)
+        for k, v in plant.items():
+            hx[k] = v
+        x = planted(lb, np, ctx, n, world, rank, 11, plant)
+        im = lb.isamax(n, x, 1)
+        check(f"isamax [{name}]", im == oracle.isamax(n, hx, 1))
+        vals = [float(im)]
+        if not np.isnan(hx).any():
+            prod = float(np.sum(np.abs(hx.astype(np.float64) * hy)))
+            d, nr, sa = lb.sdot(n, x, 1, y, 1), lb.snrm2(n, x, 1), lb.sasum(n, x, 1)
+            check(f"sdot [{name}]", abs(float(d) - float(oracle.sdot(n, hx, 1, hy, 1))) <= 2 * n * u * prod)
+            check(f"snrm2 [{name}]", abs(float(nr) - float(oracle.snrm2(n, hx, 1))) <= 2 * n * u * float(oracle.snrm2(n, hx, 1)))
+            check(f"sasum [{name}]", abs(float(sa) - float(oracle.sasum(n, hx, 1))) <= 2 * n * u * float(np.sum(np.abs(hx))))
+            vals += [float(d), float(nr), float(sa)]
+        check(f"all ranks hold the same bits [{name}]", agree(vals))
+    hx = lb.hash_fill_reference(n, 11)
+    x = ctx.alloc_sharded(n).fill_hash(11)
+    ip.saxpy_(n, SAXPY_A, x, 1, y, 1)
+    want = oracle.saxpy(n, SAXPY_A, hx, 1, hy, 1)
+    check("saxpy bit-exact on this rank's slice", np.array_equal(y.to_host().view(np.uint32), want[lo:hi].view(np.uint32)))
+    del x, y
+
+    # ---- BASELINE.json configs[2] at full size (n_global = 2^log2_big): exact values, double-precision cross-checks, planted extrema
+    N = 1 << log2_big
+    lo, hi = sharded.shard_range(N, world, rank)
+    ones = ctx.alloc_sharded(N).fill(1.0)
+    half = ctx.alloc_sharded(N).fill(0.5)
+    check("sasum(0.5 x 2^k) exact", float(lb.sasum(N, half, 1)) == N / 2)
+    check("sdot(1, 0.5) exact", float(lb.sdot(N, ones, 1, half, 1)) == N / 2)
+    check("snrm2(1 x 2^k) exact", float(lb.snrm2(N, ones, 1)) == float(np.float32(math.sqrt(N))))
+    check("isamax(all equal) = 0", lb.isamax(N, ones, 1) == 0)
+    del half
+    x, yv = ctx.alloc_sharded(N).fill_hash(21), ctx.alloc_sharded(N).fill_hash(22)
+    pos = ctx.alloc_sharded(N).fill_hash(23, 0.0, 1.0)
+    wide = lambda a, b: float(lb.sdsdot(N, 0.0, a, 1, b, 1))          # noqa: E731  products and sum in double (Single.hs:231-262)
+    d, nr, sa = float(lb.sdot(N, x, 1, yv, 1)), float(lb.snrm2(N, x, 1)), float(lb.sasum(N, pos, 1))
+    nx2, ny2 = wide(x, x), wide(yv, yv)
+    # tolerance: 2^-18 of ||x|| ||y|| (>= sum|x_i y_i|) -- far inside the stated k n eps sum|x_i y_i|, which is > 1 at this n
+    check("sdot vs double-precision accumulation", abs(d - wide(x, yv)) <= 2.0 ** -18 * math.sqrt(nx2 * ny2))
+    check("snrm2 vs sqrt(double-precision sum of squares)", abs(nr - math.sqrt(nx2)) <= 2.0 ** -20 * math.sqrt(nx2))
+    check("sasum vs double-precision sum", abs(sa - wide(pos, ones)) <= 2.0 ** -18 * wide(pos, ones))
+    check("all ranks hold the same bits [2^%d]" % log2_big, agree([d, nr, sa, nx2]))
+    del pos, ones
+    for name, plant, want in (("max at the last element of shard 0", {sharded.shard_range(N, world, 0)[1] - 1: 3.0}, sharded.shard_range(N, world, 0)[1] - 1),
+                              ("tie: last element of the vector and first of the last shard", {N - 1: -4.0, sharded.shard_range(N, world, world - 1)[0]: 4.0},
+                               sharded.shard_range(N, world, world - 1)[0]),
+                              ("NaN at 0 wins", {0: float("nan"), N - 1: 5.0}, 0)):
+        xp = planted(lb, np, ctx, N, world, rank, 21, plant)
+        im = lb.isamax(N, xp, 1)
+        check(f"isamax 2^{log2_big} [{name}]", im == want and agree([float(im)]))
+        del xp
+    # saxpy at full size: bit-exact windows at both ends of this rank's block against the fp32 definition
+    ip.saxpy_(N, SAXPY_A, x, 1, yv, 1)
+    w = min(1 << 16, hi - lo)
+    for off in (0, (hi - lo) - w):
+        got = np.empty(w, dtype=np.float32)
+        ctx.wrap(yv.ptr + 4 * off, w, keepalive=yv).download_async(got); ctx.sync()
+        wx, wy = lb.hash_fill_reference(w, 21, offset=lo + off), lb.hash_fill_reference(w, 22, offset=lo + off)
+        want_w = (wy + (np.float32(SAXPY_A) * wx).astype(np.float32)).astype(np.float32)
+        check(f"saxpy 2^{log2_big} window @{off} bit-exact", np.array_equal(got.view(np.uint32), want_w.view(np.uint32)))
+    del x, yv
+    ok = agree([float(len(fails))]) and not fails
+    return {"status": "ok" if ok else "FAILED: " + "; ".join(fails[:6]), "checks": checks, "ranks": world,
+            "covers": (f"n = 2^22+3 vs the oracle on the whole vector: isamax with maxima / ties at shard edges and both NaN rules, sdot / snrm2 / sasum within "
+                       f"2 n u sum|.|, saxpy bit-exact per slice; n_global = 2^{log2_big} (BASELINE.json configs[2]): exact sums of constants, sdot / snrm2 / sasum "
+                       f"against double-precision accumulation (sdsdot), planted extrema at shard edges, saxpy bit-exact windows; every result identical on all ranks")}
+
+
 def run_ours(args) -> None:
     import numpy as np
     import torch
@@ -195,10 +337,11 @@ def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    dist = None
+    dist, idle = None, None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idle = dist.new_group(backend="gloo")        # a CPU-side barrier: ranks waiting there leave their GPU idle
     ctx = lb.Context(local)
     if world > 1:
         sharded.attach_torch_distributed(ctx)
@@ -214,26 +357,28 @@ def run_ours(args) -> None:
 
     n = 1 << args.log2n
     ng = n * world
-    K, W = args.steps, args.warmup
+    K, W, P = args.steps, max(args.warmup, 3), args.passes
     x, y = ctx.alloc_sharded(ng).fill_hash(1), ctx.alloc_sharded(ng).fill_hash(2)
     assert len(x) == n
     res = ctx.alloc(8)
     flags = lb.srotmg(1.5, 0.75, 2.0, 0.5)
     cs, sn = math.cos(0.3), math.sin(0.3)
 
-    calls = {
-        "sdot": lambda: ip.sdot_async(ng, x, 1, y, 1, res),
-        "saxpy": lambda: ip.saxpy_(ng, SAXPY_A, x, 1, y, 1),
-        "snrm2": lambda: ip.snrm2_async(ng, x, 1, res),
-        "sdsdot": lambda: ip.sdsdot_async(ng, 0.5, x, 1, y, 1, res),
-        "sasum": lambda: ip.sasum_async(ng, x, 1, res),
-        "isamax": lambda: ip.isamax_async(ng, x, 1, res),
-        "sscal": lambda: ip.sscal_(ng, SAXPY_A, x, 1),
-        "scopy": lambda: ip.scopy_(ng, x, 1, y, 1),
-        "sswap": lambda: ip.sswap_(ng, x, 1, y, 1),
-        "srot": lambda: ip.srot_(ng, x, 1, y, 1, cs, sn),
-        "srotm": lambda: ip.srotm_(flags, ng, x, 1, y, 1),
-    }
+    def make_calls(xv, yv, nn, out):
+        return {
+            "sdot": lambda: ip.sdot_async(nn, xv, 1, yv, 1, out),
+            "saxpy": lambda: ip.saxpy_(nn, SAXPY_A, xv, 1, yv, 1),
+            "snrm2": lambda: ip.snrm2_async(nn, xv, 1, out),
+            "sdsdot": lambda: ip.sdsdot_async(nn, 0.5, xv, 1, yv, 1, out),
+            "sasum": lambda: ip.sasum_async(nn, xv, 1, out),
+            "isamax": lambda: ip.isamax_async(nn, xv, 1, out),
+            "sscal": lambda: ip.sscal_(nn, SAXPY_A, xv, 1),
+            "scopy": lambda: ip.scopy_(nn, xv, 1, yv, 1),
+            "sswap": lambda: ip.sswap_(nn, xv, 1, yv, 1),
+            "srot": lambda: ip.srot_(nn, xv, 1, yv, 1, cs, sn),
+            "srotm": lambda: ip.srotm_(flags, nn, xv, 1, yv, 1),
+        }
+    calls = make_calls(x, y, ng, res)
 
     def barrier():
         ctx.sync()
@@ -249,64 +394,98 @@ def run_ours(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.tolist()
 
+    def agree(values) -> bool:
+        """True when every rank passes bit-identical numbers (NaN == NaN)."""
+        if dist is None:
+            return True
+        a = torch.tensor(np.asarray(values, dtype=np.float64).view(np.int64), device="cuda")
+        lo_t, hi_t = a.clone(), a.clone()
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN); dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+        return bool(torch.equal(lo_t, hi_t))
+
     sampler = ClockSampler(local) if rank == 0 else None
     t_load0 = time.time()
 
-    # ---- the step: W warm-up, then exactly K timed steps bracketed by barrier + synchronize ----
-    for _ in range(max(W, 3)):
-        for r in STEP_ROUTINES:
-            calls[r]()
+    # ---- the step: W warm-up steps, then exactly K timed steps (of P passes each) bracketed by barrier + synchronize ----
+    def one_step():
+        for _ in range(P):
+            for r in STEP_ROUTINES:
+                calls[r]()
+    for _ in range(W):
+        one_step()
     e0, e1 = ctx.event(), ctx.event()
     barrier()
     launches0, pdl0 = ctx.launch_count(), ctx.pdl_count()
     e0.record()
     for s in range(K):
-        for r in STEP_ROUTINES:
-            calls[r]()
+        one_step()
     e1.record()
     barrier()
     launches, pdl_launches = ctx.launch_count() - launches0, ctx.pdl_count() - pdl0
     ms_total = e0.elapsed_ms(e1)
     step_check = res.to_host()   # reads the last snrm2 result: the step's output reaches the host
 
-    # ---- the same K steps again with a CUDA event around every launch: per-kernel launch durations in
+    # ---- the same passes again with a CUDA event around every launch: per-kernel launch durations in
     # step context (the roofline's `achieved`).  Not part of `value`: an event between two kernels
     # forbids the programmatic overlap of a reduction's tail with the next kernel. ----
-    marks = [[ctx.event() for _ in range(len(STEP_ROUTINES) + 1)] for _ in range(K)]
+    KI = min(K * P, 60)
+    marks = [[ctx.event() for _ in range(len(STEP_ROUTINES) + 1)] for _ in range(KI)]
     barrier()
-    for s in range(K):
+    for s in range(KI):
         marks[s][0].record()
         for j, r in enumerate(STEP_ROUTINES):
             calls[r]()
             marks[s][j + 1].record()
     barrier()
-    per_routine_in_step = {r: sum(marks[s][j].elapsed_ms(marks[s][j + 1]) for s in range(K)) / K
+    per_routine_in_step = {r: sum(marks[s][j].elapsed_ms(marks[s][j + 1]) for s in range(KI)) / KI
                            for j, r in enumerate(STEP_ROUTINES)}
+    del marks
     ms_step, saxpy_ms_in_step = max_over_ranks([ms_total / K, per_routine_in_step["saxpy"]])[:2]
-    value = STEP_BYTES_PER_ELEM * ng / ms_step / 1e6
+    value = STEP_BYTES_PER_ELEM * ng * P / ms_step / 1e6
 
-    # ---- every routine alone (K launches back to back), for the per-routine table ----
-    routines = {}
-    order = ["sdot", "saxpy", "snrm2", "sasum", "isamax", "sscal", "scopy", "sswap", "srot", "srotm", "sdsdot"]
-    times = []
-    for r in order:
-        x.fill_hash(1); y.fill_hash(2)
-        for _ in range(3):
-            calls[r]()
-        barrier()
-        a, b = ctx.event().record(), None
-        for _ in range(K):
-            calls[r]()
-        b = ctx.event().record()
-        barrier()
-        times.append(a.elapsed_ms(b) / K)
-    times = max_over_ranks(times)
+    # ---- every routine alone (KR launches back to back), for the per-routine table ----
+    KR = max(K, 20)
     peak, peak_src = measured_peak()
-    for r, ms in zip(order, times):
-        gbs = BYTES_PER_ELEM[r] * ng / ms / 1e6
-        routines[r] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "GBps_per_gpu": round(gbs / world, 1),
-                       "pct_of_8TBs_per_gpu": round(100 * gbs / world / NOMINAL_HBM_GBS, 1),
-                       "frac_of_measured_peak": round(gbs / world / peak, 3)}
+
+    def table(call_map, order, nn_global, bytes_of):
+        out = {}
+        times = []
+        for r in order:
+            x.fill_hash(1); y.fill_hash(2)
+            times.append(time_calls(ctx, barrier, lambda i, f=call_map[r]: f(), KR))
+        for r, ms in zip(order, max_over_ranks(times)):
+            gbs = bytes_of(r) * nn_global / ms / 1e6
+            out[r] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "GBps_per_gpu": round(gbs / world, 1),
+                      "pct_of_8TBs_per_gpu": round(100 * gbs / world / NOMINAL_HBM_GBS, 1),
+                      "frac_of_measured_peak": round(gbs / world / peak, 3)}
+        return out
+    order = ["sdot", "saxpy", "snrm2", "sasum", "isamax", "sscal", "scopy", "sswap", "srot", "srotm", "sdsdot"]
+    routines = table(calls, order, ng, lambda r: BYTES_PER_ELEM[r])
+    # srotm's other constructors (Single.hs:475-476 FLAGNEG1: four products; :481-482 FLAG1), FLAG0 is the row above
+    neg1 = lb.ModGivensRot(-1, 1.0, 1.0, 1.0, 0.9, -0.3, 0.2, 1.1)
+    flag1 = lb.ModGivensRot(1, 1.0, 1.0, 1.0, 0.8, 0.0, 0.0, 0.7)
+    routines.update(table({"srotm_FLAGNEG1": lambda: ip.srotm_(neg1, ng, x, 1, y, 1), "srotm_FLAG1": lambda: ip.srotm_(flag1, ng, x, 1, y, 1)},
+                          ["srotm_FLAGNEG1", "srotm_FLAG1"], ng, lambda r: 16))
+
+    # ---- the reference's own input distribution (test/Gen.hs:39-44 genNiceFloat: 10% zeros, the rest +-genEveryday, i.e.
+    # uniform on (2^-24, 2^24-1), test/Bench.hs:20-31) at the same n: the value-dependent kernels (snrm2's range classes,
+    # isamax's running maximum) must not care ----
+    routines_everyday = {}
+    if not args.no_everyday:
+        rng = np.random.default_rng(99 + rank)
+        m = min(1 << 24, n)
+        kind = rng.random(m)
+        tile = rng.uniform(2.0 ** -24, 2.0 ** 24 - 1, m).astype(np.float32)
+        tile = np.where(kind < 1 / 9, np.float32(0), np.where(kind < 5 / 9, tile, -tile)).astype(np.float32)
+        rev = tile[::-1].copy()
+        for v in (x, y):
+            for k in range(n // m):
+                ctx.wrap(v.ptr + 4 * k * m, m, keepalive=v).upload(tile if v is x else rev)
+        times = [time_calls(ctx, barrier, lambda i, f=calls[r]: f(), KR) for r in ("sdot", "snrm2", "sasum", "isamax")]
+        for r, ms in zip(("sdot", "snrm2", "sasum", "isamax"), max_over_ranks(times)):
+            gbs = BYTES_PER_ELEM[r] * ng / ms / 1e6
+            routines_everyday[r] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "pct_of_8TBs_per_gpu": round(100 * gbs / world / NOMINAL_HBM_GBS, 1)}
+        routines_everyday["distribution"] = "genNiceFloat: 1/9 zeros, 4/9 +everyday, 4/9 -everyday, everyday = U(2^-24, 2^24-1) (Gen.hs:39-44, 208-214)"
 
     # ---- the Double instances (ddot, daxpy, ...: SURVEY.md 8f.3) on the same bytes: n/2 doubles per GPU ----
     routines_f64 = {}
@@ -324,20 +503,56 @@ def run_ours(args) -> None:
         dtimes = []
         for r, f in dcalls.items():
             xd.fill_hash(1); yd.fill_hash(2)
-            for _ in range(3):
-                f()
-            barrier()
-            a = ctx.event().record()
-            for _ in range(K):
-                f()
-            b = ctx.event().record()
-            barrier()
-            dtimes.append(a.elapsed_ms(b) / K)
+            dtimes.append(time_calls(ctx, barrier, lambda i, f=f: f(), KR))
         dtimes = max_over_ranks(dtimes)
         for (r, _), ms in zip(dcalls.items(), dtimes):
             gbs = 2 * BYTES_PER_ELEM["s" + r[1:] if r != "idamax" else "isamax"] * ngd / ms / 1e6
             routines_f64[r] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "pct_of_8TBs_per_gpu": round(100 * gbs / world / NOMINAL_HBM_GBS, 1)}
         del xd, yd, resd
+
+    # ---- strong scaling: the metric's n is the GLOBAL n ----
+    # n_global = 2^28 (the metric's size) and 2^30 (BASELINE.json configs[2]) block-sharded over the ranks.  When one rank's
+    # operand is <= 2x the 126 MB L2, SETS buffer sets are rotated so that no call finds its operands cached.  The same-box
+    # one-GPU time of the same n (rank 0 alone, a context without a communicator, the other ranks idle) gives the speed-up.
+    strong = None
+    STRONG_R = ("sdot", "saxpy", "snrm2", "sasum", "isamax")
+    if world > 1 and not args.no_strong:
+        strong = {"routines": list(STRONG_R), "exchange": exchange}
+        for lg in (28, 30):
+            N = 1 << lg
+            per_rank_bytes = 4 * N // world
+            SETS = 4 if per_rank_bytes <= 2 * 126_000_000 else (2 if per_rank_bytes <= 4 * 126_000_000 else 1)
+            xs_ = [ctx.alloc_sharded(N).fill_hash(31 + i) for i in range(SETS)]
+            ys_ = [ctx.alloc_sharded(N).fill_hash(41 + i) for i in range(SETS)]
+            cm = [make_calls(xs_[i], ys_[i], N, res) for i in range(SETS)]
+            KS = 40 if lg == 28 else 20
+            tN = max_over_ranks([time_calls(ctx, barrier, lambda i, r=r: cm[i % SETS][r](), KS, warm=2 * SETS) for r in STRONG_R])
+            del cm, xs_, ys_
+            # one GPU, same n, same box
+            t1 = [0.0] * len(STRONG_R)
+            if rank == 0:
+                solo = lb.Context(local)
+                S1 = 2 if 4 * N <= 4 * 126_000_000 else 1
+                sx = [solo.alloc(N).fill_hash(31 + i) for i in range(S1)]
+                sy = [solo.alloc(N).fill_hash(41 + i) for i in range(S1)]
+                sres = solo.alloc(8)
+                scm = [make_calls(sx[i], sy[i], N, sres) for i in range(S1)]
+
+                def solo_barrier():
+                    solo.sync()
+                t1 = [time_calls(solo, solo_barrier, lambda i, r=r: scm[i % S1][r](), KS, warm=2) for r in STRONG_R]
+                del scm, sx, sy, sres
+                solo.close()
+            dist.barrier(group=idle)
+            t1 = max_over_ranks(t1)
+            strong[f"n_global=2^{lg}"] = {
+                r: {"ms": round(a, 4), "ms_1gpu": round(b, 4), "speedup_vs_1gpu": round(b / a, 2),
+                    "GBps": round(BYTES_PER_ELEM[r] * N / a / 1e6, 1), "pct_of_8TBs_per_gpu": round(100 * BYTES_PER_ELEM[r] * N / a / 1e6 / world / NOMINAL_HBM_GBS, 1)}
+                for r, a, b in zip(STRONG_R, tN, t1)}
+            strong[f"n_global=2^{lg}"]["buffer_sets_rotated"] = SETS
+        strong["limiter"] = ("at n_global = 2^28 a rank streams 2^28/N elements in tens of microseconds, so the fixed per-call cost shows: the in-kernel "
+                             "record exchange (one NVLink round trip, ~3-5 us), the skew between the ranks' independent launches, and the kernel's own "
+                             "ramp-up / tail (t0 ~2.5 us on one GPU); at 2^30 the same costs are ~4x smaller relative to the streaming time")
 
     # ---- end to end: host buffers in, host results out, copies inside the timed region ----
     # The caller's x, y live in pinned HOST memory.  Per step: upload x and y in chunks; each chunk's saxpy goes
@@ -359,9 +574,9 @@ def run_ours(args) -> None:
     wd = [ctx_dl.wrap(yout.ptr + 4 * k * m, m, keepalive=yout) for k in range(C)]
     evs = [ctx.event() for _ in range(C)]
 
-    def e2e_step():
+    def e2e_step(src_x, src_y):
         for k in range(C):
-            xs[k].upload_async(hx[k * m:(k + 1) * m]); ys[k].upload_async(hy[k * m:(k + 1) * m])
+            xs[k].upload_async(src_x[k * m:(k + 1) * m]); ys[k].upload_async(src_y[k * m:(k + 1) * m])
             ip.saxpy_into(m, SAXPY_A, xs[k], 1, ys[k], 1, ws[k])
             evs[k].record()
             ctx_dl.wait_event(evs[k])
@@ -370,22 +585,33 @@ def run_ours(args) -> None:
         ip.snrm2_async(ng, x, 1, res.view(2, 2))
         res.download_async(hres)
         ctx.sync(); ctx_dl.sync()                   # the caller holds the results here
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    tw0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
-    barrier()
-    e2e_ms = max_over_ranks([(time.perf_counter() - tw0) / Ke * 1e3])[0]
+
+    def time_e2e(src_x, src_y, steps):
+        for _ in range(2):
+            e2e_step(src_x, src_y)
+        barrier()
+        tw0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step(src_x, src_y)
+        barrier()
+        return max_over_ranks([(time.perf_counter() - tw0) / steps * 1e3])[0]
+    e2e_ms = time_e2e(hx, hy, Ke)
     e2e = {"value": round(STEP_BYTES_PER_ELEM * ng / e2e_ms / 1e6, 2), "unit": "GB/s", "ms_per_step": round(e2e_ms, 3), "steps": Ke,
+           "passes_per_step": 1,
            "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": (4 * n + 32) * world, "chunks": C,
            "timing": "host wall clock around Ke steps, each ending in a synchronise of both streams; max over ranks",
            "api": ("pinned host x,y -> per chunk: lbk_vec_upload_async x2, lbk_saxpy_oop, event -> second context: lbk_wait_event, "
                    "lbk_vec_download_async(y') -> lbk_sdot_async, lbk_snrm2_async, download scalars -> lbk_sync x2")}
-    ctx_dl.sync()
-    t_load1 = time.time()
-    clocks = sampler.stop(t_load0, t_load1) if sampler else None
+    # the same step from memory the caller did NOT get from lbk_host_alloc: pageable (what a plain Data.Vector.Storable /
+    # numpy buffer is; the driver stages it through its own bounce buffer, synchronously), and the same buffers after
+    # lbk_host_register (page-locked in place)
+    px, py = np.array(hx), np.array(hy)
+    pageable_ms = time_e2e(px, py, 3)
+    with lb.registered(px), lb.registered(py):
+        registered_ms = time_e2e(px, py, 3)
+    e2e["from_pageable_host_memory"] = {"value": round(STEP_BYTES_PER_ELEM * ng / pageable_ms / 1e6, 2), "ms_per_step": round(pageable_ms, 3)}
+    e2e["from_registered_host_memory"] = {"value": round(STEP_BYTES_PER_ELEM * ng / registered_ms / 1e6, 2), "ms_per_step": round(registered_ms, 3),
+                                          "how": "lbk_host_register on the caller's own buffers (not timed: a one-off per buffer)"}
 
     # ---- parity spot check of the timed configuration (size-independent property) ----
     # after the e2e step: y' = y + a*x exactly (separately rounded), checked on a slice against numpy fp32
@@ -393,13 +619,63 @@ def run_ours(args) -> None:
     want = (hy[sl] + np.float32(SAXPY_A) * hx[sl]).astype(np.float32)
     assert np.array_equal(hy_out[sl].view(np.uint32), want.view(np.uint32)), "saxpy result differs from the fp32 definition"
 
+    # ---- transfers alone: toDevice of one 2^28-element vector (Device.hs toDevice = lbk_vec_upload) by kind of host memory, and
+    # every rank's H2D / D2H running together -- the ceiling the end-to-end figure sits under ----
+    def wall_ms(f, reps=3):
+        f(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            f()
+        barrier()
+        return max_over_ranks([(time.perf_counter() - t0) / reps * 1e3])[0]
+    gb = 4 * n * world / 1e6
+    up_pinned = wall_ms(lambda: (x.upload_async(hx), ctx.sync()))
+    up_pageable = wall_ms(lambda: (x.upload_async(px), ctx.sync()))
+    with lb.registered(px):
+        up_registered = wall_ms(lambda: (x.upload_async(px), ctx.sync()))
+    t0 = time.perf_counter(); lb._ffi.check(lb._ffi.lib().lbk_host_register(px.ctypes.data, px.nbytes)); reg_ms = (time.perf_counter() - t0) * 1e3
+    lb._ffi.check(lb._ffi.lib().lbk_host_unregister(px.ctypes.data))
+    down_pinned = wall_ms(lambda: (x.download_async(hy_out), ctx.sync()))
+    ydl = ctx_dl.wrap(y.ptr, n, keepalive=y)
+    both = wall_ms(lambda: (x.upload_async(hx), ydl.download_async(hy_out), ctx.sync(), ctx_dl.sync()))
+    del ydl
+    host_copy = wall_ms(lambda: np.copyto(py, px))
+    transfers = {"unit": "GB/s (aggregate over ranks, all ranks transferring at once)", "n_per_gpu": n,
+                 "toDevice_pinned": round(gb / up_pinned, 1), "toDevice_pageable": round(gb / up_pageable, 1),
+                 "toDevice_registered": round(gb / up_registered, 1), "host_register_ms_per_GiB": round(reg_ms / (px.nbytes / 2 ** 30), 1),
+                 "fromDevice_pinned": round(gb / down_pinned, 1), "h2d_and_d2h_together": round(2 * gb / both, 1),
+                 "host_memcpy_1_thread_per_rank": round(2 * gb / host_copy, 1),
+                 "note": ("the e2e step moves 8 B/elem up and 4 B/elem down per 24 algorithmic bytes: at the h2d+d2h rate R (GB/s, both directions "
+                          "together) its ceiling is 2 R; host_memcpy is numpy copyto on every rank at once (read + write bytes)")}
+    del px, py
+    ctx_dl.sync()
+    t_load1 = time.time()
+    clocks = sampler.stop(t_load0, t_load1) if sampler else None
+
+    del xs, ys, ws, wd, evs, yout
+    ctx_dl.close()
+
+    # ---- untimed parity block on this very job (sharded path vs oracle / exact properties) ----
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(lb, np, ctx, world, rank, agree, 30 if world > 1 else 28)
+
+    # ---- the same step from ONE host thread: lbk_init_multi over all GPUs of the job (rank 0 alone; the others wait on the CPU) ----
+    del x, y
+    single = None
+    if not args.no_single:
+        if rank == 0:
+            single = single_process_arm(lb, np, args, world, local, K, W, P)
+        if dist is not None:
+            dist.barrier(group=idle)
+
     if rank == 0:
         saxpy_gbs_gpu = BYTES_PER_ELEM["saxpy"] * n / saxpy_ms_in_step / 1e6
         roofline = {"bound": "hbm", "kernel": f"lbk::{ncu_traffic('saxpy_kernel') or 'map_unit_kernel<AxpyF<float>, 8, 2, 6, 0>'} (saxpy, the largest share of the step)",
                     "achieved": round(saxpy_gbs_gpu, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": round(saxpy_gbs_gpu / peak, 4), "frac_of_nominal_8TBs": round(saxpy_gbs_gpu / NOMINAL_HBM_GBS, 4),
                     "algorithmic_bytes_per_launch": BYTES_PER_ELEM["saxpy"] * n, "launch_ms": round(saxpy_ms_in_step, 4),
-                    "launch_ms_how": "CUDA events around each launch, on the library's stream, in an instrumented repeat of the K timed steps",
+                    "launch_ms_how": f"CUDA events around each launch, on the library's stream, in an instrumented repeat of {KI} passes of the timed step",
                     "traffic": ncu_traffic("saxpy")}
         cpu_baseline = None
         if world == 1 and not args.no_cpu:
@@ -410,23 +686,76 @@ def run_ours(args) -> None:
                             "sample": (f"{cpu_steps} steps of sdot+saxpy(pure)+snrm2 on a 2^{args.ref_log2n}-element sample (the oracle, C port of the "
                                        f"reference's Haskell, single thread as the reference is); host {model}, {ncpu} logical CPUs")}
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args, world), exchange=exchange),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "exchange": exchange,
             "pct_of_8TBs_per_gpu": round(100 * value / world / NOMINAL_HBM_GBS, 1),
             "frac_of_measured_peak_per_gpu": round(value / world / peak, 3),
+            "timed_region_ms": round(ms_step * K, 2),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "pdl_launches": int(pdl_launches), "clocks": clocks, "routines": routines, "routines_f64": routines_f64,
+            "pdl_launches": int(pdl_launches), "clocks": clocks, "parity_check": parity["status"] if parity else None, "parity": parity,
+            "strong": strong, "single_process": single, "transfers": transfers,
+            "routines": routines, "routines_everyday": routines_everyday, "routines_f64": routines_f64,
             "step_routines_ms": {r: round(v, 4) for r, v in per_routine_in_step.items()},
             "last_snrm2": float(step_check[0]),
         }
         emit(line)
-    del xs, ys, ws, wd, evs
-    ctx_dl.close()
     ctx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def single_process_arm(lb, np, args, world: int, local: int, K: int, W: int, P: int) -> dict:
+    """The same step through the single-process multi-device context: ONE host thread, rank r = GPU r.  On one GPU the context
+    lists that GPU twice (two ranks, two streams, half the vector each), which is what the driver's one-GPU boxes exercise."""
+    from lambda_blas_b200 import inplace as ip
+    devs = list(range(world)) if world > 1 else [local, local]
+    R = len(devs)
+    n = 1 << args.log2n
+    ng = n * world
+    out = {"devices": devs, "n_global": ng}
+    m = lb.MultiContext(devs)
+    try:
+        x, y = m.alloc_sharded(ng).fill_hash(1), m.alloc_sharded(ng).fill_hash(2)
+        res = m.alloc(8)
+
+        def step():
+            for _ in range(P):
+                ip.sdot_async(ng, x, 1, y, 1, res); ip.saxpy_(ng, SAXPY_A, x, 1, y, 1); ip.snrm2_async(ng, x, 1, res)
+        modes = (("threads", True), ("serial", False)) if world > 1 else (("serial", False),)
+        for name, threaded in modes:
+            m.set_threads(threaded)
+            for _ in range(W):
+                step()
+            m.sync()
+            e0, e1 = m.event(), m.event()
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(K):
+                step()
+            e1.record()
+            m.sync()
+            wall = (time.perf_counter() - t0) * 1e3 / K
+            dev = e0.elapsed_ms(e1) / K
+            # latency of a synchronous call (host blocks for the scalar): where the launch skew between the ranks shows
+            xs, ys = m.alloc_sharded(1 << 22).fill_hash(3), m.alloc_sharded(1 << 22).fill_hash(4)
+            for _ in range(20):
+                lb.sdot(1 << 22, xs, 1, ys, 1)
+            t0 = time.perf_counter()
+            for _ in range(200):
+                lb.sdot(1 << 22, xs, 1, ys, 1)
+            lat = (time.perf_counter() - t0) / 200 * 1e6
+            del xs, ys
+            out[name] = {"value": round(STEP_BYTES_PER_ELEM * ng * P / dev / 1e6, 1), "unit": "GB/s", "ms_per_step": round(dev, 4),
+                         "ms_per_step_host_wall": round(wall, 4), "sdot_2^22_sync_call_us": round(lat, 1)}
+        out["last_snrm2"] = float(res.to_host()[0])
+        out["timing"] = "CUDA events per device on its own stream, the longest rank counts; host wall clock around the same K steps beside it"
+        out["launches"] = m.launch_count()
+        del x, y, res
+    finally:
+        m.close()
+    return out
 
 
 
@@ -533,7 +862,12 @@ def main():
     ap.add_argument("--ref-log2n", type=int, default=26, help="log2 of the CPU sample length")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks per vector in the end-to-end pipeline")
+    ap.add_argument("--passes", type=int, default=12, help="passes of sdot+saxpy+snrm2 per timed step (12 passes = 10.7 ms per step on one B200)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling section (multi-rank runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity block")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-process (lbk_init_multi) arm")
+    ap.add_argument("--no-everyday", action="store_true", help="skip the pass over the reference's own input distribution")
     ap.add_argument("--no-f64", action="store_true", help="skip the table of the Double instances")
     ap.add_argument("--launch", action="append", default=[], metavar="ROUTINE:VARIANT:THREADS:BLOCKS_PER_SM",
                     help="override a routine's launch shape (lbk_set_launch), for A/B runs; the default shapes are the product")

@@ -35,6 +35,22 @@ int main()
                     (long long)idamax(3, vd, 1), dnrm2(3, vd, 1));
         ok = ok && ddot(3, ud, 1, vd, 1) == 32.0 && wd[0] == 6 && wd[2] == 12 && idamax(3, vd, 1) == 2 &&
              std::fabs(dnrm2(3, vd, 1) - std::sqrt(77.0)) <= 2e-15 * std::sqrt(77.0);
+        {   // ONE host thread, vectors sharded over ranks (lbk_init_multi); device 0 listed twice = two ranks on one GPU
+            Context m(std::vector<int>{0, 0});
+            std::vector<float> hx(100003), hy(100003);
+            for (size_t i = 0; i < hx.size(); ++i) { hx[i] = (float)((i * 37) % 101) - 50.f; hy[i] = (float)((i * 11) % 13) - 6.f; }
+            hx[50001] = -77.f; hx[50002] = 77.f;                         // the maximum and its tie on either side of the shard edge
+            DVector xs = DVector::sharded(m, hx), ys = DVector::sharded(m, hy);
+            double want = 0;
+            for (size_t i = 0; i < hx.size(); ++i) want += (double)hx[i] * hy[i];
+            DVector zs = saxpy((int64_t)hx.size(), 2.0f, xs, 1, ys, 1);    // pure, sharded like its arguments
+            auto hz = zs.to_host();                                      // gathered into one host buffer
+            bool mok = xs.is_sharded() && zs.is_sharded() && sdot((int64_t)hx.size(), xs, 1, ys, 1) == (float)want &&
+                       isamax((int64_t)hx.size(), xs, 1) == 50001 && hz[50002] == 2.0f * 77.f + hy[50002] && hz.back() == 2.0f * hx.back() + hy.back();
+            std::printf("multi-device context: sdot = %g (want %g), isamax = %lld, %s\n", sdot((int64_t)hx.size(), xs, 1, ys, 1), want,
+                        (long long)isamax((int64_t)hx.size(), xs, 1), mok ? "ok" : "MISMATCH");
+            ok = ok && mok;
+        }
         std::printf(ok ? "OK\n" : "MISMATCH\n");
         return ok ? 0 : 1;
     } catch (const Error &e) {

@@ -31,6 +31,13 @@ class Context {
     {
         if (int s = lbk_init(device, &c_)) throw Error(s, lbk_last_error(nullptr));
     }
+    // ONE host thread, many GPUs (lbk_init_multi): rank r is devices[r]; DVectorT::sharded(...) vectors are block
+    // shards over the ranks and every routine below fans out over them.
+    explicit Context(const std::vector<int> &devices)
+    {
+        if (int s = lbk_init_multi((int)devices.size(), devices.data(), &c_)) throw Error(s, lbk_last_error(nullptr));
+    }
+    // vectors that outlive the context keep the native context alive until they are freed (include/lbk.h)
     ~Context() { lbk_shutdown(c_); }
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;
@@ -73,6 +80,23 @@ template <class T> class DVectorT {
     {
         ctx.check(lbk_vec_upload(v_.get(), host.data(), n_));       // explicit host -> device
     }
+    // toDeviceSharded: ONE host buffer scattered over the ranks of a multi-device context (each rank uploads its own
+    // block on its own stream); on a one-device context it is the same as the constructor above.
+    static DVectorT sharded(const Context &ctx, const std::vector<T> &host)
+    {
+        DVectorT v(ctx, adopt(ctx, (int64_t)host.size(), true), (int64_t)host.size());
+        ctx.check(lbk_vec_upload(v.get(), host.data(), v.size()));
+        return v;
+    }
+    static DVectorT sharded(const Context &ctx, int64_t n) { return DVectorT(ctx, adopt(ctx, n, true), n); }
+    // an uninitialised vector with this one's length, element type and shard layout: what a pure result is made of
+    DVectorT like() const
+    {
+        lbk_vec *v = nullptr;
+        ctx_->check(lbk_vec_alloc_like(v_.get(), &v));
+        return DVectorT(*ctx_, v, n_);
+    }
+    bool is_sharded() const { return lbk_vec_is_sharded(v_.get()) != 0; }
     std::vector<T> to_host() const                                   // explicit device -> host
     {
         std::vector<T> h((size_t)n_);
@@ -84,9 +108,29 @@ template <class T> class DVectorT {
     const Context &ctx() const { return *ctx_; }
 
   private:
+    DVectorT(const Context &ctx, lbk_vec *v, int64_t n) : ctx_(&ctx), n_(n) { v_.reset(v, [](lbk_vec *p) { lbk_vec_free(p); }); }
+    static lbk_vec *adopt(const Context &ctx, int64_t n, bool shard)
+    {
+        lbk_vec *v = nullptr;
+        ctx.check(shard ? (sizeof(T) == 8 ? lbk_vec_alloc_sharded_f64(ctx.get(), n, &v) : lbk_vec_alloc_sharded(ctx.get(), n, &v)) : Abi<T>::alloc(ctx.get(), n, &v));
+        return v;
+    }
     const Context *ctx_;
     int64_t n_;
     std::shared_ptr<lbk_vec> v_;
+};
+
+// Page-locks a host buffer the caller owns for the lifetime of the object (lbk_host_register): uploads from it
+// then run at the rate of a pinned copy.
+class HostRegistration {
+  public:
+    HostRegistration(void *p, size_t nbytes) : p_(p) { if (int s = lbk_host_register(p, (int64_t)nbytes)) throw Error(s, lbk_last_error(nullptr)); }
+    ~HostRegistration() { lbk_host_unregister(p_); }
+    HostRegistration(const HostRegistration &) = delete;
+    HostRegistration &operator=(const HostRegistration &) = delete;
+
+  private:
+    void *p_;
 };
 using DVector = DVectorT<float>;         // Vector Float
 using DVectorD = DVectorT<double>;       // Vector Double
@@ -118,20 +162,20 @@ template <class T> int64_t iamax(int64_t n, const DVectorT<T> &x, int64_t incx)
 
 // ---- pure vector results -----------------------------------------------------------------------------
 template <class T> DVectorT<T> scal(int64_t n, T a, const DVectorT<T> &x, int64_t incx)
-{ DVectorT<T> o(x.ctx(), x.size()); x.ctx().check(Abi<T>::scal_oop(x.ctx().get(), n, a, x.get(), incx, o.get())); return o; }
+{ DVectorT<T> o = x.like(); x.ctx().check(Abi<T>::scal_oop(x.ctx().get(), n, a, x.get(), incx, o.get())); return o; }
 template <class T> DVectorT<T> copy(int64_t n, const DVectorT<T> &x, int64_t incx, const DVectorT<T> &y, int64_t incy)
-{ DVectorT<T> o(y.ctx(), y.size()); x.ctx().check(Abi<T>::copy_oop(x.ctx().get(), n, x.get(), incx, y.get(), incy, o.get())); return o; }
+{ DVectorT<T> o = y.like(); x.ctx().check(Abi<T>::copy_oop(x.ctx().get(), n, x.get(), incx, y.get(), incy, o.get())); return o; }
 template <class T> DVectorT<T> axpy(int64_t n, T a, const DVectorT<T> &x, int64_t incx, const DVectorT<T> &y, int64_t incy)
-{ DVectorT<T> o(y.ctx(), y.size()); x.ctx().check(Abi<T>::axpy_oop(x.ctx().get(), n, a, x.get(), incx, y.get(), incy, o.get())); return o; }
+{ DVectorT<T> o = y.like(); x.ctx().check(Abi<T>::axpy_oop(x.ctx().get(), n, a, x.get(), incx, y.get(), incy, o.get())); return o; }
 template <class T> std::pair<DVectorT<T>, DVectorT<T>> swap(int64_t n, const DVectorT<T> &x, int64_t incx, const DVectorT<T> &y, int64_t incy)
 {
-    DVectorT<T> xo(x.ctx(), x.size()), yo(y.ctx(), y.size());
+    DVectorT<T> xo = x.like(), yo = y.like();
     x.ctx().check(Abi<T>::swap_oop(x.ctx().get(), n, x.get(), incx, y.get(), incy, xo.get(), yo.get()));
     return {xo, yo};
 }
 template <class T> std::pair<DVectorT<T>, DVectorT<T>> rot(int64_t n, const DVectorT<T> &x, int64_t incx, const DVectorT<T> &y, int64_t incy, T c, T s)
 {
-    DVectorT<T> xo(x.ctx(), x.size()), yo(y.ctx(), y.size());
+    DVectorT<T> xo = x.like(), yo = y.like();
     x.ctx().check(Abi<T>::rot_oop(x.ctx().get(), n, x.get(), incx, y.get(), incy, c, s, xo.get(), yo.get()));
     return {xo, yo};
 }
@@ -140,7 +184,7 @@ template <class T> std::pair<DVectorT<T>, DVectorT<T>> rotm(const ModGivensRotT<
     if (flags.flag == -2) return {x, y};                              // Single.hs:473: the arguments themselves
     T p[5];
     flags.sparam(p);
-    DVectorT<T> xo(x.ctx(), x.size()), yo(y.ctx(), y.size());
+    DVectorT<T> xo = x.like(), yo = y.like();
     x.ctx().check(Abi<T>::rotm_oop(x.ctx().get(), n, x.get(), incx, y.get(), incy, p, xo.get(), yo.get()));
     return {xo, yo};
 }

@@ -79,12 +79,20 @@ int lbk_init(int device, lbk_ctx **ctx);
  * NVLink; mapped host memory when the devices are not peers) and folds what it received in rank order, so all
  * ranks hold the same bits and the caller reads rank 0's.  lbk_vec_alloc / lbk_vec_wrap make UNSHARDED vectors:
  * whole on devs[0], with the full increment semantics of a one-device context; the vectors of one call are all
- * sharded or all unsharded.  The same device may appear more than once in devs[] (ranks then share a GPU, each
- * with its own stream, and run without programmatic dependent launch): the sharded path on a one-GPU box. */
+ * sharded or all unsharded.  The same device may appear more than once in devs[]: ranks then share a GPU, each with
+ * its own stream -- the sharded path on a one-GPU box.  Kernels of ONE GPU must not wait for one another (nothing
+ * guarantees they run at the same time), so such a context ends its reductions with a stream-ordered exchange
+ * instead of the in-kernel one: every rank's kernel leaves its record in its ring slot, every stream waits for the
+ * other ranks' "record written" events, and a finish kernel per rank folds the records in rank order -- the same
+ * fold, the same bits.  lbk_set_fused_exchange(ctx, 0 / 1) selects that exchange / the in-kernel one on any
+ * multi-device context (rank contexts can be driven by hand only with the in-kernel exchange). */
 int lbk_init_multi(int ndev, const int *devs, lbk_ctx **ctx);
 /* The rank context of rank r (borrowed; it goes with the multi-device context): a one-device context with
  * nranks = ndev whose sharded vectors are that rank's blocks -- for callers that drive the ranks themselves. */
 int lbk_multi_rank(lbk_ctx *ctx, int rank, lbk_ctx **rank_ctx);
+/* The scalar rank `rank` itself holds for the most recent SYNCHRONOUS reduction (8 bytes: the float / double in the
+ * low bytes, or the int64 index).  All ranks fold the same records in the same order; this lets a test see it. */
+int lbk_multi_result(lbk_ctx *ctx, int rank, void *out8);
 /* enabled = 1: one launcher thread per device (they spin for 200 us after a call, then sleep); 0: the calling
  * thread launches rank after rank (each launch costs 2-3 us, so the last of 8 GPUs starts ~20 us late). */
 int lbk_set_multi_threads(lbk_ctx *ctx, int enabled);

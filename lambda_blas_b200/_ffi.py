@@ -38,6 +38,7 @@ PROTOTYPES = {
     "lbk_init": (_int, [_int, _pvp]),
     "lbk_init_multi": (_int, [_int, _pint, _pvp]),
     "lbk_multi_rank": (_int, [_vp, _int, _pvp]),
+    "lbk_multi_result": (_int, [_vp, _int, _vp]),
     "lbk_set_multi_threads": (_int, [_vp, _int]),
     "lbk_set_exchange_timeout": (_int, [_vp, _i64]),
     "lbk_shutdown": (_int, [_vp]),

@@ -953,13 +953,24 @@ reduce_strided_kernel(const typename Op::Scalar *x, i64 incx, i64 kx0, const typ
                       i64 idx_base, Record *partials, unsigned *ticket, FinishArgs fa)
 {
     using T = typename Op::Scalar;
-    typename Op::Partial p = Op::empty();
     // a plain grid-stride loop: the compiler unrolls it four times with the loads hoisted, which measured
-    // faster than explicit tiling (ptxas interleaves predicated tile loads with their uses)
+    // faster than explicit tiling (ptxas interleaves predicated tile loads with their uses).  The loop keeps the
+    // routine's register accumulator (for iamax: running maximum + ordinal of its first occurrence, one compare per
+    // element -- profiles/r02_ncu_more.md: merging a (key, 64-bit index) candidate per element ran at a third of the
+    // DRAM rate); the ordinal becomes an index once, after the loop.
     const i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        Op::single(p, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : T(0), idx_base + i);
+    const i64 first = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    typename Op::Acc acc = Op::zero();
+    unsigned ord = 0;
+    for (i64 i = first; i < n; i += stride, ++ord)
+        Op::step(acc, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : T(0), ord);
+    typename Op::Partial p = Op::empty();
     const u64 x0_bits = apply_x0<Op>(p, fa);
+    if constexpr (Op::IS_IAMAX) {
+        if (acc.val >= T(0)) p = Op::merge(Op::candidate(acc.val, idx_base + first + (i64)acc.ord * stride), p);
+    } else {
+        Op::add_acc(p, acc);
+    }
     grid_finish<Op>(p, partials, ticket, fa, x0_bits);
 }
 
@@ -967,6 +978,23 @@ __global__ void finish_records_kernel(const Record *recs, int nranks, FinishArgs
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     finish_record(fold_by_kind(recs, nranks, fa.kind), fa);
+}
+
+// The single-process multi-device context's stream-ordered exchange (no kernel waits for another): every rank's
+// reduction kernel leaves its record in its own ring slot (mode 1), the host makes every rank's stream wait for
+// the other ranks' "record written" events, and this kernel then reads all ranks' slots -- peer memory, or mapped
+// host memory between devices that are not peers -- and folds them in rank order.
+__global__ void finish_gather_kernel(const Record *const *srcs, int slot, int nranks, FinishArgs fa)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Record all[kMaxRanks];
+    for (int r = 0; r < nranks; ++r) {
+        const volatile u64 *src = reinterpret_cast<const volatile u64 *>(srcs[r] + slot);
+        u64 *dst = reinterpret_cast<u64 *>(&all[r]);
+#pragma unroll
+        for (int w = 0; w < (int)(sizeof(Record) / 8); ++w) dst[w] = src[w];
+    }
+    finish_record(fold_by_kind(all, nranks, fa.kind), fa);
 }
 
 // ------------------------------------------------------------------------------------------------

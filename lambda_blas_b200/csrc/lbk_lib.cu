@@ -41,15 +41,18 @@ static_assert(sizeof(lbk_record) == sizeof(Record), "host and device records sha
     X(0, 4, 4, 1) X(1, 4, 2, 1) X(2, 4, 8, 1) X(3, 8, 2, 1) X(4, 8, 4, 1) X(5, 4, 4, 0) \
     X(6, 8, 1, 1) X(7, 4, 1, 1) X(8, 1, 4, 1) X(9, 8, 2, 0) X(10, 8, 8, 1) \
     X(11, 8, 4, 2) X(12, 8, 4, 3) X(13, 8, 4, 4) X(14, 8, 4, 5) \
-    X(15, 8, 4, 6) X(16, 8, 2, 6) X(17, 8, 1, 6) X(18, 8, 8, 6) X(19, 4, 4, 6) X(20, 4, 2, 6) X(21, 4, 8, 6) X(22, 4, 1, 6)
-constexpr int kNumVariants = 23;
-static const int kVariantVec[kNumVariants] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 4, 4, 4, 4};
-constexpr int kScalarVariant = 8;   // VEC == 1: any alignment
+    X(15, 8, 4, 6) X(16, 8, 2, 6) X(17, 8, 1, 6) X(18, 8, 8, 6) X(19, 4, 4, 6) X(20, 4, 2, 6) X(21, 4, 8, 6) X(22, 4, 1, 6) \
+    X(23, 1, 8, 6) X(24, 1, 16, 6) X(25, 1, 16, 1) X(26, 1, 8, 1)
+constexpr int kNumVariants = 27;
+static const int kVariantVec[kNumVariants] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 4, 4, 4, 4, 1, 1, 1, 1};
+constexpr int kScalarVariant = 8;   // VEC == 1: any alignment (the reversed pairing's any-alignment shape)
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
 
 // launch shapes are per routine and shared by the Float and Double instances (they are in bytes per access)
-enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_FILL, R_MAPSTRIDED, R_REDSTRIDED, R_COUNT };
-static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm", "fill", "mapstrided", "redstrided"};
+enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_FILL, R_MAPSTRIDED, R_REDSTRIDED,
+               R_MAPMISALIGNED, R_REDMISALIGNED, R_COUNT };
+static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm", "fill", "mapstrided", "redstrided",
+                                            "mapmisaligned", "redmisaligned"};
 struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
 // Defaults from the n = 2^28 sweeps on B200 (profiles/r01_tune_*.csv; tools/tune.py), reductions tuned
 // with their tails overlapped (PDL).  blocks_per_sm 0 = one resident wave (occupancy x SMs); larger
@@ -67,6 +70,10 @@ static const LaunchCfg kDefaultCfg[R_COUNT] = {
     /* the general-stride map kernel: variant 0/1 = without/with the load fence (no measurable effect
        there); threads / blocks_per_sm 0 = chosen from the increments in launch_map_strided */ {0, 0, 0},
     /* the general-stride reduce kernel: threads (<= 256) and blocks per SM of its grid-stride loop (0: from the increments) */ {0, 256, 0},
+    /* unit stride, operands misaligned DIFFERENTLY (x and y start at different offsets inside a 16-byte pack): 4-byte accesses,
+       fully coalesced (a warp still moves 128 contiguous bytes per instruction), many of them in flight per thread and as large
+       a tile per block as the wide shapes have -- profiles/r02_misaligned.md */
+    /* map */ {26, 256, kOneTilePerBlock}, /* reduce */ {26, 512, 16},
 };
 
 constexpr int kMaxGrid = 148 * 32 * 2;   // partial-record scratch (blocks)
@@ -89,6 +96,16 @@ struct lbk_ctx {
     bool threaded = false;
     bool host_mailbox = false;        // the mailboxes live in mapped host memory (no peer access between the devices)
     void *sink = nullptr;             // 64 device bytes: where ranks >= 1 put the scalar of an enqueue-only reduction
+    // the stream-ordered exchange of a multi-device context (ranks that share a device, or fused exchange off):
+    // this rank's record ring (two parities), the table of all ranks' rings, the "record written" event, and the
+    // finish this rank still owes for the reduction it launched last (lbk_lib.cu, exchange_finish)
+    Record *rec_ring = nullptr;
+    const Record **ring_table_dev = nullptr;
+    cudaEvent_t xchg_ev = nullptr;
+    bool finish_pending = false;
+    bool in_multi_call = false;       // set by the multi-device context around a fanned-out reduction
+    FinishArgs pending_fa;
+    unsigned ring_seq = 0;
     Record *partials = nullptr;
     unsigned *ticket = nullptr;
     double *snap = nullptr;           // two slots: snapshots of x[0], y[0] for zero output increments
@@ -320,6 +337,9 @@ static void destroy_one(lbk_ctx *c)
             nccl_api()->CommDestroy(c->comm);
         }
         if (c->mailbox) { if (c->host_mailbox) cudaFreeHost(c->mailbox); else cudaFree(c->mailbox); }
+        if (c->rec_ring) { if (c->host_mailbox) cudaFreeHost(c->rec_ring); else cudaFree(c->rec_ring); }
+        cudaFree(c->ring_table_dev);
+        if (c->xchg_ev) cudaEventDestroy(c->xchg_ev);
         cudaFree(c->peers_dev);
         if (c->error_flag_host) cudaFreeHost(c->error_flag_host);
         cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->snap); cudaFree(c->sink);
@@ -442,6 +462,12 @@ extern "C" int lbk_init_multi(int ndev, const int *devs, lbk_ctx **out)
             if (peer) { e = cudaMalloc(&s->mailbox, mb); if (e == cudaSuccess) e = cudaMemset(s->mailbox, 0, mb); }
             else { e = cudaHostAlloc((void **)&s->mailbox, mb, cudaHostAllocPortable | cudaHostAllocMapped); if (e == cudaSuccess) memset(s->mailbox, 0, mb); }
             if (e == cudaSuccess) e = cudaMalloc(&s->peers_dev, sizeof(void *) * lbk::kMaxRanks);
+            if (e == cudaSuccess) {
+                if (peer) { e = cudaMalloc(&s->rec_ring, 2 * sizeof(Record)); if (e == cudaSuccess) e = cudaMemset(s->rec_ring, 0, 2 * sizeof(Record)); }
+                else { e = cudaHostAlloc((void **)&s->rec_ring, 2 * sizeof(Record), cudaHostAllocPortable | cudaHostAllocMapped); if (e == cudaSuccess) memset(s->rec_ring, 0, 2 * sizeof(Record)); }
+            }
+            if (e == cudaSuccess) e = cudaMalloc(&s->ring_table_dev, sizeof(void *) * lbk::kMaxRanks);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->xchg_ev, cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
             if (e != cudaSuccess) return bail(LBK_ERR_CUDA, std::string("lbk_init_multi: mailbox: ") + cudaGetErrorString(e));
         }
@@ -450,16 +476,19 @@ extern "C" int lbk_init_multi(int ndev, const int *devs, lbk_ctx **out)
             DevGuard g(s->device);
             for (int q = 0; q < ndev; ++q) s->peer_ptrs[q] = m->subs[q]->mailbox;     // unified addressing: the same pointer on every device
             cudaError_t e = cudaMemcpy(s->peers_dev, s->peer_ptrs, sizeof(void *) * lbk::kMaxRanks, cudaMemcpyHostToDevice);
+            const Record *rings[lbk::kMaxRanks] = {};
+            for (int q = 0; q < ndev; ++q) rings[q] = m->subs[q]->rec_ring;
+            if (e == cudaSuccess) e = cudaMemcpy(s->ring_table_dev, rings, sizeof(void *) * lbk::kMaxRanks, cudaMemcpyHostToDevice);
             if (e != cudaSuccess) return bail(LBK_ERR_CUDA, std::string("lbk_init_multi: peer table: ") + cudaGetErrorString(e));
-            s->fused_exchange = true;
+            // Ranks that SHARE a device must not wait for one another inside kernels: nothing guarantees that two
+            // kernels of one GPU run at the same time (and the next kernel of a stream, resident early under
+            // programmatic dependent launch, can hold the slots the awaited kernel needs).  There the exchange is
+            // stream-ordered instead: records, events, a finish kernel (exchange_finish).
+            s->fused_exchange = !dup;
             s->exchange_seq = 0;
-            // Two ranks on ONE device: a kernel's last block waits in the exchange for the other rank's kernel, which
-            // needs SM slots -- slots that this rank's NEXT kernel, resident early under programmatic dependent launch
-            // and parked at its griddepcontrol.wait, could be holding.  No early residency on a shared device.
-            if (dup) { s->pdl.enabled = false; }
         }
         m->host_mailbox = !peer;
-        m->fused_exchange = true;
+        m->fused_exchange = !dup;
         const char *t = getenv("LBK_MULTI_THREADS");
         m->threaded = t ? atoi(t) != 0 : !dup;
         if (m->threaded) make_team(m);
@@ -473,6 +502,20 @@ extern "C" int lbk_multi_rank(lbk_ctx *c, int rank, lbk_ctx **out)
     if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_multi_rank: null argument");
     if (!is_multi(c) || rank < 0 || rank >= (int)c->subs.size()) return fail(c, LBK_ERR_ARG, "lbk_multi_rank: not a multi-device context, or no such rank");
     *out = c->subs[rank];
+    return LBK_OK;
+}
+
+// The scalar rank `rank` itself holds for the context's most recent SYNCHRONOUS reduction (8 bytes: a float or double
+// in the low bytes, or the int64 index): every rank computes the result from the same records in the same order, and
+// this is how a test sees that they all hold the same bits.  Synchronises that rank's stream.
+extern "C" int lbk_multi_result(lbk_ctx *c, int rank, void *out8)
+{
+    if (!c || !out8) return fail(c, LBK_ERR_ARG, "lbk_multi_result: null argument");
+    if (!is_multi(c) || rank < 0 || rank >= (int)c->subs.size()) return fail(c, LBK_ERR_ARG, "lbk_multi_result: not a multi-device context, or no such rank");
+    lbk_ctx *s = c->subs[rank];
+    DevGuard guard(s->device);
+    CU(c, cudaStreamSynchronize(s->stream));
+    memcpy(out8, s->result_host, 8);
     return LBK_OK;
 }
 
@@ -518,6 +561,7 @@ extern "C" int lbk_sync(lbk_ctx *c)
     if (!c) return fail(nullptr, LBK_ERR_ARG, "lbk_sync: null context");
     LIVE(c, "lbk_sync");
     if (is_multi(c)) return all_ranks(c, [](lbk_ctx *s, int) { return lbk_sync(s); });
+    ON_DEVICE(c);
     CU(c, cudaStreamSynchronize(c->stream));
     return check_exchange_error(c);
 }
@@ -681,8 +725,10 @@ extern "C" int lbk_comm_transport(lbk_ctx *c, int *fused)
 extern "C" int lbk_set_fused_exchange(lbk_ctx *c, int enabled)
 {
     if (!c) return fail(c, LBK_ERR_ARG, "lbk_set_fused_exchange: null context");
-    if (is_multi(c) || c->parent) {
-        if (!enabled && c->nranks > 1) return fail(c, LBK_ERR_UNSUPPORTED, "lbk_set_fused_exchange: a multi-device context has no NCCL communicator; its exchange is always in-kernel");
+    if (c->parent) return fail(c, LBK_ERR_ARG, "lbk_set_fused_exchange: set it on the multi-device context, for all ranks");
+    if (is_multi(c)) {      // in-kernel over the peer mailboxes (1) or stream-ordered: records, events, a finish kernel (0)
+        for (lbk_ctx *s : c->subs) { s->fused_exchange = enabled != 0 && c->subs.size() > 1; }
+        c->fused_exchange = enabled != 0 && c->subs.size() > 1;
         return LBK_OK;
     }
     if (enabled && !c->mailbox) return fail(c, LBK_ERR_UNSUPPORTED, "lbk_set_fused_exchange: peer mailboxes were not mapped on this communicator");
@@ -889,6 +935,7 @@ extern "C" int lbk_vec_upload_async(lbk_vec *v, const void *host, int64_t len)
     if (!v || len < 0 || len > (is_multi(v->ctx) ? v->global_len : v->len) || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_upload: bad argument");
     LIVE(v->ctx, "lbk_vec_upload");
     if (is_multi(v->ctx)) return multi_transfer(v, (const char *)host, nullptr, len, true);
+    ON_DEVICE(v->ctx);
     if (len) { lbk_pdl::interrupt(v->ctx->pdl); CU(v->ctx, cudaMemcpyAsync(v->ptr, host, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream)); }
     return LBK_OK;
 }
@@ -902,6 +949,7 @@ extern "C" int lbk_vec_download_async(const lbk_vec *v, void *host, int64_t len)
     if (!v || len < 0 || len > (is_multi(v->ctx) ? v->global_len : v->len) || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, "lbk_vec_download: bad argument");
     LIVE(v->ctx, "lbk_vec_download");
     if (is_multi(v->ctx)) return multi_transfer(const_cast<lbk_vec *>(v), nullptr, (char *)host, len, false);
+    ON_DEVICE(v->ctx);
     if (len) { lbk_pdl::interrupt(v->ctx->pdl); CU(v->ctx, cudaMemcpyAsync(host, v->ptr, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyDeviceToHost, v->ctx->stream)); }
     return LBK_OK;
 }
@@ -1047,6 +1095,7 @@ extern "C" int lbk_event_elapsed_ms(lbk_event *a, lbk_event *b, float *ms)
         *ms = worst;
         return LBK_OK;
     }
+    ON_DEVICE(b->ctx);
     CU(b->ctx, cudaEventSynchronize(b->ev));
     CU(b->ctx, cudaEventElapsedTime(ms, a->ev, b->ev));
     return LBK_OK;
@@ -1153,16 +1202,24 @@ template <class T> static inline int variant_vec(int variant)
 
 // Picks the variant that the pointers' alignment allows and the scalar head count.
 template <class T>
-static void resolve_alignment(int *variant, i64 *head, const T *const *ptrs, int nptr, i64 n)
+static bool resolve_alignment(int *variant, i64 *head, const T *const *ptrs, int nptr, i64 n, int scalar_variant)
 {
     for (;;) {
         const int vec = variant_vec<T>(*variant);
-        if (vec == 1) { *head = 0; return; }
+        if (vec == 1) {
+            // 4- or 8-byte accesses need no alignment, but a warp's 128 contiguous bytes should not straddle two 128-byte
+            // lines on the WRITTEN side: peel up to a line of scalar elements so that the last pointer (a destination
+            // whenever the routine has one) starts on a line boundary (profiles/r02_misaligned.md)
+            const i64 per_line = 128 / (i64)sizeof(T);
+            const i64 m = (i64)(((uintptr_t)ptrs[nptr - 1] / sizeof(T)) % (uintptr_t)per_line);
+            *head = std::min<i64>((per_line - m) % per_line, n);
+            return *variant == scalar_variant;
+        }
         const int m = misalign(ptrs[0], vec);
         bool same = true;
         for (int i = 1; i < nptr; ++i) same = same && misalign(ptrs[i], vec) == m;
-        if (same) { *head = std::min<i64>((vec - m) % vec, n); return; }
-        *variant = (kVariantVec[*variant] == 8) ? kVec4Fallback : kScalarVariant;
+        if (same) { *head = std::min<i64>((vec - m) % vec, n); return false; }
+        *variant = (kVariantVec[*variant] == 8) ? kVec4Fallback : scalar_variant;
     }
 }
 // Reversed pairing: x+head and (y+n)-head must both be pack aligned; otherwise the scalar shape is used.
@@ -1249,9 +1306,10 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
 {
     using T = typename F::Scalar;
     const LaunchCfg &cfg = c->cfg[rid];
+    const LaunchCfg *pcfg = &cfg;
     int variant = cfg.variant;
     // the reversed pairing has one shape: 16-byte packs x 4, 128 threads, no fence (config-4 sweep, profiles/)
-    const int threads = rev ? 128 : (cfg.threads > 0 ? cfg.threads : 256);
+    int threads = rev ? 128 : (cfg.threads > 0 ? cfg.threads : 256);
     i64 head = 0;
     const void *k;
     if (rev) {
@@ -1268,13 +1326,20 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
         if (F::RY) ptrs[np++] = yr;
         if (F::WX) ptrs[np++] = xw;
         if (F::WY) ptrs[np++] = yw;
-        resolve_alignment<T>(&variant, &head, ptrs, np, n);
+        // x and y misaligned differently: 8 accesses of one element in flight per operand, or 4 for the routines that write
+        // both vectors; 256 threads (profiles/r02_misaligned.md)
+        LaunchCfg mis = c->cfg[R_MAPMISALIGNED];
+        if (mis.variant == kDefaultCfg[R_MAPMISALIGNED].variant && F::WX && F::WY) mis.variant = kScalarVariant;
+        if (resolve_alignment<T>(&variant, &head, ptrs, np, n, kVariantVec[mis.variant] == 1 ? mis.variant : kScalarVariant) && variant == mis.variant) {
+            pcfg = &c->cfg[R_MAPMISALIGNED];
+            if (mis.threads > 0) threads = mis.threads;
+        }
         k = map_kernel_ptr<F>(variant);
     }
     const i64 npack = (n - head) / variant_vec<T>(variant);
     const i64 per_tile = (i64)variant_unroll(variant) * threads;
     int grid;
-    int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid, 0x7fffffff);   // maps keep no per-block scratch
+    int s = grid_for(c, k, *pcfg, threads, (npack + per_tile - 1) / per_tile, &grid, 0x7fffffff);   // maps keep no per-block scratch
     if (s) return s;
     F fc = f;
     unsigned fence_mask = 0;     // see map_unit_kernel: always 0, but only known at run time
@@ -1474,6 +1539,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
     ON_DEVICE(c);
     const bool exchange = c->nranks > 1 && X.v->sharded;
     const bool fused = exchange && c->fused_exchange;
+    const bool by_events = exchange && !fused && c->parent != nullptr;      // a rank of a multi-device context: exchange_finish follows
     const i64 nl = X.n_local;
     const T *x = (const T *)X.ptr(), *y = Y ? (const T *)Y->ptr() : nullptr;
     const i64 incx = X.inc, incy = Y ? Y->inc : 1;
@@ -1488,11 +1554,12 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         fa.error_flag = c->error_flag_dev;
         fa.timeout_ns = c->exchange_timeout_ns;
     }
-    if (exchange && !fused && !c->comm) return fail(c, LBK_ERR_UNSUPPORTED, "sharded reduction: this context has neither peer mailboxes nor an NCCL communicator");
+    if (exchange && !fused && !by_events && !c->comm) return fail(c, LBK_ERR_UNSUPPORTED, "sharded reduction: this context has neither peer mailboxes nor an NCCL communicator");
+    if (by_events && !c->in_multi_call) return fail(c, LBK_ERR_UNSUPPORTED, "sharded reduction on a rank context: with the stream-ordered exchange (ranks sharing a device, or fused exchange off) the ranks are driven through the multi-device context");
     fa.n_global = n;
     fa.sb = sb;
     fa.out = out;
-    fa.rec_out = c->rec_send;
+    fa.rec_out = by_events ? c->rec_ring + (++c->ring_seq & 1u) : c->rec_send;
     fa.x0 = (X.i0 == 0 && nl > 0) ? x : nullptr;     // logical element 0 lives at x[0] for incx >= 1
     if (out == c->result_dev) {                        // a synchronous call: the host polls for this tag
         if (++c->result_seq == 0) ++c->result_seq;
@@ -1504,8 +1571,9 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
     const bool unit = nl > 0 && ((incx == 1 && (!Y || incy == 1)) || (Y && incx == -1 && incy == -1) || rev);
     if (unit) {
         const LaunchCfg &cfg = c->cfg[rid];
+        const LaunchCfg *pcfg = &cfg;
         int variant = cfg.variant;
-        const int threads = cfg.threads > 0 ? cfg.threads : 256;
+        int threads = cfg.threads > 0 ? cfg.threads : 256;
         const T *ptrs[2] = {x, y};
         i64 head = 0;
         const void *k;
@@ -1514,13 +1582,17 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
             k = variant == kScalarVariant ? (const void *)lbk::reduce_unit_kernel<Op, 1, 4, 1, true>
                                           : (const void *)lbk::reduce_unit_kernel<Op, vec_t<T>(4), 4, 1, true>;
         } else {
-            resolve_alignment<T>(&variant, &head, ptrs, Y ? 2 : 1, nl);
+            const LaunchCfg &mis = c->cfg[R_REDMISALIGNED];
+            if (resolve_alignment<T>(&variant, &head, ptrs, Y ? 2 : 1, nl, kVariantVec[mis.variant] == 1 ? mis.variant : kScalarVariant) && variant == mis.variant) {
+                pcfg = &mis;
+                if (mis.threads > 0) threads = mis.threads;
+            }
             k = reduce_kernel_ptr<Op>(variant);
         }
         const i64 npack = (nl - head) / variant_vec<T>(variant);
         const i64 per_tile = (i64)variant_unroll(variant) * threads;
         int grid;
-        int s = grid_for(c, k, cfg, threads, (npack + per_tile - 1) / per_tile, &grid);
+        int s = grid_for(c, k, *pcfg, threads, (npack + per_tile - 1) / per_tile, &grid);
         if (s) return s;
         i64 nn = nl, ib = idx_base;
         lbk_pdl::Op op;
@@ -1549,6 +1621,13 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         lbk::reduce_strided_kernel<Op><<<grid, threads, 0, c->stream>>>(x, incx, first_index(nl, incx), y, incy,
                                                                           first_index(nl, incy), nl, idx_base, c->partials, c->ticket, fa);
         KERNEL_CHECK(c);
+    }
+    if (by_events) {           // the record is in this rank's ring slot once this event has fired
+        lbk_pdl::interrupt(c->pdl);
+        CU(c, cudaEventRecord(c->xchg_ev, c->stream));
+        c->pending_fa = fa;
+        c->finish_pending = true;
+        return LBK_OK;
     }
     if (exchange && !fused) {
         lbk_pdl::interrupt(c->pdl);
@@ -1620,7 +1699,7 @@ static int finish_sync(lbk_ctx *c, int s, R *out)
         if (!seen && (spin & 63) == 63 &&
             std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
     }
-    if (!seen) CU(c, cudaStreamSynchronize(c->stream));
+    if (!seen) { ON_DEVICE(c); CU(c, cudaStreamSynchronize(c->stream)); }
     std::atomic_thread_fence(std::memory_order_acquire);
     *out = *reinterpret_cast<volatile R *>(c->result_host);
     return check_exchange_error(c);
@@ -1645,6 +1724,23 @@ static int ivi_common(lbk_ctx *c, const char *who, int rid, i64 n, const lbk_vec
     return reduce_dispatch<lbk::IamaxOp<T>>(c, rid, 2, n, X, nullptr, 0.0, out_dev);
 }
 
+// Second half of a multi-device context's stream-ordered exchange, after EVERY rank has launched its reduction and
+// recorded its event: this rank's stream waits for the other ranks' records, then folds all of them.
+static int exchange_finish(lbk_ctx *c)
+{
+    if (!c->finish_pending) return LBK_OK;
+    c->finish_pending = false;
+    ON_DEVICE(c);
+    lbk_pdl::interrupt(c->pdl);
+    for (lbk_ctx *q : c->parent->subs)
+        if (q != c) CU(c, cudaStreamWaitEvent(c->stream, q->xchg_ev, 0));
+    FinishArgs fa = c->pending_fa;
+    fa.mode = 0;
+    lbk::finish_gather_kernel<<<1, 32, 0, c->stream>>>(c->ring_table_dev, (int)(c->ring_seq & 1u), c->nranks, fa);
+    KERNEL_CHECK(c);
+    return LBK_OK;
+}
+
 // A reduction on a multi-device context.  call(rank context, rank, out) enqueues the routine on one rank with
 // `out` as the device-visible address of its scalar: every rank computes the same bits (the records are folded
 // in rank order everywhere); the caller gets rank 0's -- through rank 0's mapped result slot (synchronous
@@ -1664,7 +1760,10 @@ static int multi_reduce(lbk_ctx *m, const char *who, std::initializer_list<const
         if ((s = check_out_vec(m->subs[0], who, out_vec->parts[0], out_dtype, out_bytes))) { m->err = m->subs[0]->err; return s; }
         out0 = out_vec->parts[0]->ptr;
     }
+    for (lbk_ctx *sc : m->subs) { sc->in_multi_call = true; sc->finish_pending = false; }
     s = fan_out(m, count, [&](lbk_ctx *sc, int r) { return call(sc, r, out_host ? sc->result_dev : (r == 0 ? out0 : sc->sink)); });
+    for (lbk_ctx *sc : m->subs) sc->in_multi_call = false;
+    if (!s && count > 1 && !m->fused_exchange) s = fan_out(m, count, [&](lbk_ctx *sc, int) { return exchange_finish(sc); });
     if (!out_host) return s;
     s = finish_sync(m->subs[0], s, out_host);
     if (s && m->err.empty()) m->err = m->subs[0]->err;

@@ -171,6 +171,12 @@ class MultiContext(Context):
         """One launcher thread per device (True) or rank after rank from the calling thread (False)."""
         _ffi.check(_ffi.lib().lbk_set_multi_threads(self.handle, int(enabled)), self.handle)
 
+    def rank_result(self, rank: int) -> bytes:
+        """The 8 bytes rank `rank` itself holds for the most recent synchronous reduction (lbk_multi_result)."""
+        buf = C.create_string_buffer(8)
+        _ffi.check(_ffi.lib().lbk_multi_result(self.handle, rank, buf), self.handle)
+        return buf.raw
+
     def rank_context(self, rank: int) -> "Context":
         """The borrowed one-device context of `rank` (for callers that drive the ranks themselves)."""
         cache = self.__dict__.setdefault("_ranks", {})

@@ -135,3 +135,39 @@ def test_strided_sweep_config4(blas, ctx, oracle):
             gx, gy = blas.srot(n, xv, incx, yv, incy, c, s)
             wx, wy = oracle.srot(n, hx, incx, hy, incy, c, s)
             assert np.array_equal(bits(gx.to_host()), bits(wx)) and np.array_equal(bits(gy.to_host()), bits(wy)), (incx, incy)
+
+
+def test_strided_sweep_config4_full_size(blas, ctx, oracle):
+    """BASELINE.json configs[3] at its stated size, n = 2^26: inc in {1,2,7,-1} squared for sdot / saxpy / srot.  The inputs are
+    generated on the device (2 x 1.9 GB); the elementwise results are compared bit for bit with the oracle on windows of logical
+    elements (head, middle, tail) whose inputs the host regenerates from the same counter hash; sdot against the device's own
+    double-precision accumulation (sdsdot, itself oracle-checked to 1 ulp at the smaller sizes) within the reduction bound."""
+    n = 1 << 26
+    span = 1 + (n - 1) * 7
+    x, y = ctx.alloc(span).fill_hash(1), ctx.alloc(span).fill_hash(2)
+    c, s = np.float32(np.cos(0.3)), np.float32(np.sin(0.3))
+    w = 4096
+    starts = [0, n // 2 - 1234, n - w]
+
+    def window(i0, inc, seed):
+        """Physical range holding logical elements [i0, i0+w) of a call (n, inc), and the host copy of it."""
+        a = abs(inc)
+        lo = i0 * a if inc > 0 else (n - 1 - (i0 + w - 1)) * a
+        ln = 1 + (w - 1) * a
+        return lo, ln, blas.hash_fill_reference(ln, seed, offset=lo)
+
+    for incx in (1, 2, 7, -1):
+        for incy in (1, 2, 7, -1):
+            lx, ly = 1 + (n - 1) * abs(incx), 1 + (n - 1) * abs(incy)
+            xv, yv = x.view(0, lx), y.view(0, ly)
+            wide, got = float(blas.sdsdot(n, 0.0, xv, incx, yv, incy)), float(blas.sdot(n, xv, incx, yv, incy))
+            assert abs(got - wide) <= 64 * 2.0 ** -24 * n / 2, (incx, incy, got, wide)
+            ya = blas.saxpy(n, 0.75, xv, incx, yv, incy)
+            gx, gy = blas.srot(n, xv, incx, yv, incy, c, s)
+            for i0 in starts:
+                xlo, xln, hx = window(i0, incx, 1)
+                ylo, yln, hy = window(i0, incy, 2)
+                assert np.array_equal(bits(ya.view(ylo, yln).to_host()), bits(oracle.saxpy(w, 0.75, hx, incx, hy, incy))), (incx, incy, i0)
+                wx, wy = oracle.srot(w, hx, incx, hy, incy, c, s)
+                assert np.array_equal(bits(gx.view(xlo, xln).to_host()), bits(wx)) and np.array_equal(bits(gy.view(ylo, yln).to_host()), bits(wy)), (incx, incy, i0)
+            del ya, gx, gy

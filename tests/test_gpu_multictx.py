@@ -129,24 +129,44 @@ def test_nan_rule_and_ties_across_ranks(blas, oracle, mctx):
 
 
 def test_every_rank_holds_the_same_bits(blas, mctx):
-    """Drive the ranks by hand through their rank contexts (lbk_multi_rank): each rank's own copy of the result is
-    bit-identical to every other rank's, for all four reductions (the fold is in rank order everywhere)."""
+    """Every rank folds the same records in the same order: each rank's own copy of the result (lbk_multi_result) is
+    bit-identical to every other rank's, for all four reductions and both exchanges."""
+    R, n = mctx.nranks, (1 << 18) + 5
+    x, y = mctx.alloc_sharded(n).fill_hash(3), mctx.alloc_sharded(n).fill_hash(4)
+    hx = blas.hash_fill_reference(n, 3)
+    shared_gpu = len(set(mctx.devices)) < R
+    for fused in ((False,) if shared_gpu else (True, False)):      # ranks that share a GPU never wait for one another in a kernel
+        mctx.set_fused_exchange(fused)
+        assert mctx.fused_exchange() == fused
+        for nbytes, call in ((4, lambda: blas.sdot(n, x, 1, y, 1)), (4, lambda: blas.snrm2(n, x, 1)), (4, lambda: blas.sasum(n, x, 1)),
+                             (8, lambda: blas.isamax(n, x, 1))):
+            got = call()
+            mine = [mctx.rank_result(r)[:nbytes] for r in range(R)]
+            assert all(b == mine[0] for b in mine), mine
+            want = np.frombuffer(mine[0], dtype=np.int64 if nbytes == 8 else np.float32)[0]
+            assert want == got
+        assert blas.isamax(n, x, 1) == int(np.argmax(np.abs(hx)))
+    mctx.set_fused_exchange(not shared_gpu)
+
+
+def test_ranks_driven_by_hand(blas, mctx):
+    """The rank contexts (lbk_multi_rank) are one-device contexts whose sharded vectors are their blocks: a caller may drive them
+    itself -- with the in-kernel exchange, i.e. on distinct GPUs; with the stream-ordered exchange the call is refused."""
     from lambda_blas_b200 import inplace as ip
     R, n = mctx.nranks, (1 << 18) + 5
     x, y = mctx.alloc_sharded(n).fill_hash(3), mctx.alloc_sharded(n).fill_hash(4)
     outs = [mctx.rank_context(r).alloc(8) for r in range(R)]
-    got = []
-    for nwords, call in ((1, lambda r: ip.sdot_async(n, x.part(r), 1, y.part(r), 1, outs[r])), (1, lambda r: ip.snrm2_async(n, x.part(r), 1, outs[r])),
-                         (1, lambda r: ip.sasum_async(n, x.part(r), 1, outs[r])), (2, lambda r: ip.isamax_async(n, x.part(r), 1, outs[r]))):
-        for r in range(R):          # enqueue only: rank 0's kernel waits in its exchange until rank R-1's has been launched
-            call(r)
-        mctx.sync()
-        words = [outs[r].to_host()[:nwords].view(np.uint32).tolist() for r in range(R)]      # a float result is one word, the index two
-        assert all(w == words[0] for w in words), words
-        got.append(words[0])
-    hx = blas.hash_fill_reference(n, 3)
-    assert np.array(got[3], dtype=np.uint32).view(np.int64)[0] == int(np.argmax(np.abs(hx)))
-    assert np.array(got[2], dtype=np.uint32).view(np.float32)[0] == pytest.approx(float(np.sum(np.abs(hx.astype(np.float64)))), rel=1e-5)
+    if len(set(mctx.devices)) < R:
+        with pytest.raises(blas.LbkError) as ei:
+            ip.sdot_async(n, x.part(0), 1, y.part(0), 1, outs[0])
+        assert ei.value.status == 6
+        return
+    for r in range(R):          # enqueue only: rank 0's kernel waits in its exchange until rank R-1's has been launched
+        ip.sdot_async(n, x.part(r), 1, y.part(r), 1, outs[r])
+    mctx.sync()
+    words = [outs[r].to_host()[:1].view(np.uint32).tolist() for r in range(R)]
+    assert all(w == words[0] for w in words), words
+    assert np.array(words[0], dtype=np.uint32).view(np.float32)[0] == blas.sdot(n, x, 1, y, 1)
 
 
 def test_unsharded_vectors_keep_full_semantics(blas, oracle, mctx):
@@ -183,6 +203,7 @@ def test_a_missing_peer_times_out_instead_of_hanging(blas):
     from lambda_blas_b200 import inplace as ip
     m = blas.MultiContext([0, 0], threads=False)
     try:
+        m.set_fused_exchange(True)          # the in-kernel exchange, asked for explicitly: ONE kernel, waiting alone
         m.set_exchange_timeout(100)
         x = m.alloc_sharded(1 << 12).fill_hash(1)
         r0 = m.rank_context(0)

@@ -46,7 +46,7 @@ def test_streaming_kernels_use_wide_accesses_and_pdl(sass):
     assert unit
     for name, ins in unit.items():
         wide = [i for i in ins if re.match(r"(LDG|STG)\.E.*\.(128|256)", i)]
-        scalar_shape = "ELi1ELi4E" in name           # the any-alignment shape (one element per access)
+        scalar_shape = re.search(r"ELi1ELi(4|8|16)E", name) is not None      # the any-alignment shapes (one element per access)
         assert wide or scalar_shape, name
         assert "PREEXIT" in ins and "ACQBULK" in ins, name           # releases its dependents, waits for its predecessors
     reduces = [v for k, v in kernels.items() if "reduce_unit_kernel" in k]
