@@ -7,8 +7,10 @@ The call surface is the reference's (src/Numerical/BLAS/Single.hs:41-61): the
 polymorphic names (@dot@, @axpy@, ...) with their deprecated aliases for Float
 (@sdot@, ..., Single.hs:84,113,129,147,165,201,222,421,441,484) and Double (@ddot@,
 ..., Single.hs:86,115,131,149,167,203,224,423,443,486): same argument order, same
-results -- with @Vector a@ replaced by the device-resident 'DVector' @a@ and the
-result in 'IO', because the work is enqueued on a CUDA stream.  Where the reference
+results -- with @Vector a@ replaced by the device-resident 'DVector' @a@ (defined in
+"Numerical.BLAS.Device.Types", re-exported by the patched "Numerical.BLAS.Types") and the
+result in 'IO', because the work is enqueued on a CUDA stream.  The O(1) host
+scalars 'rotg' / 'rotmg' stay pure, exactly as in the reference (Single.hs:274,318).  Where the reference
 is polymorphic over @Num a@/@Storable a@, this module is polymorphic over 'Elt',
 the class of the two element types the C ABI is instantiated for.  Like the reference the vector
 routines are pure in effect: they return NEW device vectors and leave their
@@ -28,7 +30,14 @@ lambda_blas_b200/_ffi.py, which is what the test-suite drives.
 module Numerical.BLAS.Device
     ( -- * Context and device vectors
       Context, withContext, newContext, closeContext, sync
-    , Elt, DVector, dvLength, toDevice, fromDevice, cloneD
+    , Elt, DVector, dvLength, dvLayout, Layout(..), toDevice, fromDevice, cloneD
+      -- * One host thread, many GPUs: sharded vectors (lbk_init_multi)
+    , withContextMulti, newContextMulti, toDeviceSharded, allocSharded, setMultiThreads, setFusedExchange
+    , setExchangeTimeout
+      -- * Asynchronous and pinned transfers
+    , withRegistered, toDeviceAsync, fromDeviceAsync
+      -- * Enqueue-only reductions (the result lands in a device vector)
+    , dotAsync, asumAsync, nrm2Async, iamaxAsync
       -- * Products and norms
     , dot, sdsdot, asum, nrm2, iamax
     , sdot, ddot, sasum, dasum, snrm2, dnrm2, isamax, idamax
@@ -42,8 +51,9 @@ module Numerical.BLAS.Device
     , LbkError(..)
     ) where
 
-import Control.Exception (Exception, bracket, throwIO)
+import Control.Exception (bracket, bracket_, throwIO)
 import Control.Monad (when)
+import Data.Word (Word8)
 import qualified Data.Vector.Storable as V
 import qualified Data.Vector.Storable.Mutable as VM
 import Foreign.C.String (CString, peekCString)
@@ -52,23 +62,10 @@ import Foreign.ForeignPtr
 import Foreign.Marshal.Alloc (alloca)
 import Foreign.Marshal.Array (allocaArray, peekArray, withArray)
 import Foreign.Ptr
-import Foreign.Storable (Storable, peek)
+import Foreign.Storable (Storable, peek, sizeOf)
+import System.IO.Unsafe (unsafePerformIO)
+import Numerical.BLAS.Device.Types
 import Numerical.BLAS.Types (GivensRot(..), ModGivensRot(..))
-
--- ---------------------------------------------------------------------------
--- opaque handles
--- ---------------------------------------------------------------------------
-data LbkCtx
-data LbkVec a          -- phantom: the element type of the device buffer
-
--- | One GPU, one stream, reduction scratch (and, after @lbk_comm_init@, a communicator).
-newtype Context = Context (Ptr LbkCtx)
-
--- | A device-resident @Vector a@: a finalised handle plus the context that owns it.
-data DVector a = DVector { dvCtx :: !Context, dvPtr :: !(ForeignPtr (LbkVec a)), dvLength :: !Int }
-
-data LbkError = LbkError Int String deriving Show
-instance Exception LbkError
 
 -- ---------------------------------------------------------------------------
 -- the C ABI (include/lbk.h).  `unsafe` only for calls that merely enqueue or are
@@ -78,6 +75,12 @@ instance Exception LbkError
 type V a = Ptr (LbkVec a)
 
 foreign import ccall        "lbk_init"        c_init        :: CInt -> Ptr (Ptr LbkCtx) -> IO CInt
+foreign import ccall        "lbk_init_multi"  c_init_multi  :: CInt -> Ptr CInt -> Ptr (Ptr LbkCtx) -> IO CInt
+foreign import ccall unsafe "lbk_set_multi_threads"    c_set_multi_threads    :: Ptr LbkCtx -> CInt -> IO CInt
+foreign import ccall unsafe "lbk_set_fused_exchange"   c_set_fused_exchange   :: Ptr LbkCtx -> CInt -> IO CInt
+foreign import ccall unsafe "lbk_set_exchange_timeout" c_set_exchange_timeout :: Ptr LbkCtx -> Int -> IO CInt
+foreign import ccall        "lbk_host_register"   c_host_register   :: Ptr Word8 -> Int -> IO CInt
+foreign import ccall        "lbk_host_unregister" c_host_unregister :: Ptr Word8 -> IO CInt
 foreign import ccall        "lbk_shutdown"    c_shutdown    :: Ptr LbkCtx -> IO CInt
 foreign import ccall        "lbk_sync"        c_sync        :: Ptr LbkCtx -> IO CInt
 foreign import ccall unsafe "lbk_last_error"  c_last_error  :: Ptr LbkCtx -> IO CString
@@ -88,6 +91,14 @@ foreign import ccall        "lbk_vec_alloc"    s_vec_alloc    :: Ptr LbkCtx -> I
 foreign import ccall        "lbk_vec_upload"   s_vec_upload   :: V Float -> Ptr Float -> Int -> IO CInt
 foreign import ccall        "lbk_vec_download" s_vec_download :: V Float -> Ptr Float -> Int -> IO CInt
 foreign import ccall        "lbk_vec_clone"    s_vec_clone    :: V Float -> Ptr (V Float) -> IO CInt
+foreign import ccall        "lbk_vec_alloc_sharded" s_vec_alloc_sharded :: Ptr LbkCtx -> Int -> Ptr (V Float) -> IO CInt
+foreign import ccall        "lbk_vec_alloc_like"    s_vec_alloc_like    :: V Float -> Ptr (V Float) -> IO CInt
+foreign import ccall unsafe "lbk_vec_upload_async"   s_vec_upload_async   :: V Float -> Ptr Float -> Int -> IO CInt
+foreign import ccall unsafe "lbk_vec_download_async" s_vec_download_async :: V Float -> Ptr Float -> Int -> IO CInt
+foreign import ccall unsafe "lbk_sdot_async"   s_dot_async   :: Ptr LbkCtx -> Int -> V Float -> Int -> V Float -> Int -> V Float -> IO CInt
+foreign import ccall unsafe "lbk_sasum_async"  s_asum_async  :: Ptr LbkCtx -> Int -> V Float -> Int -> V Float -> IO CInt
+foreign import ccall unsafe "lbk_snrm2_async"  s_nrm2_async  :: Ptr LbkCtx -> Int -> V Float -> Int -> V Float -> IO CInt
+foreign import ccall unsafe "lbk_isamax_async" s_iamax_async :: Ptr LbkCtx -> Int -> V Float -> Int -> V Float -> IO CInt
 foreign import ccall "lbk_sdot"   s_dot   :: Ptr LbkCtx -> Int -> V Float -> Int -> V Float -> Int -> Ptr Float -> IO CInt
 foreign import ccall "lbk_sdsdot" c_sdsdot :: Ptr LbkCtx -> Int -> Float -> V Float -> Int -> V Float -> Int -> Ptr Float -> IO CInt
 foreign import ccall "lbk_sasum"  s_asum  :: Ptr LbkCtx -> Int -> V Float -> Int -> Ptr Float -> IO CInt
@@ -113,6 +124,14 @@ foreign import ccall        "lbk_vec_alloc_f64" d_vec_alloc   :: Ptr LbkCtx -> I
 foreign import ccall        "lbk_vec_upload"   d_vec_upload   :: V Double -> Ptr Double -> Int -> IO CInt
 foreign import ccall        "lbk_vec_download" d_vec_download :: V Double -> Ptr Double -> Int -> IO CInt
 foreign import ccall        "lbk_vec_clone"    d_vec_clone    :: V Double -> Ptr (V Double) -> IO CInt
+foreign import ccall        "lbk_vec_alloc_sharded_f64" d_vec_alloc_sharded :: Ptr LbkCtx -> Int -> Ptr (V Double) -> IO CInt
+foreign import ccall        "lbk_vec_alloc_like"    d_vec_alloc_like    :: V Double -> Ptr (V Double) -> IO CInt
+foreign import ccall unsafe "lbk_vec_upload_async"   d_vec_upload_async   :: V Double -> Ptr Double -> Int -> IO CInt
+foreign import ccall unsafe "lbk_vec_download_async" d_vec_download_async :: V Double -> Ptr Double -> Int -> IO CInt
+foreign import ccall unsafe "lbk_ddot_async"   d_dot_async   :: Ptr LbkCtx -> Int -> V Double -> Int -> V Double -> Int -> V Double -> IO CInt
+foreign import ccall unsafe "lbk_dasum_async"  d_asum_async  :: Ptr LbkCtx -> Int -> V Double -> Int -> V Double -> IO CInt
+foreign import ccall unsafe "lbk_dnrm2_async"  d_nrm2_async  :: Ptr LbkCtx -> Int -> V Double -> Int -> V Double -> IO CInt
+foreign import ccall unsafe "lbk_idamax_async" d_iamax_async :: Ptr LbkCtx -> Int -> V Double -> Int -> V Double -> IO CInt
 foreign import ccall "lbk_ddot"   d_dot   :: Ptr LbkCtx -> Int -> V Double -> Int -> V Double -> Int -> Ptr Double -> IO CInt
 foreign import ccall "lbk_dasum"  d_asum  :: Ptr LbkCtx -> Int -> V Double -> Int -> Ptr Double -> IO CInt
 foreign import ccall "lbk_dnrm2"  d_nrm2  :: Ptr LbkCtx -> Int -> V Double -> Int -> Ptr Double -> IO CInt
@@ -139,6 +158,14 @@ class (Storable a, RealFrac a) => Elt a where
     cVecUpload   :: V a -> Ptr a -> Int -> IO CInt
     cVecDownload :: V a -> Ptr a -> Int -> IO CInt
     cVecClone    :: V a -> Ptr (V a) -> IO CInt
+    cVecAllocSharded  :: Ptr LbkCtx -> Int -> Ptr (V a) -> IO CInt
+    cVecAllocLike     :: V a -> Ptr (V a) -> IO CInt
+    cVecUploadAsync   :: V a -> Ptr a -> Int -> IO CInt
+    cVecDownloadAsync :: V a -> Ptr a -> Int -> IO CInt
+    cDotAsync   :: Ptr LbkCtx -> Int -> V a -> Int -> V a -> Int -> V a -> IO CInt
+    cAsumAsync  :: Ptr LbkCtx -> Int -> V a -> Int -> V a -> IO CInt
+    cNrm2Async  :: Ptr LbkCtx -> Int -> V a -> Int -> V a -> IO CInt
+    cIamaxAsync :: Ptr LbkCtx -> Int -> V a -> Int -> V a -> IO CInt
     cDot     :: Ptr LbkCtx -> Int -> V a -> Int -> V a -> Int -> Ptr a -> IO CInt
     cAsum    :: Ptr LbkCtx -> Int -> V a -> Int -> Ptr a -> IO CInt
     cNrm2    :: Ptr LbkCtx -> Int -> V a -> Int -> Ptr a -> IO CInt
@@ -160,6 +187,9 @@ class (Storable a, RealFrac a) => Elt a where
 
 instance Elt Float where
     cVecAlloc = s_vec_alloc; cVecUpload = s_vec_upload; cVecDownload = s_vec_download; cVecClone = s_vec_clone
+    cVecAllocSharded = s_vec_alloc_sharded; cVecAllocLike = s_vec_alloc_like
+    cVecUploadAsync = s_vec_upload_async; cVecDownloadAsync = s_vec_download_async
+    cDotAsync = s_dot_async; cAsumAsync = s_asum_async; cNrm2Async = s_nrm2_async; cIamaxAsync = s_iamax_async
     cDot = s_dot; cAsum = s_asum; cNrm2 = s_nrm2; cIamax = s_iamax
     cAxpy = s_axpy; cScal = s_scal; cCopy = s_copy; cSwap = s_swap; cRot = s_rot; cRotm = s_rotm
     cAxpyOop = s_axpy_oop; cScalOop = s_scal_oop; cCopyOop = s_copy_oop; cSwapOop = s_swap_oop
@@ -167,6 +197,9 @@ instance Elt Float where
 
 instance Elt Double where
     cVecAlloc = d_vec_alloc; cVecUpload = d_vec_upload; cVecDownload = d_vec_download; cVecClone = d_vec_clone
+    cVecAllocSharded = d_vec_alloc_sharded; cVecAllocLike = d_vec_alloc_like
+    cVecUploadAsync = d_vec_upload_async; cVecDownloadAsync = d_vec_download_async
+    cDotAsync = d_dot_async; cAsumAsync = d_asum_async; cNrm2Async = d_nrm2_async; cIamaxAsync = d_iamax_async
     cDot = d_dot; cAsum = d_asum; cNrm2 = d_nrm2; cIamax = d_iamax
     cAxpy = d_axpy; cScal = d_scal; cCopy = d_copy; cSwap = d_swap; cRot = d_rot; cRotm = d_rotm
     cAxpyOop = d_axpy_oop; cScalOop = d_scal_oop; cCopyOop = d_copy_oop; cSwapOop = d_swap_oop
@@ -176,33 +209,74 @@ instance Elt Double where
 -- helpers
 -- ---------------------------------------------------------------------------
 check :: Context -> CInt -> IO ()
-check (Context c) st = when (st /= 0) $ do
-    msg <- c_last_error c >>= peekCString
+check ctx st = when (st /= 0) $ do
+    msg <- c_last_error (ctxPtr ctx) >>= peekCString
     throwIO (LbkError (fromIntegral st) msg)
+
+checkNoCtx :: CInt -> IO ()
+checkNoCtx st = when (st /= 0) $ c_last_error nullPtr >>= peekCString >>= throwIO . LbkError (fromIntegral st)
 
 newContext :: Int -> IO Context
 newContext dev = alloca $ \ pp -> do
-    st <- c_init (fromIntegral dev) pp
-    when (st /= 0) $ c_last_error nullPtr >>= peekCString >>= throwIO . LbkError (fromIntegral st)
-    Context <$> peek pp
+    c_init (fromIntegral dev) pp >>= checkNoCtx
+    p <- peek pp
+    return (Context p 1)
 
+-- | ONE host thread, many GPUs (@lbk_init_multi@): rank r is @devs !! r@.  'toDeviceSharded' then makes vectors
+-- that are block-sharded over the ranks, and every routine of this module fans out over the devices; a
+-- reduction returns the scalar all ranks agree on.  'toDevice' still makes whole vectors (on the first device).
+newContextMulti :: [Int] -> IO Context
+newContextMulti devs = alloca $ \ pp -> withArray (map fromIntegral devs) $ \ pd -> do
+    c_init_multi (fromIntegral (length devs)) pd pp >>= checkNoCtx
+    p <- peek pp
+    return (Context p (length devs))
+
+-- | @lbk_shutdown@.  Device vectors that are still reachable keep the native context alive until their
+-- finalisers have run (the C library counts handles), so closing first and collecting later is safe.
 closeContext :: Context -> IO ()
-closeContext (Context c) = () <$ c_shutdown c
+closeContext ctx = () <$ c_shutdown (ctxPtr ctx)
 
 withContext :: Int -> (Context -> IO a) -> IO a
 withContext dev = bracket (newContext dev) closeContext
 
-sync :: Context -> IO ()
-sync ctx@(Context c) = c_sync c >>= check ctx
+withContextMulti :: [Int] -> (Context -> IO a) -> IO a
+withContextMulti devs = bracket (newContextMulti devs) closeContext
 
-adopt :: Context -> Int -> V a -> IO (DVector a)
-adopt ctx n p = do fp <- newForeignPtr (castFunPtr p_vec_free) p
-                   return (DVector ctx fp n)
+sync :: Context -> IO ()
+sync ctx = c_sync (ctxPtr ctx) >>= check ctx
+
+-- | One launcher thread per device ('True', the default on distinct devices) or rank after rank from the calling thread.
+setMultiThreads :: Context -> Bool -> IO ()
+setMultiThreads ctx on = c_set_multi_threads (ctxPtr ctx) (if on then 1 else 0) >>= check ctx
+
+-- | In-kernel record exchange over peer memory ('True') or the stream-ordered one (records, events, a finish kernel).
+setFusedExchange :: Context -> Bool -> IO ()
+setFusedExchange ctx on = c_set_fused_exchange (ctxPtr ctx) (if on then 1 else 0) >>= check ctx
+
+-- | Milliseconds a sharded reduction waits for its peers' records before it fails with @LBK_ERR_NCCL@.
+setExchangeTimeout :: Context -> Int -> IO ()
+setExchangeTimeout ctx ms = c_set_exchange_timeout (ctxPtr ctx) ms >>= check ctx
+
+adopt :: Context -> Int -> Layout -> V a -> IO (DVector a)
+adopt ctx n lay p = do fp <- newForeignPtr (castFunPtr p_vec_free) p
+                       return (DVector ctx fp n lay)
 
 allocD :: Elt a => Context -> Int -> IO (DVector a)
-allocD ctx@(Context c) n = alloca $ \ pp -> do
-    cVecAlloc c n pp >>= check ctx
-    peek pp >>= adopt ctx n
+allocD ctx n = alloca $ \ pp -> do
+    cVecAlloc (ctxPtr ctx) n pp >>= check ctx
+    peek pp >>= adopt ctx n Whole
+
+-- | An uninitialised vector of logical length n, block-sharded over the ranks of a multi-device context.
+allocSharded :: Elt a => Context -> Int -> IO (DVector a)
+allocSharded ctx n = alloca $ \ pp -> do
+    cVecAllocSharded (ctxPtr ctx) n pp >>= check ctx
+    peek pp >>= adopt ctx n (if ctxRanks ctx > 1 then Sharded else Whole)
+
+-- | An uninitialised vector with the length, element type and layout of its argument: what a pure result is made of.
+allocLike :: Elt a => DVector a -> IO (DVector a)
+allocLike d = alloca $ \ pp -> withForeignPtr (dvPtr d) $ \ dp -> do
+    cVecAllocLike dp pp >>= check (dvCtx d)
+    peek pp >>= adopt (dvCtx d) (dvLength d) (dvLayout d)
 
 -- | Explicit host -> device transfer (the north star's "explicit host transfer").
 toDevice :: Elt a => Context -> V.Vector a -> IO (DVector a)
@@ -212,7 +286,16 @@ toDevice ctx v = do
         cVecUpload dp hp (V.length v) >>= check ctx
     return d
 
--- | Explicit device -> host transfer.
+-- | Explicit host -> devices transfer of ONE host vector into block shards: every rank uploads its own block on its
+-- own stream (one PCIe link each).
+toDeviceSharded :: Elt a => Context -> V.Vector a -> IO (DVector a)
+toDeviceSharded ctx v = do
+    d <- allocSharded ctx (V.length v)
+    V.unsafeWith v $ \ hp -> withForeignPtr (dvPtr d) $ \ dp ->
+        cVecUpload dp hp (V.length v) >>= check ctx
+    return d
+
+-- | Explicit device -> host transfer (of the whole logical vector: shards are gathered into one host buffer).
 fromDevice :: Elt a => DVector a -> IO (V.Vector a)
 fromDevice d = do
     mv <- VM.new (dvLength d)
@@ -220,14 +303,34 @@ fromDevice d = do
         cVecDownload dp hp (dvLength d) >>= check (dvCtx d)
     V.unsafeFreeze mv
 
+-- | Page-locks the buffer of a host vector for the duration of the action (@lbk_host_register@): uploads from it
+-- ('toDevice', 'toDeviceAsync') then run at the rate of a pinned copy instead of through the driver's staging buffer.
+withRegistered :: Storable a => V.Vector a -> IO b -> IO b
+withRegistered v act
+    | V.null v  = act
+    | otherwise = V.unsafeWith v $ \ hp ->
+        let p = castPtr hp :: Ptr Word8
+            nbytes = V.length v * sizeOf (V.head v)
+        in bracket_ (c_host_register p nbytes >>= checkNoCtx) (c_host_unregister p) act
+
+-- | Enqueue-only upload into an existing device vector; the host vector must stay alive (and should be registered)
+-- until 'sync'.
+toDeviceAsync :: Elt a => DVector a -> V.Vector a -> IO ()
+toDeviceAsync d v = V.unsafeWith v $ \ hp -> withForeignPtr (dvPtr d) $ \ dp ->
+    cVecUploadAsync dp hp (min (V.length v) (dvLength d)) >>= check (dvCtx d)
+
+-- | Enqueue-only download into a mutable host vector; valid after 'sync'.
+fromDeviceAsync :: Elt a => DVector a -> VM.IOVector a -> IO ()
+fromDeviceAsync d mv = VM.unsafeWith mv $ \ hp -> withForeignPtr (dvPtr d) $ \ dp ->
+    cVecDownloadAsync dp hp (min (VM.length mv) (dvLength d)) >>= check (dvCtx d)
+
 cloneD :: Elt a => DVector a -> IO (DVector a)
 cloneD d = alloca $ \ pp -> withForeignPtr (dvPtr d) $ \ dp -> do
     cVecClone dp pp >>= check (dvCtx d)
-    peek pp >>= adopt (dvCtx d) (dvLength d)
+    peek pp >>= adopt (dvCtx d) (dvLength d) (dvLayout d)
 
 with2 :: DVector a -> DVector a -> (Ptr LbkCtx -> V a -> V a -> IO b) -> IO b
-with2 x y f = let Context c = dvCtx x in
-    withForeignPtr (dvPtr x) $ \ px -> withForeignPtr (dvPtr y) $ \ py -> f c px py
+with2 x y f = withForeignPtr (dvPtr x) $ \ px -> withForeignPtr (dvPtr y) $ \ py -> f (ctxPtr (dvCtx x)) px py
 
 -- ---------------------------------------------------------------------------
 -- reductions (Single.hs:73-87, 155-168, 174-204, 211-225, 231-262)
@@ -244,7 +347,7 @@ sdsdot n sb x incx y incy = alloca $ \ po -> with2 x y $ \ c px py -> do
     peek po
 
 ivi :: Elt a => (Ptr LbkCtx -> Int -> V a -> Int -> Ptr a -> IO CInt) -> Int -> DVector a -> Int -> IO a
-ivi f n x incx = let Context c = dvCtx x in
+ivi f n x incx = let c = ctxPtr (dvCtx x) in
     alloca $ \ po -> withForeignPtr (dvPtr x) $ \ px -> do
         f c n px incx po >>= check (dvCtx x)
         peek po
@@ -255,38 +358,52 @@ nrm2 = ivi cNrm2
 
 -- | 0-based logical index, -1 when n<1 or incx<1 (Single.hs:217-220).
 iamax :: Elt a => Int -> DVector a -> Int -> IO Int
-iamax n x incx = let Context c = dvCtx x in
+iamax n x incx = let c = ctxPtr (dvCtx x) in
     alloca $ \ po -> withForeignPtr (dvPtr x) $ \ px -> do
         cIamax c n px incx po >>= check (dvCtx x)
         peek po
+
+-- | Enqueue-only forms: the scalar lands in element 0 of @out@ (for 'iamaxAsync': the 64-bit index in its first
+-- 8 bytes), a 'Whole' device vector of the routine's element type; nothing is synchronised.
+dotAsync :: Elt a => Int -> DVector a -> Int -> DVector a -> Int -> DVector a -> IO ()
+dotAsync n x incx y incy out = with2 x y $ \ c px py -> withForeignPtr (dvPtr out) $ \ po ->
+    cDotAsync c n px incx py incy po >>= check (dvCtx x)
+
+iviAsync :: (Ptr LbkCtx -> Int -> V a -> Int -> V a -> IO CInt) -> Int -> DVector a -> Int -> DVector a -> IO ()
+iviAsync f n x incx out = with2 x out $ \ c px po -> f c n px incx po >>= check (dvCtx x)
+
+asumAsync, nrm2Async, iamaxAsync :: Elt a => Int -> DVector a -> Int -> DVector a -> IO ()
+asumAsync = iviAsync cAsumAsync
+nrm2Async = iviAsync cNrm2Async
+iamaxAsync = iviAsync cIamaxAsync
 
 -- ---------------------------------------------------------------------------
 -- pure vector results: new device vectors, arguments untouched (Util.hs:134-142)
 -- ---------------------------------------------------------------------------
 scal :: Elt a => Int -> a -> DVector a -> Int -> IO (DVector a)
 scal n a x incx = do
-    o <- allocD (dvCtx x) (dvLength x)
+    o <- allocLike x
     with2 x o $ \ c px po -> cScalOop c n a px incx po >>= check (dvCtx x)
     return o
 
 copy :: Elt a => Int -> DVector a -> Int -> DVector a -> Int -> IO (DVector a)
 copy n x incx y incy = do
-    o <- allocD (dvCtx y) (dvLength y)
+    o <- allocLike y
     with2 x y $ \ c px py -> withForeignPtr (dvPtr o) $ \ po ->
         cCopyOop c n px incx py incy po >>= check (dvCtx x)
     return o
 
 axpy :: Elt a => Int -> a -> DVector a -> Int -> DVector a -> Int -> IO (DVector a)
 axpy n a x incx y incy = do
-    o <- allocD (dvCtx y) (dvLength y)
+    o <- allocLike y
     with2 x y $ \ c px py -> withForeignPtr (dvPtr o) $ \ po ->
         cAxpyOop c n a px incx py incy po >>= check (dvCtx x)
     return o
 
 pair :: Elt a => DVector a -> DVector a -> (Ptr LbkCtx -> V a -> V a -> V a -> V a -> IO CInt) -> IO (DVector a, DVector a)
 pair x y f = do
-    xo <- allocD (dvCtx x) (dvLength x)
-    yo <- allocD (dvCtx y) (dvLength y)
+    xo <- allocLike x
+    yo <- allocLike y
     with2 x y $ \ c px py -> with2 xo yo $ \ _ pxo pyo -> f c px py pxo pyo >>= check (dvCtx x)
     return (xo, yo)
 
@@ -316,7 +433,7 @@ axpy_ :: Elt a => Int -> a -> DVector a -> Int -> DVector a -> Int -> IO ()
 axpy_ n a x incx y incy = with2 x y $ \ c px py -> cAxpy c n a px incx py incy >>= check (dvCtx x)
 
 scal_ :: Elt a => Int -> a -> DVector a -> Int -> IO ()
-scal_ n a x incx = let Context c = dvCtx x in
+scal_ n a x incx = let c = ctxPtr (dvCtx x) in
     withForeignPtr (dvPtr x) $ \ px -> cScal c n a px incx >>= check (dvCtx x)
 
 copy_, swap_ :: Elt a => Int -> DVector a -> Int -> DVector a -> Int -> IO ()
@@ -333,14 +450,15 @@ rotm_ flags n x incx y incy = withArray (sparam flags) $ \ pp ->
 -- ---------------------------------------------------------------------------
 -- host scalars (Single.hs:274-300, 318-357); pure, like the reference's
 -- ---------------------------------------------------------------------------
-rotg :: Elt a => a -> a -> IO (GivensRot a)
-rotg a b = allocaArray 4 $ \ po -> do
+rotg :: Elt a => a -> a -> GivensRot a
+rotg a b = unsafePerformIO $ allocaArray 4 $ \ po -> do      -- a pure C function of its arguments (lbk_scalars.cpp)
     _ <- cRotg a b po
     [r, z, c, s] <- peekArray 4 po
     return (GIVENSROT (r, z, c, s))
+{-# NOINLINE rotg #-}
 
-rotmg :: Elt a => a -> a -> a -> a -> IO (ModGivensRot a)
-rotmg sd1 sd2 sx1 sy1 = allocaArray 8 $ \ po -> do
+rotmg :: Elt a => a -> a -> a -> a -> ModGivensRot a
+rotmg sd1 sd2 sx1 sy1 = unsafePerformIO $ allocaArray 8 $ \ po -> do
     _ <- cRotmg sd1 sd2 sx1 sy1 po nullPtr
     [flag, a, b, c, e11, e12, e21, e22] <- peekArray 8 po
     return $ case (round flag :: Int) of
@@ -348,6 +466,7 @@ rotmg sd1 sd2 sx1 sy1 = allocaArray 8 $ \ po -> do
         -1 -> FLAGNEG1 { d1 = a, d2 = b, x1 = c, h11 = e11, h12 = e12, h21 = e21, h22 = e22 }
         0  -> FLAG0    { d1 = a, d2 = b, x1 = c, h12 = e12, h21 = e21 }
         _  -> FLAG1    { d1 = a, d2 = b, x1 = c, h11 = e11, h22 = e22 }
+{-# NOINLINE rotmg #-}
 
 -- ---------------------------------------------------------------------------
 -- the reference's deprecated monomorphic aliases (Single.hs:83-87, 112-116, 128-132,
@@ -391,11 +510,11 @@ srotm :: ModGivensRot Float -> Int -> DVector Float -> Int -> DVector Float -> I
 srotm = rotm
 drotm :: ModGivensRot Double -> Int -> DVector Double -> Int -> DVector Double -> Int -> IO (DVector Double, DVector Double)
 drotm = rotm
-srotg :: Float -> Float -> IO (GivensRot Float)
+srotg :: Float -> Float -> GivensRot Float
 srotg = rotg
-drotg :: Double -> Double -> IO (GivensRot Double)
+drotg :: Double -> Double -> GivensRot Double
 drotg = rotg
-srotmg :: Float -> Float -> Float -> Float -> IO (ModGivensRot Float)
+srotmg :: Float -> Float -> Float -> Float -> ModGivensRot Float
 srotmg = rotmg
-drotmg :: Double -> Double -> Double -> Double -> IO (ModGivensRot Double)
+drotmg :: Double -> Double -> Double -> Double -> ModGivensRot Double
 drotmg = rotmg

@@ -953,16 +953,30 @@ reduce_strided_kernel(const typename Op::Scalar *x, i64 incx, i64 kx0, const typ
                       i64 idx_base, Record *partials, unsigned *ticket, FinishArgs fa)
 {
     using T = typename Op::Scalar;
-    // a plain grid-stride loop: the compiler unrolls it four times with the loads hoisted, which measured
-    // faster than explicit tiling (ptxas interleaves predicated tile loads with their uses).  The loop keeps the
-    // routine's register accumulator (for iamax: running maximum + ordinal of its first occurrence, one compare per
-    // element -- profiles/r02_ncu_more.md: merging a (key, 64-bit index) candidate per element ran at a third of the
-    // DRAM rate); the ordinal becomes an index once, after the loop.
+    // A grid-stride loop in groups of kStridedUnroll elements: all loads of a group are issued before the first is used.
+    // The loads are volatile asm (load_pack), which keeps them in that order: written as plain C++ loads the compiler
+    // hoists them for the sums but serialises them for iamax -- LDG, FSETP, FSEL, LDG, ... on one register, one load in
+    // flight per thread, 56% of the DRAM rate (profiles/r02_ncu_all_2p28.md, profiles/r02_strided_reductions.md).  The loop keeps the
+    // routine's register accumulator (iamax: running maximum + ordinal of its first occurrence, one compare per element);
+    // the ordinal becomes an index once, after the loop.
+    constexpr int U = kStridedUnroll;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     const i64 first = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     typename Op::Acc acc = Op::zero();
     unsigned ord = 0;
-    for (i64 i = first; i < n; i += stride, ++ord)
+    i64 i = first;
+    for (; i + (U - 1) * stride < n; i += U * stride, ord += U) {
+        Pack<T, 1> xv[U], yv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            load_pack<1, 0, true>(xv[u], x + kx0 + (i + u * stride) * incx);
+            if constexpr (Op::TWO) load_pack<1, 0, true>(yv[u], y + ky0 + (i + u * stride) * incy);
+            else yv[u].v[0] = T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) Op::step(acc, xv[u].v[0], yv[u].v[0], ord + u);
+    }
+    for (; i < n; i += stride, ++ord)
         Op::step(acc, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : T(0), ord);
     typename Op::Partial p = Op::empty();
     const u64 x0_bits = apply_x0<Op>(p, fa);

@@ -1612,10 +1612,22 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
     } else {
         const LaunchCfg &scfg = c->cfg[R_REDSTRIDED];
         const int threads = (scfg.threads > 0 && scfg.threads <= 256) ? scfg.threads : 256;
-        // config-4 sweep (profiles/r01_strided_launch_sweep.md): 8 blocks of 256 per SM for increments of 1-2,
-        // 32 when an increment of 4 or more puts every element in its own sector
+        // Every block does the same share of the work (grid-stride), so the grid is a whole number of resident waves:
+        // one wave for increments of 1-2, four when an increment of 4 or more puts every element in its own sector
+        // (config-4 sweep, profiles/r01_strided_launch_sweep.md).  The wave comes from the kernel's occupancy, not from
+        // a constant: isamax's instance needs 40 registers, 6 resident blocks of 256 -- on a grid of 8 per SM its last
+        // quarter ran as a second, mostly empty wave at 2.5x the time (profiles/r02_strided_reductions.md).
         const bool wide = std::max(iabs64(incx), Y ? iabs64(incy) : 0) >= 4;
-        const i64 cap = (i64)c->sms * (scfg.blocks_per_sm > 0 ? scfg.blocks_per_sm : (wide ? 32 : 8));
+        static std::atomic<int> cached{0};      // per instantiation: (threads << 8) | resident blocks
+        int resident = cached.load(std::memory_order_relaxed);
+        if ((resident >> 8) != threads) {
+            int r = 0;
+            CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, lbk::reduce_strided_kernel<Op>, threads, 0));
+            resident = (threads << 8) | std::min(std::max(r, 1), 255);
+            cached.store(resident, std::memory_order_relaxed);
+        }
+        resident &= 255;
+        const i64 cap = (i64)c->sms * (scfg.blocks_per_sm > 0 ? scfg.blocks_per_sm : (wide ? 4 * resident : resident));
         const int grid = (int)std::max<i64>(1, std::min<i64>(std::min<i64>((std::max<i64>(nl, 1) + threads - 1) / threads, cap), kMaxGrid));
         lbk_pdl::interrupt(c->pdl);
         lbk::reduce_strided_kernel<Op><<<grid, threads, 0, c->stream>>>(x, incx, first_index(nl, incx), y, incy,

@@ -21,7 +21,7 @@ from lambda_blas_b200 import inplace as ip  # noqa: E402
 
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 26
 n = 1 << lg
-GROUPS = os.environ.get("GROUPS", "strided,rotm,misaligned,streams,f64").split(",")
+GROUPS = os.environ.get("LBK_GROUPS", "strided,rotm,misaligned,streams,f64").split(",")
 ctx = lb.Context(0)
 ctx.set_pdl(False)                       # one kernel at a time: ncu serialises launches anyway
 span = 1 + (n - 1) * 7 if "strided" in GROUPS else n

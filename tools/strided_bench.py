@@ -19,13 +19,17 @@ print("# overrides:", overrides)
 span = 1 + (n - 1) * 7
 x, y, out = ctx.alloc(span).fill_hash(1), ctx.alloc(span).fill_hash(2), ctx.alloc(4)
 c, s = math.cos(0.3), math.sin(0.3)
-B = {"sdot": 8, "saxpy": 12, "srot": 16}
+B = {"sdot": 8, "saxpy": 12, "srot": 16, "sasum": 4, "isamax": 4, "snrm2": 4}
 print("routine,incx,incy,us,GBps_algorithmic")
 ROUTINES = os.environ.get("ROUTINES", "sdot,saxpy,srot").split(",")
 for r in ROUTINES:
     for incx in incs:
         for incy in incs:
+            if r in ("sasum", "isamax", "snrm2") and (incy != incs[0] or incx < 1):
+                continue                      # one-vector reductions: positive incx only, once per incx
             f = {"sdot": lambda: ip.sdot_async(n, x, incx, y, incy, out),
+                 "sasum": lambda: ip.sasum_async(n, x, incx, out), "isamax": lambda: ip.isamax_async(n, x, incx, out),
+                 "snrm2": lambda: ip.snrm2_async(n, x, incx, out),
                  "saxpy": lambda: ip.saxpy_(n, 1.0, x, incx, y, incy),
                  "srot": lambda: ip.srot_(n, x, incx, y, incy, c, s)}[r]
             for _ in range(3):
