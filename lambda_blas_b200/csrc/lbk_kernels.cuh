@@ -973,8 +973,12 @@ reduce_strided_kernel(const typename Op::Scalar *x, i64 incx, i64 kx0, const typ
             if constexpr (Op::TWO) load_pack<1, 0, true>(yv[u], y + ky0 + (i + u * stride) * incy);
             else yv[u].v[0] = T(0);
         }
+        // the group as one pack: iamax and nrm2 first reduce the whole group (a max / min tree over all U values, which
+        // also keeps every load ahead of the first use) and only look at single elements when the group matters
+        Pack<T, U> gx, gy;
 #pragma unroll
-        for (int u = 0; u < U; ++u) Op::step(acc, xv[u].v[0], yv[u].v[0], ord + u);
+        for (int u = 0; u < U; ++u) { gx.v[u] = xv[u].v[0]; gy.v[u] = yv[u].v[0]; }
+        pack_step<Op, U>(acc, gx, gy, ord);
     }
     for (; i < n; i += stride, ++ord)
         Op::step(acc, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : T(0), ord);
