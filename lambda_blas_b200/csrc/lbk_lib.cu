@@ -53,7 +53,7 @@ enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY,
                R_MAPMISALIGNED, R_REDMISALIGNED, R_COUNT };
 static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm", "fill", "mapstrided", "redstrided",
                                             "mapmisaligned", "redmisaligned"};
-struct LaunchCfg { int variant; int threads; int blocks_per_sm; };   // <= 0: default / from occupancy
+struct LaunchCfg { int variant; int threads; int blocks_per_sm; bool pinned = false; };   // <= 0: default / from occupancy; pinned: set by lbk_set_launch, taken literally
 // Defaults from the n = 2^28 sweeps on B200 (profiles/r01_tune_*.csv; tools/tune.py), reductions tuned
 // with their tails overlapped (PDL).  blocks_per_sm 0 = one resident wave (occupancy x SMs); larger
 // values oversubscribe the SMs and let the hardware block scheduler balance the load; kOneTilePerBlock
@@ -596,7 +596,8 @@ extern "C" int lbk_set_launch(lbk_ctx *c, const char *routine, int variant, int 
     for (int r = 0; r < R_COUNT; ++r)
         if (!strcmp(routine, kRoutineNames[r]) || !strcmp(routine, "all")) {
             c->cfg[r] = LaunchCfg{variant >= 0 ? variant : kDefaultCfg[r].variant, threads > 0 ? threads : kDefaultCfg[r].threads,
-                                  (variant < 0 && threads <= 0 && blocks_per_sm <= 0) ? kDefaultCfg[r].blocks_per_sm : blocks_per_sm};
+                                  (variant < 0 && threads <= 0 && blocks_per_sm <= 0) ? kDefaultCfg[r].blocks_per_sm : blocks_per_sm,
+                                  blocks_per_sm > 0};      // an explicit grid is taken literally (no size adaptation)
             if (strcmp(routine, "all")) return LBK_OK;
         }
     if (!strcmp(routine, "all")) return LBK_OK;
@@ -1270,12 +1271,22 @@ static int variant_unroll(int variant)
     return 1;
 }
 
-static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int threads, i64 ntiles, int *grid, i64 max_grid = kMaxGrid)
+// adapt: a reduction's grid-stride loop wants a dozen tiles per block.  The default 16 (8) blocks per SM were tuned at
+// n = 2^28, where a block runs ~28 tiles; at the sizes a rank sees when n_global = 2^28 is sharded over 8 GPUs (2^25) the
+// same grid leaves 3.5 tiles per block and a ragged, half-empty last wave: sasum 22.6 -> 18.3 us, isamax 26.3 -> 18.4 us
+// with a quarter of the blocks (profiles/r02_midsize_launch.md).  So the blocks per SM are halved, down to 4, until
+// a block has its dozen tiles.
+static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int threads, i64 ntiles, int *grid, i64 max_grid = kMaxGrid,
+                    bool adapt = false)
 {
     int bps = cfg.blocks_per_sm;
     if (bps <= 0) {
         CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, 0));
         if (bps < 1) bps = 1;
+    } else if (adapt && bps < kOneTilePerBlock) {
+        const int floor_bps = std::max(1, 1024 / threads);          // 1024 threads per SM
+        while (bps > floor_bps && ntiles < (i64)12 * c->sms * bps) bps /= 2;
+        if (bps < floor_bps) bps = floor_bps;
     }
     i64 g = std::min<i64>(std::max<i64>(ntiles, 1), (i64)c->sms * bps);
     *grid = (int)std::min<i64>(g, max_grid);
@@ -1592,7 +1603,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         const i64 npack = (nl - head) / variant_vec<T>(variant);
         const i64 per_tile = (i64)variant_unroll(variant) * threads;
         int grid;
-        int s = grid_for(c, k, *pcfg, threads, (npack + per_tile - 1) / per_tile, &grid);
+        int s = grid_for(c, k, *pcfg, threads, (npack + per_tile - 1) / per_tile, &grid, kMaxGrid, !pcfg->pinned);
         if (s) return s;
         i64 nn = nl, ib = idx_base;
         lbk_pdl::Op op;
