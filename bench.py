@@ -639,14 +639,23 @@ def run_ours(args) -> None:
     ydl = ctx_dl.wrap(y.ptr, n, keepalive=y)
     both = wall_ms(lambda: (x.upload_async(hx), ydl.download_async(hy_out), ctx.sync(), ctx_dl.sync()))
     del ydl
+    # the e2e step's own transfers with nothing else: x and y up (8 B/elem) while y' comes down (4 B/elem) on the second stream
+    youtd = ctx_dl.wrap(yout.ptr, n, keepalive=yout)
+    floor_ms = wall_ms(lambda: (x.upload_async(hx), y.upload_async(hy), youtd.download_async(hy_out), ctx.sync(), ctx_dl.sync()))
+    del youtd
+    e2e["transfers_only_ms_per_step"] = round(floor_ms, 3)
+    e2e["frac_of_transfers_only"] = round(floor_ms / e2e_ms, 3)
+    e2e["bound"] = ("host<->device transfers: the same 8 B/elem up + 4 B/elem down with NO kernels take transfers_only_ms_per_step "
+                    "(all ranks at once); compute is hidden under them")
     host_copy = wall_ms(lambda: np.copyto(py, px))
     transfers = {"unit": "GB/s (aggregate over ranks, all ranks transferring at once)", "n_per_gpu": n,
                  "toDevice_pinned": round(gb / up_pinned, 1), "toDevice_pageable": round(gb / up_pageable, 1),
                  "toDevice_registered": round(gb / up_registered, 1), "host_register_ms_per_GiB": round(reg_ms / (px.nbytes / 2 ** 30), 1),
                  "fromDevice_pinned": round(gb / down_pinned, 1), "h2d_and_d2h_together": round(2 * gb / both, 1),
                  "host_memcpy_1_thread_per_rank": round(2 * gb / host_copy, 1),
-                 "note": ("the e2e step moves 8 B/elem up and 4 B/elem down per 24 algorithmic bytes: at the h2d+d2h rate R (GB/s, both directions "
-                          "together) its ceiling is 2 R; host_memcpy is numpy copyto on every rank at once (read + write bytes)")}
+                 "note": ("every figure is the aggregate over all ranks transferring at once -- at N > 1 this is the host's ceiling (one VM, one NUMA "
+                          "node, shared host DRAM and PCIe root complexes: profiles/r02_host_topology_*.txt); host_memcpy is numpy copyto on every "
+                          "rank at once (read + write bytes)")}
     del px, py
     ctx_dl.sync()
     t_load1 = time.time()

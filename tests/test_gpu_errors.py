@@ -74,3 +74,40 @@ def test_foreign_handles_and_bad_arguments(blas, ctx):
             ctx.set_launch("sdot", 99, 0, 0)
     finally:
         other.close()
+
+
+def test_huge_counts_and_increments_do_not_wrap(blas, ctx):
+    """1 + (n-1)*|inc| must not be computed in wrapping int64 arithmetic: a span that overflows is out of range, not tiny."""
+    import ctypes as C
+    from lambda_blas_b200 import _ffi
+    L = _ffi.lib()
+    x = ctx.to_device(np.arange(16, dtype=np.float32))
+    out, iout = C.c_float(), C.c_int64()
+    big = 1 << 62
+    for n, inc in ((big, 4), (big + 1, 8), (3, big), (2, -(1 << 63)), (1 << 61, -8), ((1 << 63) - 1, (1 << 63) - 1)):
+        assert L.lbk_sdot(ctx.handle, n, x.handle, inc, x.handle, 1, C.byref(out)) == 4, (n, inc)        # LBK_ERR_RANGE
+        assert L.lbk_saxpy(ctx.handle, n, 1.0, x.handle, 1, x.handle, inc) == 4, (n, inc)
+        if inc > 0:
+            assert L.lbk_isamax(ctx.handle, n, x.handle, inc, C.byref(iout)) == 4, (n, inc)
+    # n == 1 never applies the increment: any value is fine (Single.hs:91-96: first(1, inc) = 0)
+    assert L.lbk_sdot(ctx.handle, 1, x.handle, (1 << 63) - 1, x.handle, -(1 << 63), C.byref(out)) == 0 and out.value == 0.0
+    assert L.lbk_isamax(ctx.handle, 1, x.handle, 1 << 62, C.byref(iout)) == 0 and iout.value == 0
+    v = C.c_void_p()
+    assert L.lbk_vec_view(x.handle, (1 << 63) - 1, 2, C.byref(v)) == 3                                   # offset + len would wrap
+    lo, hi, off = C.c_int64(), C.c_int64(), C.c_int64()
+    assert L.lbk_shard_span(1 << 40, 8, 3, 1 << 62, 1 << 20, C.byref(lo), C.byref(hi), C.byref(off)) == 4
+
+
+def test_pure_results_keep_the_shard_layout(blas):
+    """A rank that holds a WHOLE short vector (global length below the world size) must still hand out sharded results:
+    lbk_vec_alloc_like copies the layout instead of guessing it from the geometry."""
+    m = blas.MultiContext([0, 0, 0])
+    try:
+        for n in (1, 2, 3, 7):
+            x = m.to_device_sharded(np.arange(1, n + 1, dtype=np.float32))
+            y = blas.sscal(n, 2.0, x, 1)
+            assert y.is_sharded and len(y) == n
+            np.testing.assert_array_equal(y.to_host(), 2 * np.arange(1, n + 1, dtype=np.float32))
+            assert blas.sasum(n, y, 1) == n * (n + 1) and blas.isamax(n, y, 1) == n - 1
+    finally:
+        m.close()
