@@ -630,7 +630,9 @@ def run_ours(args) -> None:
         return max_over_ranks([(time.perf_counter() - t0) / reps * 1e3])[0]
     gb = 4 * n * world / 1e6
     up_pinned = wall_ms(lambda: (x.upload_async(hx), ctx.sync()))
-    up_pageable = wall_ms(lambda: (x.upload_async(px), ctx.sync()))
+    up_pageable = wall_ms(lambda: x.upload(px))                        # lbk_vec_upload: 4 pinned staging lanes inside the library
+    up_pageable_driver = wall_ms(lambda: (x.upload_async(px), ctx.sync()))      # cudaMemcpyAsync from pageable memory: the driver's own staging
+    down_pageable = wall_ms(lambda: x.download(py))                    # into an existing (already touched) pageable array
     with lb.registered(px):
         up_registered = wall_ms(lambda: (x.upload_async(px), ctx.sync()))
     t0 = time.perf_counter(); lb._ffi.check(lb._ffi.lib().lbk_host_register(px.ctypes.data, px.nbytes)); reg_ms = (time.perf_counter() - t0) * 1e3
@@ -650,6 +652,7 @@ def run_ours(args) -> None:
     host_copy = wall_ms(lambda: np.copyto(py, px))
     transfers = {"unit": "GB/s (aggregate over ranks, all ranks transferring at once)", "n_per_gpu": n,
                  "toDevice_pinned": round(gb / up_pinned, 1), "toDevice_pageable": round(gb / up_pageable, 1),
+                 "toDevice_pageable_plain_cudaMemcpy": round(gb / up_pageable_driver, 1), "fromDevice_pageable": round(gb / down_pageable, 1),
                  "toDevice_registered": round(gb / up_registered, 1), "host_register_ms_per_GiB": round(reg_ms / (px.nbytes / 2 ** 30), 1),
                  "fromDevice_pinned": round(gb / down_pinned, 1), "h2d_and_d2h_together": round(2 * gb / both, 1),
                  "host_memcpy_1_thread_per_rank": round(2 * gb / host_copy, 1),

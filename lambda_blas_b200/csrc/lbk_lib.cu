@@ -25,6 +25,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using lbk::i64;
@@ -99,6 +100,10 @@ struct lbk_ctx {
     // the stream-ordered exchange of a multi-device context (ranks that share a device, or fused exchange off):
     // this rank's record ring (two parities), the table of all ranks' rings, the "record written" event, and the
     // finish this rank still owes for the reduction it launched last (lbk_lib.cu, exchange_finish)
+    // pinned staging lanes for synchronous transfers from / to PAGEABLE host memory (staged_transfer), made on first use
+    void *stage_buf[8] = {};
+    cudaEvent_t stage_ev[8] = {};
+    size_t stage_chunk = 0;
     Record *rec_ring = nullptr;
     const Record **ring_table_dev = nullptr;
     cudaEvent_t xchg_ev = nullptr;
@@ -340,6 +345,7 @@ static void destroy_one(lbk_ctx *c)
         if (c->rec_ring) { if (c->host_mailbox) cudaFreeHost(c->rec_ring); else cudaFree(c->rec_ring); }
         cudaFree(c->ring_table_dev);
         if (c->xchg_ev) cudaEventDestroy(c->xchg_ev);
+        for (int i = 0; i < 8; ++i) { if (c->stage_buf[i]) cudaFreeHost(c->stage_buf[i]); if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]); }
         cudaFree(c->peers_dev);
         if (c->error_flag_host) cudaFreeHost(c->error_flag_host);
         cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->snap); cudaFree(c->sink);
@@ -940,10 +946,109 @@ extern "C" int lbk_vec_upload_async(lbk_vec *v, const void *host, int64_t len)
     if (len) { lbk_pdl::interrupt(v->ctx->pdl); CU(v->ctx, cudaMemcpyAsync(v->ptr, host, (size_t)esz(v->dtype) * (size_t)len, cudaMemcpyHostToDevice, v->ctx->stream)); }
     return LBK_OK;
 }
+// The synchronous transfers (what the reference-shaped `toDevice` / `fromDevice` of the host mirrors call) from or to
+// PAGEABLE host memory -- a plain Data.Vector.Storable / numpy / std::vector buffer.  cudaMemcpy stages such a copy through
+// the driver's own bounce buffer on one thread: 7-11 GB/s against 53-55 GB/s from pinned memory (bench.py `transfers`).
+// Here a few host threads ("lanes") each own a pinned chunk: a lane copies its chunk of the caller's buffer into pinned memory
+// while the other lanes' chunks are in flight on the copy engine (uploads), or copies a landed chunk out while the next ones
+// arrive (downloads).  Pinned, registered and small buffers take the direct path.
+constexpr int kMaxStageLanes = 8;
+constexpr size_t kStageMinBytes = (size_t)16 << 20;
+// Lanes and chunk size (tools/transfer_sweep.py, profiles/r02_transfers.md: one lane moves ~10 GB/s, 6 lanes x 8 MiB reach 47 GB/s up /
+// 43 down of the 55 GB/s a pinned buffer gets; the driver's own pageable path: 10.7).  Default: 6 lanes, fewer when the ranks of a
+// multi-device context (each with its own lanes) would oversubscribe the host's cores; LBK_STAGE_LANES / LBK_STAGE_CHUNK_MB override.
+static int stage_lanes(const lbk_ctx *c)
+{
+    static const int forced = [] { const char *e = getenv("LBK_STAGE_LANES"); return e ? std::min(std::max(atoi(e), 1), kMaxStageLanes) : 0; }();
+    if (forced) return forced;
+    const int ranks = c->parent ? (int)c->parent->subs.size() : 1;
+    const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
+    return std::min(6, std::max(1, cores / (2 * ranks)));
+}
+static size_t stage_chunk_bytes()
+{
+    static const size_t bytes = [] { const char *e = getenv("LBK_STAGE_CHUNK_MB"); int v = e ? atoi(e) : 8; return (size_t)std::min(std::max(v, 1), 64) << 20; }();
+    return bytes;
+}
+
+static bool is_pageable(const void *host)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int staged_transfer(lbk_ctx *c, char *dev, char *host, size_t bytes, bool up)
+{
+    ON_DEVICE(c);
+    const int kStageLanes = stage_lanes(c);
+    const size_t kStageChunk = stage_chunk_bytes();
+    c->stage_chunk = kStageChunk;
+    for (int i = 0; i < kStageLanes; ++i) {
+        if (!c->stage_buf[i]) CU(c, cudaHostAlloc(&c->stage_buf[i], kStageChunk, cudaHostAllocDefault));
+        if (!c->stage_ev[i]) CU(c, cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+    }
+    lbk_pdl::interrupt(c->pdl);
+    const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+    std::atomic<int> failed{0};
+    auto lane = [&](int t) {
+        if (cudaSetDevice(c->device) != cudaSuccess) { failed.store(1); return; }
+        bool in_flight = false;
+        for (size_t i = (size_t)t; i < nchunks && !failed.load(std::memory_order_relaxed); i += kStageLanes) {
+            const size_t off = i * kStageChunk, len = std::min(kStageChunk, bytes - off);
+            cudaError_t e = cudaSuccess;
+            if (up) {
+                if (in_flight) e = cudaEventSynchronize(c->stage_ev[t]);        // this lane's previous chunk has left its buffer
+                if (e == cudaSuccess) {
+                    memcpy(c->stage_buf[t], host + off, len);
+                    e = cudaMemcpyAsync(dev + off, c->stage_buf[t], len, cudaMemcpyHostToDevice, c->stream);
+                }
+                if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[t], c->stream);
+                in_flight = true;
+            } else {
+                e = cudaMemcpyAsync(c->stage_buf[t], dev + off, len, cudaMemcpyDeviceToHost, c->stream);
+                if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[t], c->stream);
+                if (e == cudaSuccess) e = cudaEventSynchronize(c->stage_ev[t]);
+                if (e == cudaSuccess) memcpy(host + off, c->stage_buf[t], len);
+            }
+            if (e != cudaSuccess) failed.store((int)e);
+        }
+    };
+    std::thread workers[kMaxStageLanes - 1];
+    for (int t = 1; t < kStageLanes; ++t) workers[t - 1] = std::thread(lane, t);
+    lane(0);
+    for (int t = 1; t < kStageLanes; ++t) workers[t - 1].join();
+    if (int e = failed.load()) { cudaGetLastError(); return fail(c, LBK_ERR_CUDA, std::string("staged transfer: ") + cudaGetErrorString((cudaError_t)e)); }
+    return LBK_OK;
+}
+
+// One rank's synchronous transfer: staged when the host side is large and pageable, direct otherwise.
+static int sync_transfer_one(lbk_vec *v, char *host, int64_t len, bool up)
+{
+    lbk_ctx *c = v->ctx;
+    const size_t bytes = (size_t)esz(v->dtype) * (size_t)len;
+    int s;
+    if (bytes >= kStageMinBytes && is_pageable(host)) s = staged_transfer(c, v->ptr, host, bytes, up);
+    else s = up ? lbk_vec_upload_async(v, host, len) : lbk_vec_download_async(v, host, len);
+    return s ? s : lbk_sync(c);
+}
+
+static int sync_transfer(lbk_vec *v, char *host, int64_t len, bool up, const char *who)
+{
+    if (!v || len < 0 || len > (is_multi(v->ctx) ? v->global_len : v->len) || (len > 0 && !host)) return fail(v ? v->ctx : nullptr, LBK_ERR_ARG, std::string(who) + ": bad argument");
+    LIVE(v->ctx, who);
+    if (!is_multi(v->ctx)) return sync_transfer_one(v, host, len, up);
+    lbk_ctx *m = v->ctx;      // every rank moves its own block of the one host buffer, on its own stream (and staging lanes)
+    return fan_out(m, v->sharded ? (int)m->subs.size() : 1, [&](lbk_ctx *, int r) {
+        lbk_vec *p = v->parts[r];
+        const i64 lo = p->shard_off, cnt = std::max<i64>(0, std::min<i64>(len, lo + p->len) - lo);
+        return cnt > 0 ? sync_transfer_one(p, host + lo * esz(v->dtype), cnt, up) : (int)LBK_OK;
+    });
+}
+
 extern "C" int lbk_vec_upload(lbk_vec *v, const void *host, int64_t len)
 {
-    int s = lbk_vec_upload_async(v, host, len);
-    return s ? s : lbk_sync(v->ctx);
+    return sync_transfer(v, const_cast<char *>(static_cast<const char *>(host)), len, true, "lbk_vec_upload");
 }
 extern "C" int lbk_vec_download_async(const lbk_vec *v, void *host, int64_t len)
 {
@@ -956,8 +1061,7 @@ extern "C" int lbk_vec_download_async(const lbk_vec *v, void *host, int64_t len)
 }
 extern "C" int lbk_vec_download(const lbk_vec *v, void *host, int64_t len)
 {
-    int s = lbk_vec_download_async(v, host, len);
-    return s ? s : lbk_sync(v->ctx);
+    return sync_transfer(const_cast<lbk_vec *>(v), static_cast<char *>(host), len, false, "lbk_vec_download");
 }
 
 extern "C" int lbk_vec_clone(const lbk_vec *v, lbk_vec **out)

@@ -296,6 +296,13 @@ class DVector:
             _ffi.check(_ffi.lib().lbk_vec_download(self._h, out.ctypes.data_as(C.c_void_p), n), self.ctx.handle)
         return out
 
+    def download(self, out: np.ndarray) -> np.ndarray:
+        """Synchronous device -> host into an existing array (lbk_vec_download; pageable memory goes through staging lanes)."""
+        assert out.dtype == self.dtype and out.flags.c_contiguous and out.size >= len(self)
+        if len(self):
+            _ffi.check(_ffi.lib().lbk_vec_download(self._h, out.ctypes.data_as(C.c_void_p), len(self)), self.ctx.handle)
+        return out
+
     def upload(self, host) -> "DVector":
         a = np.ascontiguousarray(host, dtype=self.dtype)
         _ffi.check(_ffi.lib().lbk_vec_upload(self._h, a.ctypes.data_as(C.c_void_p), a.size), self.ctx.handle)

@@ -252,3 +252,22 @@ def test_host_register_and_caller_device_is_restored(blas, ctx):
         assert blas.snrm2(a.size, v, 1) > 0                     # runs on device 0 ...
         assert torch.cuda.current_device() == 1                 # ... and leaves the caller's device alone
         torch.cuda.set_device(0)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_staged_transfers_of_pageable_memory_round_trip(blas, ctx, dt):
+    """lbk_vec_upload / lbk_vec_download of a large PAGEABLE buffer go through the library's pinned staging lanes (ragged sizes:
+    a partial last chunk, fewer chunks than lanes); the bytes must come back unchanged, also through a sharded vector."""
+    rng = np.random.default_rng(3)
+    for n in ((16 << 20) // np.dtype(dt).itemsize, (40 << 20) // np.dtype(dt).itemsize + 12345, (8 << 20) // np.dtype(dt).itemsize - 7):
+        h = rng.integers(0, 2 ** 31, n).astype(dt)
+        v = ctx.alloc(n, dt)
+        v.upload(h)
+        assert same(v.to_host(), h)
+        assert float(blas.asum(n, v, 1)) == pytest.approx(float(np.sum(h, dtype=np.float64)), rel=1e-5)
+    m = blas.MultiContext([0, 0, 0])
+    try:
+        h = rng.integers(0, 2 ** 31, (100 << 20) // 4 + 3).astype(np.float32)
+        assert same(m.to_device_sharded(h).to_host(), h)
+    finally:
+        m.close()
