@@ -609,6 +609,26 @@ def run_ours(args) -> None:
     pageable_ms = time_e2e(px, py, 3)
     with lb.registered(px), lb.registered(py):
         registered_ms = time_e2e(px, py, 3)
+    # the reference's own call sequence, nothing hand-pipelined: toDevice x, toDevice y (pageable host vectors), pure saxpy, sdot,
+    # snrm2, fromDevice of the result -- synchronous calls of lambda_blas_b200.single, as a Haskell caller of Device.hs would write them
+    pz = np.empty(n, dtype=np.float32); pz.fill(0)
+
+    def reference_shaped():
+        dx, dy = ctx.to_device(px), ctx.to_device(py)
+        z = lb.saxpy(n, SAXPY_A, dx, 1, dy, 1)
+        lb.sdot(n, dx, 1, dy, 1); lb.snrm2(n, dx, 1)
+        z.download(pz)
+    reference_shaped()
+    barrier()
+    tw0 = time.perf_counter()
+    for _ in range(3):
+        reference_shaped()
+    barrier()
+    shaped_ms = max_over_ranks([(time.perf_counter() - tw0) / 3 * 1e3])[0]
+    e2e["reference_call_sequence_pageable"] = {
+        "value": round(STEP_BYTES_PER_ELEM * ng / shaped_ms / 1e6, 2), "ms_per_step": round(shaped_ms, 3),
+        "calls": "to_device(x), to_device(y) [lbk_vec_upload, staged], saxpy (pure), sdot, snrm2, download(z) [lbk_vec_download, staged]; per rank on its own block"}
+    del pz
     e2e["from_pageable_host_memory"] = {"value": round(STEP_BYTES_PER_ELEM * ng / pageable_ms / 1e6, 2), "ms_per_step": round(pageable_ms, 3)}
     e2e["from_registered_host_memory"] = {"value": round(STEP_BYTES_PER_ELEM * ng / registered_ms / 1e6, 2), "ms_per_step": round(registered_ms, 3),
                                           "how": "lbk_host_register on the caller's own buffers (not timed: a one-off per buffer)"}
