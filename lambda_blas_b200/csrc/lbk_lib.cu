@@ -961,7 +961,13 @@ static int stage_lanes(const lbk_ctx *c)
 {
     static const int forced = [] { const char *e = getenv("LBK_STAGE_LANES"); return e ? std::min(std::max(atoi(e), 1), kMaxStageLanes) : 0; }();
     if (forced) return forced;
-    const int ranks = c->parent ? (int)c->parent->subs.size() : 1;
+    // ranks sharing this host's cores: the ranks of the multi-device context, or the processes torchrun / mpirun started here
+    static const int local_world = [] {
+        for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS"})
+            if (const char *e = getenv(name)) { const int v = atoi(e); if (v > 0) return v; }
+        return 1;
+    }();
+    const int ranks = std::max(c->parent ? (int)c->parent->subs.size() : 1, local_world);
     const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
     return std::min(6, std::max(1, cores / (2 * ranks)));
 }
@@ -1375,11 +1381,13 @@ static int variant_unroll(int variant)
     return 1;
 }
 
-// adapt: a reduction's grid-stride loop wants a dozen tiles per block.  The default 16 (8) blocks per SM were tuned at
+// adapt: a reduction's grid-stride loop wants two dozen tiles per block.  The default 16 (8) blocks per SM were tuned at
 // n = 2^28, where a block runs ~28 tiles; at the sizes a rank sees when n_global = 2^28 is sharded over 8 GPUs (2^25) the
 // same grid leaves 3.5 tiles per block and a ragged, half-empty last wave: sasum 22.6 -> 18.3 us, isamax 26.3 -> 18.4 us
-// with a quarter of the blocks (profiles/r02_midsize_launch.md).  So the blocks per SM are halved, down to 4, until
-// a block has its dozen tiles.
+// with a quarter of the blocks (profiles/r02_midsize_launch.md).  So the blocks per SM are halved, down to 1024 threads
+// per SM, until a block has its 24 tiles (LBK_TILES_PER_BLOCK overrides, for the sweeps).  1024 threads per SM also leave
+// room for the NEXT kernel's first blocks while this one is still resident, which is what hides a sharded reduction's
+// record exchange under its successor: 2 GPUs, 2^26 per rank, isamax 41.2 -> 36.5 us (36.4 without any exchange).
 static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int threads, i64 ntiles, int *grid, i64 max_grid = kMaxGrid,
                     bool adapt = false)
 {
@@ -1389,7 +1397,8 @@ static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int th
         if (bps < 1) bps = 1;
     } else if (adapt && bps < kOneTilePerBlock) {
         const int floor_bps = std::max(1, 1024 / threads);          // 1024 threads per SM
-        while (bps > floor_bps && ntiles < (i64)12 * c->sms * bps) bps /= 2;
+        static const int want = [] { const char *e = getenv("LBK_TILES_PER_BLOCK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 24; }();
+        while (bps > floor_bps && ntiles < (i64)want * c->sms * bps) bps /= 2;
         if (bps < floor_bps) bps = floor_bps;
     }
     i64 g = std::min<i64>(std::max<i64>(ntiles, 1), (i64)c->sms * bps);
