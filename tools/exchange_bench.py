@@ -23,7 +23,7 @@ out = ctx.alloc(8)
 B = {"sasum": 4, "snrm2": 4, "isamax": 4, "sdot": 8}
 if rank == 0:
     print("routine,log2n_per_rank,ranks,us_sharded,us_local,exchange_us,GBps_per_gpu_sharded")
-for lg in (22, 23, 24, 25, 26, 27):
+for lg in [int(v) for v in os.environ.get("SIZES", "22,23,24,25,26,27").split(",")]:
     n = 1 << lg
     SETS = max(2, min(8, (1 << 29) // (4 * n)))
     xs = [ctx.alloc_sharded(n * world).fill_hash(1 + i) for i in range(SETS)]
