@@ -57,7 +57,7 @@ enum lbk_status {
     LBK_ERR_ARG = 3,         /* null handle / pointer, negative length, handle of another context */
     LBK_ERR_RANGE = 4,       /* 1+(n-1)|inc| exceeds the vector (reference: undefined behaviour) */
     LBK_ERR_ALIAS = 5,       /* the two operands overlap in a way an in-place parallel update cannot honour */
-    LBK_ERR_UNSUPPORTED = 6, /* e.g. a negative, zero or unequal increment on sharded vectors */
+    LBK_ERR_UNSUPPORTED = 6, /* e.g. a zero, opposite-signed or unequal increment on sharded vectors (equal negative ones are fine) */
     LBK_ERR_NOMEM = 7
 };
 
@@ -141,8 +141,9 @@ int lbk_set_exchange_timeout(lbk_ctx *ctx, int64_t milliseconds);
 int lbk_shard_range(int64_t global_len, int nranks, int rank, int64_t *lo, int64_t *hi);
 /* Sharded vectors take positive increments: logical element i of a call (n, inc) sits at global position i*inc.
  * Which of them rank r holds: the first one, how many, and the offset of the first inside r's block.  (Two
- * operands must have equal lengths and equal increments, so that every pairing stays on one rank; negative and
- * zero increments on shards are LBK_ERR_UNSUPPORTED.) */
+ * operands must have equal lengths and equal increments, so that every pairing stays on one rank.  Two equal NEGATIVE
+ * increments pair the same elements as their absolute values and are run that way; zero, opposite-signed and unequal
+ * increments on shards are LBK_ERR_UNSUPPORTED.) */
 int lbk_shard_span(int64_t global_len, int nranks, int rank, int64_t n, int64_t inc, int64_t *first, int64_t *count, int64_t *offset);
 
 /* ---- device vectors (the representation added beside Numerical.BLAS.Types, Types.hs:3) -----

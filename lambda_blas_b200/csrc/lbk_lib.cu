@@ -1271,7 +1271,7 @@ static int check_operand(lbk_ctx *c, const char *who, const lbk_vec *v, int dtyp
         // Logical element i sits at global position i*inc; this rank holds positions [lo, hi).  Positive increments
         // keep every pairing on one rank as long as both operands are partitioned alike (checked by the caller);
         // negative ones pair x[i] with y[n-1-i] across devices and zero replicates one rank's element: refused.
-        if (inc < 1) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take positive increments only");
+        if (inc < 1) return fail(c, LBK_ERR_UNSUPPORTED, std::string(who) + ": sharded vectors take equal increments, positive or both negative (not zero, not opposite signs)");
         if (span_exceeds(n, inc, v->global_len)) return fail(c, LBK_ERR_RANGE, std::string(who) + ": 1+(n-1)*inc exceeds the vector");
         shard_span(v->shard_off, v->shard_off + v->len, n, n == 1 ? 1 : inc, &op->i0, &op->n_local, &op->base);   // n == 1: the increment is never applied
         return LBK_OK;
@@ -1584,6 +1584,9 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
         if ((use_x && !x) || (use_y && !y)) return fail(c, LBK_ERR_ARG, std::string(who) + ": null vector");
         return fan_out(c, count, [&](lbk_ctx *sc, int r) { return map_entry<F>(sc, who, rid, f, n, part(x, r), incx, part(y, r), incy, part(xo, r), part(yo, r)); });
     }
+    // Two equal NEGATIVE increments on shards pair the same elements as their absolute values do (logical i sits at position
+    // (n-1-i)|inc| in BOTH vectors), and an elementwise update cannot see the order: run it forwards, every pairing on one rank.
+    if (use_x && use_y && x && y && x->sharded && y->sharded && incx < 0 && incx == incy && incx != INT64_MIN) { incx = -incx; incy = -incy; }
     Operand X{}, Y{};
     int s;
     if (use_x && (s = check_operand(c, who, x, dtype, incx, n, &X))) return s;
@@ -1805,6 +1808,8 @@ static int dot_common(lbk_ctx *c, const char *who, int rid, int kind, i64 n, flo
 {
     constexpr int dtype = sizeof(T) == 8 ? 1 : 0;
     LIVE(c, who);
+    // equal negative increments on shards: the same set of products as with their absolute values (a sum has no order here)
+    if (x && y && x->sharded && y->sharded && incx < 0 && incx == incy && incx != INT64_MIN) { incx = -incx; incy = -incy; }
     Operand X{}, Y{};
     int s;
     if ((s = check_operand(c, who, x, dtype, incx, n, &X))) return s;

@@ -89,7 +89,7 @@ def _worker(rank, world, port, q):
             wx, wy = oracle.srot(m, hx, inc, hy, inc, np.cos(0.3), np.sin(0.3))
             ok &= np.array_equal(x2.to_host().view(bits), wx[lo:hi].view(bits)) and np.array_equal(y3.to_host().view(bits), wy[lo:hi].view(bits))
         # what would pair elements across devices is refused, not silently wrong
-        for incx, incy in ((2, 3), (-1, -1), (1, -1), (0, 1)):
+        for incx, incy in ((2, 3), (-2, -3), (1, -1), (0, 1)):
             try:
                 lb.sdot(max(n // 4, 1), x, incx, y, incy)
                 ok &= (world == 1)

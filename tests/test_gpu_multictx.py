@@ -101,9 +101,18 @@ def test_sharded_routines_match_oracle(blas, oracle, mctx, n, dt):
         y2 = y.clone()
         ip.saxpy_(m, -0.75, x, inc, y2, inc)
         assert same(y2.to_host(), o("axpy")(m, -0.75, hx, inc, hy, inc))
+    # equal NEGATIVE increments pair the same elements as their absolute values: supported on shards, bit-exact for the maps
+    for inc in (-1, -3):
+        m = (n - 1) // abs(inc) + 1
+        prod = float(np.sum(np.abs(hx[::abs(inc)][:m].astype(np.float64) * hy[::abs(inc)][:m])))
+        assert abs(float(blas.dot(m, x, inc, y, inc)) - float(o("dot")(m, hx, inc, hy, inc))) <= 2 * m * u * prod + 1e-300
+        assert same(blas.axpy(m, 0.5, x, inc, y, inc).to_host(), o("axpy")(m, 0.5, hx, inc, hy, inc))
+        a, b = blas.rot(m, x, inc, y, inc, c_, s_)
+        wa, wb = o("rot")(m, hx, inc, hy, inc, c_, s_)
+        assert same(a.to_host(), wa) and same(b.to_host(), wb)
     # what would pair elements across devices is refused, not silently wrong
     if R > 1:
-        for incx, incy in ((2, 3), (-1, -1), (1, -1), (0, 1)):
+        for incx, incy in ((2, 3), (-2, -3), (1, -1), (0, 1)):
             with pytest.raises(blas.LbkError) as ei:
                 blas.dot(max(n // 4, 1), x, incx, y, incy)
             assert ei.value.status == 6
