@@ -1381,24 +1381,25 @@ static int variant_unroll(int variant)
     return 1;
 }
 
-// adapt: a reduction's grid-stride loop wants two dozen tiles per block.  The default 16 (8) blocks per SM were tuned at
-// n = 2^28, where a block runs ~28 tiles; at the sizes a rank sees when n_global = 2^28 is sharded over 8 GPUs (2^25) the
-// same grid leaves 3.5 tiles per block and a ragged, half-empty last wave: sasum 22.6 -> 18.3 us, isamax 26.3 -> 18.4 us
-// with a quarter of the blocks (profiles/r02_midsize_launch.md).  So the blocks per SM are halved, down to 1024 threads
-// per SM, until a block has its 24 tiles (LBK_TILES_PER_BLOCK overrides, for the sweeps).  1024 threads per SM also leave
-// room for the NEXT kernel's first blocks while this one is still resident, which is what hides a sharded reduction's
-// record exchange under its successor: 2 GPUs, 2^26 per rank, isamax 41.2 -> 36.5 us (36.4 without any exchange).
+// adapt_tile_bytes > 0: a reduction's grid-stride loop wants 384 KiB per operand per block (24 tiles of 16 KiB).  The default
+// 16 (8) blocks per SM were tuned at n = 2^28, where a block streams 453 KiB; at the sizes a rank sees when n_global = 2^28 is
+// sharded over 8 GPUs (2^25) the same grid leaves 3.5 tiles per block and a ragged, half-empty last wave: sasum 22.6 -> 18.3 us,
+// isamax 26.3 -> 18.4 us with a quarter of the blocks (profiles/r02_midsize_launch.md).  So the blocks per SM are halved, down to
+// 1024 threads per SM, until a block has its 384 KiB (LBK_TILES_PER_BLOCK = that figure in 16-KiB tiles, for the sweeps).
+// 1024 threads per SM also leave room for the NEXT kernel's first blocks while this one is still resident, which is what hides a
+// sharded reduction's record exchange under its successor: 2 GPUs, 2^26 per rank, isamax 41.2 -> 36.5 us (36.4 without any
+// exchange).  The measure is bytes, not tiles: sdot's tiles are twice sasum's, and shrinking ITS grid at 2^28 cost the bench step 1.1 %.
 static int grid_for(lbk_ctx *c, const void *kernel, const LaunchCfg &cfg, int threads, i64 ntiles, int *grid, i64 max_grid = kMaxGrid,
-                    bool adapt = false)
+                    i64 adapt_tile_bytes = 0)
 {
     int bps = cfg.blocks_per_sm;
     if (bps <= 0) {
         CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, 0));
         if (bps < 1) bps = 1;
-    } else if (adapt && bps < kOneTilePerBlock) {
+    } else if (adapt_tile_bytes > 0 && bps < kOneTilePerBlock) {
         const int floor_bps = std::max(1, 1024 / threads);          // 1024 threads per SM
-        static const int want = [] { const char *e = getenv("LBK_TILES_PER_BLOCK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 24; }();
-        while (bps > floor_bps && ntiles < (i64)want * c->sms * bps) bps /= 2;
+        static const i64 want_bytes = [] { const char *e = getenv("LBK_TILES_PER_BLOCK"); const int v = e ? atoi(e) : 0; return (i64)(v > 0 ? v : 24) << 14; }();
+        while (bps > floor_bps && ntiles * adapt_tile_bytes < want_bytes * c->sms * bps) bps /= 2;
         if (bps < floor_bps) bps = floor_bps;
     }
     i64 g = std::min<i64>(std::max<i64>(ntiles, 1), (i64)c->sms * bps);
@@ -1719,7 +1720,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         const i64 npack = (nl - head) / variant_vec<T>(variant);
         const i64 per_tile = (i64)variant_unroll(variant) * threads;
         int grid;
-        int s = grid_for(c, k, *pcfg, threads, (npack + per_tile - 1) / per_tile, &grid, kMaxGrid, !pcfg->pinned);
+        int s = grid_for(c, k, *pcfg, threads, (npack + per_tile - 1) / per_tile, &grid, kMaxGrid, pcfg->pinned ? 0 : per_tile * variant_vec<T>(variant) * (i64)sizeof(T));
         if (s) return s;
         i64 nn = nl, ib = idx_base;
         lbk_pdl::Op op;
