@@ -12,11 +12,21 @@
  * CHECKER or as the reported CPU baseline.  Nothing under lambda_blas_b200/
  * may import, link or execute it.
  *
- * PARITY UNPINNED (strict sense): the reference ships no golden vectors, no
- * known-answer tests and no fixtures for this path (its tests are unseeded
- * QuickCheck properties against Fortran netlib BLAS 3.7.0, test/Main.hs:28-52),
- * and neither GHC nor gfortran exist in this image, so the reference itself
- * cannot be run here.  What pins this file instead (tests/test_oracle_*.py):
+ * PARITY PINNED TO THE REFERENCE'S SOURCE, EVALUATED (not to a GHC build).  The
+ * reference ships no golden vectors, no known-answer tests and no fixtures for
+ * this path (its tests are unseeded QuickCheck properties against Fortran netlib
+ * BLAS 3.7.0, test/Main.hs:28-52), and neither GHC nor gfortran exist in this
+ * image, so the reference cannot be COMPILED here.  Its three hot-path modules
+ * are therefore evaluated from their text, where they lie under /root/reference,
+ * by oracle/hs_eval.py (a Haskell-subset evaluator: lexer, layout rule, parser,
+ * call-by-need evaluation; the primitives of base-4.9 / vector-0.11 it relies on
+ * are restated there and listed in its header).  What pins this file:
+ *   - tests/golden/ref_golden_{f32,f64}.json, the outputs of that evaluation over
+ *     the reference's test domains (generator: tests/golden/make_ref_golden.py):
+ *     this file must reproduce them BIT FOR BIT, reductions included
+ *     (tests/test_golden.py), here and on the GPU box; in the build container
+ *     tests/test_hs_eval.py re-evaluates the source against the fixtures and
+ *     against this file on fresh random inputs;
  *   - the one worked example the reference documents (README.md:57-59, = 32);
  *   - the reference's own differential property, re-stated: this file must
  *     equal, bit for bit, oracle/netlib_l1.c (a restatement of the published
@@ -28,6 +38,9 @@
  *     rounding per term for axpy/rot/rotm, within the reduction bound for
  *     dot/sdsdot/asum/nrm2 (OpenBLAS vectorises sums and contracts FMAs, so it is
  *     not netlib; it is an independent implementation, not a restatement).
+ * Not exercised by any of this: GHC's code generator itself (the evaluator
+ * performs one correctly rounded IEEE operation per arithmetic primitive, which
+ * is what GHC 8.0's native code generator emits for Float / Double on x86-64).
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile); no
  * -march=native, so no FMA contraction and no vectorised reassociation: every

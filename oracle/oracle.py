@@ -7,8 +7,9 @@ The functions keep the reference's PURE call surface (Numerical.BLAS.Single,
 src/Numerical/BLAS/Single.hs:84,113,129,147,165,201,222,421,441,484): vector results
 are NEW numpy arrays of the destination's full length; inputs are never modified.
 
-PARITY UNPINNED in the strict sense (no golden vectors in the reference, no GHC
-here) -- see the header of lblas_oracle.c for what pins it instead.
+Parity is pinned to the reference's own SOURCE, evaluated by oracle/hs_eval.py (no GHC
+here, so not to a compiled build): tests/golden/ref_golden_*.json -- see the header of
+lblas_oracle.c.
 """
 from __future__ import annotations
 

@@ -1,7 +1,7 @@
 """Generates tests/golden/level1_golden.json: seeded inputs and the ORACLE's outputs, bit patterns as uint32.
 
-The reference holds no golden vectors and cannot be run here (no GHC), so these fixtures are outputs of
-oracle/lblas_oracle.c -- cross-checked, case by case while generating, against the netlib 3.7.0
+These fixtures are outputs of oracle/lblas_oracle.c (the set made from the REFERENCE'S source is
+ref_golden_*.json, make_ref_golden.py) -- cross-checked, case by case while generating, against the netlib 3.7.0
 restatement wherever the reference's own tests assert `native == netlib` (inc != 0 rules of Main.hs).
 They pin the oracle against silent drift (compiler flags, edits) and give the GPU tests fixed inputs.
 Run from the repo root:  python tests/golden/make_golden.py

@@ -1,6 +1,12 @@
-"""Golden fixtures (tests/golden/level1_golden.json, made by tests/golden/make_golden.py).
+"""Golden fixtures, two sets with the same layout:
 
-CPU: the oracle must reproduce them bit for bit (guards the checker itself).
+  "reference"  tests/golden/ref_golden_{f32,f64}.json -- outputs of the REFERENCE'S OWN SOURCE
+               (src/Numerical/BLAS/{Types,Util,Single}.hs) evaluated by oracle/hs_eval.py in the build container
+               (tests/golden/make_ref_golden.py): this is what pins the oracle and the CUDA path to the reference;
+  "oracle"     tests/golden/level1_golden{,_f64}.json -- outputs of oracle/lblas_oracle.c (make_golden.py): guards
+               the checker against drift.
+
+CPU: the oracle must reproduce both bit for bit -- reductions included, it is as sequential as the reference.
 GPU: the CUDA path must match them -- isamax and every elementwise routine bit for bit (NaN matches NaN),
 the reductions within 2*n*eps*sum|x_i*y_i| -- including the non-finite / signed-zero / denormal cases
 the reference's own generators never produce ("spiced" input sets) and every increment sign, 0 included.
@@ -12,17 +18,37 @@ import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = {np.float32: json.load(open(os.path.join(HERE, "golden", "level1_golden.json"))),
-         np.float64: json.load(open(os.path.join(HERE, "golden", "level1_golden_f64.json")))}
+_NAMES = {("oracle", np.float32): "level1_golden.json", ("oracle", np.float64): "level1_golden_f64.json",
+          ("reference", np.float32): "ref_golden_f32.json", ("reference", np.float64): "ref_golden_f64.json"}
+FILES = {k: json.load(open(os.path.join(HERE, "golden", v))) for k, v in _NAMES.items()}
 DTYPES = [np.float32, np.float64]
+SETS = [pytest.param(w, d, id=f"{w}-{np.dtype(d).name}") for w in ("reference", "oracle") for d in DTYPES]
 DT = np.float32          # set by each test: the instance (Float / Double) the file was made for
-G = FILES[np.float32]
+G = FILES[("oracle", np.float32)]
+MGR_FIELDS = {"FLAGNEG2": (), "FLAGNEG1": ("d1", "d2", "x1", "h11", "h12", "h21", "h22"),
+              "FLAG0": ("d1", "d2", "x1", "h12", "h21"), "FLAG1": ("d1", "d2", "x1", "h11", "h22")}      # Types.hs:15-20
+MGR_FLAG = {"FLAGNEG2": -2, "FLAGNEG1": -1, "FLAG0": 0, "FLAG1": 1}
 
 
-def use(dtype):
+def use(dtype, which="oracle"):
     global DT, G, EPS
-    DT, G = dtype, FILES[dtype]
+    DT, G = dtype, FILES[(which, dtype)]
     EPS = 2.0 ** -24 if dtype == np.float32 else 2.0 ** -53
+
+
+def check_scalars(srotg, srotmg):
+    """rotg / rotmg against the current file's scalar cases (the two sets store rotmg differently)"""
+    for s in G["scalars"]:
+        a = f32(s["args"])
+        assert same(list(srotg(a[0], a[1])), f32(s["rotg"])), ("rotg", list(a))
+        m = srotmg(*a)
+        if isinstance(s["rotmg"][0], str):       # reference set: constructor name + the constructor's own fields
+            con = s["rotmg"][0]
+            assert m.flag == MGR_FLAG[con], ("rotmg", list(a))
+            assert same([getattr(m, f) for f in MGR_FIELDS[con]], f32(s["rotmg"][1:])), ("rotmg", con, list(a))
+        else:                                    # oracle set: flag + all seven fields (absent ones 0)
+            assert m.flag == s["rotmg"][0]
+            assert same([m.d1, m.d2, m.x1, m.h11, m.h12, m.h21, m.h22], f32(s["rotmg"][1:]))
 
 
 EPS = 2.0 ** -24
@@ -62,15 +88,17 @@ def run(impl, to_dev, to_host, case):
     return outs, x, y
 
 
-def test_readme_example_in_golden(oracle):
-    use(np.float32)
+@pytest.mark.parametrize("which", ["reference", "oracle"])
+def test_readme_example_in_golden(oracle, which):
+    use(np.float32, which)
     r = G["readme_example"]
+    assert r["sdot"] == int(np.float32(32.0).view(np.uint32))       # README.md:57-59 of the reference
     assert oracle.sdot(r["n"], f32(r["x"]), 1, f32(r["y"]), 1).view(np.uint32) == r["sdot"]
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_oracle_reproduces_golden(oracle, dtype):
-    use(dtype)
+@pytest.mark.parametrize("which,dtype", SETS)
+def test_oracle_reproduces_golden(oracle, which, dtype):
+    use(dtype, which)
     srotg, srotmg = (oracle.srotg, oracle.srotmg) if dtype == np.float32 else (oracle.drotg, oracle.drotmg)
     for case in G["cases"]:
         outs, x, y = run(oracle, lambda v: v, lambda v: v, case)
@@ -88,30 +116,21 @@ def test_oracle_reproduces_golden(oracle, dtype):
         flags = oracle.ModGivensRot(int(p[0]), h11=p[1], h21=p[2], h12=p[3], h22=p[4])
         mx, my = oracle.srotm(flags, case["n"], x, case["incx"], y, case["incy"])
         assert same(mx, f32(want["srotm"][0])) and same(my, f32(want["srotm"][1]))
-    for s in G["scalars"]:
-        a = f32(s["args"])
-        assert same(list(srotg(a[0], a[1])), f32(s["rotg"]))
-        m = srotmg(*a)
-        assert m.flag == s["rotmg"][0] and same(list(m)[1:], f32(s["rotmg"][1:]))
+    check_scalars(srotg, srotmg)
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_product_host_scalars_match_golden(blas, dtype):
-    use(dtype)
+@pytest.mark.parametrize("which,dtype", SETS)
+def test_product_host_scalars_match_golden(blas, which, dtype):
+    use(dtype, which)
     srotg, srotmg = (blas.srotg, blas.srotmg) if dtype == np.float32 else (blas.drotg, blas.drotmg)
-    for s in G["scalars"]:
-        a = f32(s["args"])
-        assert same(list(srotg(a[0], a[1])), f32(s["rotg"]))
-        m = srotmg(*a)
-        assert m.flag == s["rotmg"][0]
-        assert same([m.d1, m.d2, m.x1, m.h11, m.h12, m.h21, m.h22], f32(s["rotmg"][1:]))
+    check_scalars(srotg, srotmg)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_cuda_path_matches_golden(blas, ctx, dtype):
+@pytest.mark.parametrize("which,dtype", SETS)
+def test_cuda_path_matches_golden(blas, ctx, which, dtype):
     import lambda_blas_b200 as lb
-    use(dtype)
+    use(dtype, which)
     big = 1e37 if dtype == np.float32 else 1e300
     for case in G["cases"]:
         n, ix, iy = case["n"], case["incx"], case["incy"]
