@@ -118,6 +118,12 @@ int lbk_launch_count(lbk_ctx *ctx, int64_t *launches);
  * are launched the ordinary way (only independent ones overlap), 4 = only true dependencies are. */
 int lbk_set_pdl(lbk_ctx *ctx, int enabled);
 int lbk_pdl_count(lbk_ctx *ctx, int64_t *launches);
+/* Unit-stride operands that start at DIFFERENT offsets inside a 16-byte pack (views, wrapped foreign pointers) cannot
+ * share 128/256-bit accesses.  When the read-only x is the only odd one out (axpy, copy, out-of-place scal, dot, sdsdot)
+ * the kernels still read it in aligned 16-byte packs and shift the lanes; every other case moves
+ * one element per access.  lbk_shifted_count reports how many launches read x that way; the routines "mapshifted" /
+ * "redshifted" of lbk_set_launch choose their shape (a one-element variant turns the path off). */
+int lbk_shifted_count(lbk_ctx *ctx, int64_t *launches);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink -------------------------------------- */
 /* Rank 0 makes an id and hands the 128 bytes to every rank (any transport; the host layer uses

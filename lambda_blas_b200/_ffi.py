@@ -50,6 +50,7 @@ PROTOTYPES = {
     "lbk_launch_count": (_int, [_vp, _pi64]),
     "lbk_set_pdl": (_int, [_vp, _int]),
     "lbk_pdl_count": (_int, [_vp, _pi64]),
+    "lbk_shifted_count": (_int, [_vp, _pi64]),
     "lbk_comm_unique_id": (_int, [C.c_char_p]),
     "lbk_comm_init": (_int, [_vp, _int, _int, C.c_char_p]),
     "lbk_comm_info": (_int, [_vp, _pint, _pint]),

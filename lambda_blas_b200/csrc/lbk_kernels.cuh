@@ -42,6 +42,12 @@ constexpr int kMaxThreads = 512;        // launch bound of every streaming kerne
 #endif
 constexpr int reduce_min_blocks(int bytes_per_operand) { return bytes_per_operand >= 256 ? 1 : LBK_REDUCE_MINB; }
 constexpr u64 kNanKey = ~0ull;
+// The shifted-load shapes (shift_pack) are launched with at most 256 threads and compiled for 4 resident blocks of
+// them (64 registers), or for 3 (80 registers) where two operands are loaded or the accumulator is a double: those
+// spill at 64, and 24 bytes of spill cost sdot four points (profiles/r02_misaligned.md).  ptxas -v: no shape that is a
+// default spills (tests/test_sass.py keeps it so).
+constexpr int kShiftThreads = 256;
+constexpr int shift_min_blocks(bool heavy) { return heavy ? 3 : 4; }
 
 // ------------------------------------------------------------------------------------------------
 // element-type helpers: one IEEE operation each, never contracted (the library is built with
@@ -195,38 +201,101 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
+// Shifted loads.  Unit-stride operands that are misaligned DIFFERENTLY cannot share pack boundaries: with the body
+// laid out on the other operands' boundaries, logical pack p of the read-only operand x starts XSH elements
+// (0 < XSH < VEC) past a boundary.  Instead of falling back to one element per access, a thread loads ONE aligned
+// pack and takes the few elements it lacks from a neighbouring lane's pack with a shuffle -- consecutive lanes own
+// consecutive packs.  Whichever is fewer:
+//   down (XSH <= VEC/2): the pack that holds the thread's first VEC-XSH elements; the last XSH come from lane+1;
+//   up   (XSH >  VEC/2): the pack that holds its last XSH elements; the first VEC-XSH come from lane-1.
+// The lane at the warp's edge (31 / 0) has no such neighbour and reads those elements -- its own -- one by one: at
+// most VEC/2 four-byte requests per warp and row, inside sectors the neighbouring warp fetches anyway.  The host
+// leaves at least VEC-XSH tail elements (and peels at least XSH head elements), so every aligned pack that is
+// touched lies inside the vector.  XSH is a template argument: the lane renaming is free, what is added per pack
+// is min(XSH, VEC-XSH) shuffles (profiles/r02_misaligned.md).
+// ------------------------------------------------------------------------------------------------
+template <int VEC, int XSH> struct Shift {
+    static constexpr bool DOWN = XSH > 0 && 2 * XSH <= VEC;
+    static constexpr int E = XSH <= 0 ? 1 : (DOWN ? XSH : VEC - XSH);     // elements taken from the neighbour
+    static constexpr int PACK0 = DOWN ? -XSH : VEC - XSH;                // the aligned pack, relative to the thread's first element
+    static constexpr int EDGE0 = DOWN ? VEC - XSH : 0;                   // the edge lane's own elements, likewise
+    static constexpr unsigned EDGE_LANE = DOWN ? 31u : 0u;
+};
+// a: the aligned pack; ex: on the edge lane, the E elements it read itself
+template <class T, int VEC, int XSH>
+__device__ __forceinline__ void shift_pack(Pack<T, VEC> &out, const Pack<T, VEC> &a, const T (&ex)[Shift<VEC, XSH>::E], bool edge_lane)
+{
+    using S = Shift<VEC, XSH>;
+    T nb[S::E];
+#pragma unroll
+    for (int j = 0; j < S::E; ++j) {
+        const T v = S::DOWN ? __shfl_down_sync(0xffffffffu, a.v[j], 1) : __shfl_up_sync(0xffffffffu, a.v[VEC - S::E + j], 1);
+        nb[j] = edge_lane ? ex[j] : v;
+    }
+#pragma unroll
+    for (int l = 0; l < VEC; ++l) {
+        if constexpr (S::DOWN) out.v[l] = (l + XSH < VEC) ? a.v[(l + XSH) % VEC] : nb[(l + XSH) % VEC];
+        else out.v[l] = (l < S::E) ? nb[l % S::E] : a.v[(l + VEC - S::E) % VEC];
+    }
+}
+// Loads of one row: the aligned pack and, on the edge lane, its own E elements.
+template <class T, int VEC, int XSH, int POLICY>
+__device__ __forceinline__ void shift_load(Pack<T, VEC> &a, T (&ex)[Shift<VEC, XSH>::E], const T *first, bool edge_lane)
+{
+    using S = Shift<VEC, XSH>;
+    load_pack<VEC, POLICY, true>(a, first + S::PACK0);
+    if (edge_lane) {
+#pragma unroll
+        for (int j = 0; j < S::E; ++j) { Pack<T, 1> p; load_pack<1, POLICY, true>(p, first + S::EDGE0 + j); ex[j] = p.v[0]; }
+    }
+}
+// packs of the body when x is read through shifted loads: the last aligned pack touched must end inside the vector
+template <int VEC, int XSH>
+__host__ __device__ __forceinline__ i64 body_packs(i64 n, i64 head)
+{
+    const i64 body = n - head - (XSH > 0 ? VEC - XSH : 0);
+    return body > 0 ? body / VEC : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // map functors.  (x, y) are the OLD values; the functor overwrites them with the new ones.
 // ------------------------------------------------------------------------------------------------
 template <class T> struct AxpyF {   // Single.hs:439   y + a*x
     using Scalar = T;
     T a;
     static constexpr bool RX = true, RY = true, WX = false, WY = true;
+    static constexpr bool XSHIFT = true;      // built with shifted loads of x as well (see shift_pack)
     __device__ __forceinline__ void operator()(T &x, T &y) const { y = add_rn(y, mul_rn(a, x)); }
 };
 template <class T> struct ScalF {   // Single.hs:110   x*a
     using Scalar = T;
     T a;
     static constexpr bool RX = true, RY = false, WX = true, WY = false;
+    static constexpr bool XSHIFT = true;      // out of place only: in place, source and destination are one pointer
     __device__ __forceinline__ void operator()(T &x, T &) const { x = mul_rn(x, a); }
 };
 template <class T> struct CopyF {   // Single.hs:127   \_ x -> x
     using Scalar = T;
     static constexpr bool RX = true, RY = false, WX = false, WY = true;
+    static constexpr bool XSHIFT = true;
     __device__ __forceinline__ void operator()(T &x, T &y) const { y = x; }
 };
 template <class T> struct FillF {   // no reference counterpart: lbk_vec_fill (test / bench set-up), a pure store stream
     using Scalar = T;
+    static constexpr bool XSHIFT = false;
     T value;
     static constexpr bool RX = false, RY = false, WX = true, WY = false;
     __device__ __forceinline__ void operator()(T &x, T &) const { x = value; }
 };
 template <class T> struct SwapF {   // Single.hs:143-145
     using Scalar = T;
+    static constexpr bool XSHIFT = false;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
     __device__ __forceinline__ void operator()(T &x, T &y) const { T t = x; x = y; y = t; }
 };
 template <class T> struct RotF {    // Single.hs:418-419   c*x + s*y ; c*y - s*x
     using Scalar = T;
+    static constexpr bool XSHIFT = false;
     T c, s;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
     __device__ __forceinline__ void operator()(T &x, T &y) const
@@ -238,6 +307,7 @@ template <class T> struct RotF {    // Single.hs:418-419   c*x + s*y ; c*y - s*x
 };
 template <class T> struct RotmNeg1F {   // Single.hs:475-476   h11*x + h12*y ; h21*x + h22*y
     using Scalar = T;
+    static constexpr bool XSHIFT = false;
     T h11, h12, h21, h22;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
     __device__ __forceinline__ void operator()(T &x, T &y) const
@@ -249,6 +319,7 @@ template <class T> struct RotmNeg1F {   // Single.hs:475-476   h11*x + h12*y ; h
 };
 template <class T> struct Rotm0F {      // Single.hs:478-479   x + h12*y ; h21*x + y
     using Scalar = T;
+    static constexpr bool XSHIFT = false;
     T h12, h21;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
     __device__ __forceinline__ void operator()(T &x, T &y) const
@@ -260,6 +331,7 @@ template <class T> struct Rotm0F {      // Single.hs:478-479   x + h12*y ; h21*x
 };
 template <class T> struct Rotm1F {      // Single.hs:481-482   h11*x + y ; -x + h22*y
     using Scalar = T;
+    static constexpr bool XSHIFT = false;
     T h11, h22;
     static constexpr bool RX = true, RY = true, WX = true, WY = true;
     __device__ __forceinline__ void operator()(T &x, T &y) const
@@ -297,20 +369,20 @@ __device__ __forceinline__ unsigned low_bits(double v) { return (unsigned)__doub
 // (7130 -> 6590 GB/s).
 constexpr int map_min_blocks(int loaded_bytes_per_thread) { return loaded_bytes_per_thread <= 32 ? 4 : loaded_bytes_per_thread <= 128 ? 2 : 1; }
 
-template <class F, int VEC, int UNROLL, int POLICY, bool REV = false>
-__global__ void __launch_bounds__(kMaxThreads, map_min_blocks(VEC * UNROLL * (int)sizeof(typename F::Scalar) * ((F::RX ? 1 : 0) + (F::RY ? 1 : 0))))
+template <class F, int VEC, int UNROLL, int POLICY, bool REV = false, int XSH = 0>
+__global__ void __launch_bounds__(XSH > 0 ? kShiftThreads : kMaxThreads, XSH > 0 ? shift_min_blocks(F::RX && F::RY) : map_min_blocks(VEC * UNROLL * (int)sizeof(typename F::Scalar) * ((F::RX ? 1 : 0) + (F::RY ? 1 : 0))))
 map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr, typename F::Scalar *xw,
                 typename F::Scalar *yw, i64 head, i64 n, unsigned fence_mask, int wait_mode)
 {
     using T = typename F::Scalar;
+    static_assert(XSH == 0 || (XSH > 0 && XSH < VEC && !REV && F::RX), "shifted loads: 0 < XSH < VEC, forward pairing, x is read");
     constexpr bool FENCE = POLICY == 6 && (F::RX || F::RY);
     // wait_mode (lbk_pdl.hpp): 0 wait for the predecessors only before exiting, 1 before the first store,
     // 2 before the first load -- and in that case release the dependents only afterwards
     const int wait_before_store = wait_mode == 1;
     if (wait_mode == 2) pdl_wait();
     pdl_launch_dependents();
-    const i64 body = n - head;
-    const i64 npack = body / VEC;
+    const i64 npack = body_packs<VEC, XSH>(n, head);
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
     const T *bxr = xr + head;
@@ -319,16 +391,31 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
     const T *byr = REV ? yr + (n - head) - VEC : yr + head;
     T *byw = REV ? yw + (n - head) - VEC : yw + head;
     constexpr int YS = REV ? -1 : 1;
+    // shifted loads of x: a whole warp takes the fast path together (its last lane decides), the shuffles need every lane
+    const bool edge_lane = (threadIdx.x & 31) == Shift<VEC, XSH>::EDGE_LANE;
+    const unsigned edge = XSH > 0 ? (threadIdx.x | 31u) : threadIdx.x;
 
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const i64 p0 = tile * per_tile + threadIdx.x;
         Pack<T, VEC> xv[UNROLL], yv[UNROLL];
-        if (p0 + (i64)(UNROLL - 1) * blockDim.x < npack) {   // whole tile in range for this thread
+        if (tile * per_tile + edge + (i64)(UNROLL - 1) * blockDim.x < npack) {   // whole tile in range for this thread (warp)
+            if constexpr (XSH > 0) {
+                T ex[UNROLL][Shift<VEC, XSH>::E];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
-                if constexpr (F::RX) load_pack<VEC, POLICY, !F::WX>(xv[u], bxr + e);
-                if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + YS * e);
+                for (int u = 0; u < UNROLL; ++u) {
+                    const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
+                    shift_load<T, VEC, XSH, POLICY>(xv[u], ex[u], bxr + e, edge_lane);
+                    if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + e);
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) { const Pack<T, VEC> a = xv[u]; shift_pack<T, VEC, XSH>(xv[u], a, ex[u], edge_lane); }
+            } else {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
+                    if constexpr (F::RX) load_pack<VEC, POLICY, !F::WX>(xv[u], bxr + e);
+                    if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + YS * e);
+                }
             }
             i64 held = 0;
             if constexpr (FENCE) {
@@ -358,7 +445,10 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
                 const i64 p = p0 + (i64)u * blockDim.x;
                 if (p < npack) {
                     const i64 e = p * VEC;
-                    if constexpr (F::RX) load_pack<VEC, POLICY, !F::WX>(xv[u], bxr + e);
+                    if constexpr (XSH > 0) {             // the ragged last tile: x one element at a time
+#pragma unroll
+                        for (int l = 0; l < VEC; ++l) xv[u].v[l] = bxr[e + l];
+                    } else if constexpr (F::RX) load_pack<VEC, POLICY, !F::WX>(xv[u], bxr + e);
                     if constexpr (F::RY) load_pack<VEC, POLICY, !F::WY>(yv[u], byr + YS * e);
 #pragma unroll
                     for (int l = 0; l < VEC; ++l) f(xv[u].v[l], yv[u].v[REV ? VEC - 1 - l : l]);
@@ -876,15 +966,17 @@ __device__ __forceinline__ u64 apply_x0(typename Op::Partial &p, const FinishArg
 }
 
 // reduce, unit stride.  idx_base = global logical index of element 0 of this shard (iamax).
-template <class Op, int VEC, int UNROLL, int POLICY, bool REV = false>
-__global__ void __launch_bounds__(kMaxThreads, reduce_min_blocks(VEC * UNROLL * (int)sizeof(typename Op::Scalar)))
+template <class Op, int VEC, int UNROLL, int POLICY, bool REV = false, int XSH = 0>
+__global__ void __launch_bounds__(XSH > 0 ? kShiftThreads : kMaxThreads, XSH > 0 ? shift_min_blocks(sizeof(typename Op::Acc) > sizeof(typename Op::Scalar)) : reduce_min_blocks(VEC * UNROLL * (int)sizeof(typename Op::Scalar)))
 reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i64 head, i64 n, i64 idx_base,
                    Record *partials, unsigned *ticket, FinishArgs fa, int late_trigger, int wait_first)
 {
     using T = typename Op::Scalar;
+    static_assert(XSH == 0 || (XSH > 0 && XSH < VEC && !REV && Op::TWO), "shifted loads of x: two operands, forward pairing");
     constexpr int YS = REV ? -1 : 1;     // REV: element i pairs x[i] with y[n-1-i] (see map_unit_kernel)
-    const i64 body = n - head;
-    const i64 npack = body / VEC;
+    const i64 npack = body_packs<VEC, XSH>(n, head);
+    const bool edge_lane = (threadIdx.x & 31) == Shift<VEC, XSH>::EDGE_LANE;
+    const unsigned edge = XSH > 0 ? (threadIdx.x | 31u) : threadIdx.x;      // shifted loads: a warp takes the fast path together
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
     const T *bx = x + head, *by = REV ? y + (n - head) - VEC : y + head;
@@ -900,12 +992,24 @@ reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const i64 p0 = tile * per_tile + threadIdx.x;
         Pack<T, VEC> xv[UNROLL], yv[UNROLL];
-        if (p0 + (i64)(UNROLL - 1) * blockDim.x < npack) {
+        if (tile * per_tile + edge + (i64)(UNROLL - 1) * blockDim.x < npack) {
+            if constexpr (XSH > 0) {
+                T ex[UNROLL][Shift<VEC, XSH>::E];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
-                load_pack<VEC, POLICY, true>(xv[u], bx + e);
-                if constexpr (Op::TWO) load_pack<VEC, POLICY, true>(yv[u], by + YS * e);
+                for (int u = 0; u < UNROLL; ++u) {
+                    const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
+                    shift_load<T, VEC, XSH, POLICY>(xv[u], ex[u], bx + e, edge_lane);          // see shift_pack
+                    load_pack<VEC, POLICY, true>(yv[u], by + e);
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) { const Pack<T, VEC> a = xv[u]; shift_pack<T, VEC, XSH>(xv[u], a, ex[u], edge_lane); }
+            } else {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const i64 e = (p0 + (i64)u * blockDim.x) * VEC;
+                    load_pack<VEC, POLICY, true>(xv[u], bx + e);
+                    if constexpr (Op::TWO) load_pack<VEC, POLICY, true>(yv[u], by + YS * e);
+                }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) pack_step<Op, VEC, REV>(acc, xv[u], yv[u], it * (UNROLL * VEC) + u * VEC);
@@ -915,7 +1019,10 @@ reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i
                 const i64 p = p0 + (i64)u * blockDim.x;
                 if (p < npack) {
                     const i64 e = p * VEC;
-                    load_pack<VEC, POLICY, true>(xv[u], bx + e);
+                    if constexpr (XSH > 0) {
+#pragma unroll
+                        for (int l = 0; l < VEC; ++l) xv[u].v[l] = bx[e + l];
+                    } else load_pack<VEC, POLICY, true>(xv[u], bx + e);
                     if constexpr (Op::TWO) load_pack<VEC, POLICY, true>(yv[u], by + YS * e);
                     pack_step<Op, VEC, REV>(acc, xv[u], yv[u], it * (UNROLL * VEC) + u * VEC);
                 }

@@ -51,9 +51,9 @@ constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte
 
 // launch shapes are per routine and shared by the Float and Double instances (they are in bytes per access)
 enum Routine { R_DOT, R_SDSDOT, R_ASUM, R_NRM2, R_IAMAX, R_AXPY, R_SCAL, R_COPY, R_SWAP, R_ROT, R_ROTM, R_FILL, R_MAPSTRIDED, R_REDSTRIDED,
-               R_MAPMISALIGNED, R_REDMISALIGNED, R_COUNT };
+               R_MAPMISALIGNED, R_REDMISALIGNED, R_MAPSHIFTED, R_REDSHIFTED, R_COUNT };
 static const char *kRoutineNames[R_COUNT] = {"dot", "sdsdot", "asum", "nrm2", "iamax", "axpy", "scal", "copy", "swap", "rot", "rotm", "fill", "mapstrided", "redstrided",
-                                            "mapmisaligned", "redmisaligned"};
+                                            "mapmisaligned", "redmisaligned", "mapshifted", "redshifted"};
 struct LaunchCfg { int variant; int threads; int blocks_per_sm; bool pinned = false; };   // <= 0: default / from occupancy; pinned: set by lbk_set_launch, taken literally
 // Defaults from the n = 2^28 sweeps on B200 (profiles/r01_tune_*.csv; tools/tune.py), reductions tuned
 // with their tails overlapped (PDL).  blocks_per_sm 0 = one resident wave (occupancy x SMs); larger
@@ -75,6 +75,10 @@ static const LaunchCfg kDefaultCfg[R_COUNT] = {
        fully coalesced (a warp still moves 128 contiguous bytes per instruction), many of them in flight per thread and as large
        a tile per block as the wide shapes have -- profiles/r02_misaligned.md */
     /* map */ {26, 256, kOneTilePerBlock}, /* reduce */ {26, 512, 16},
+    /* the same operands when only the READ-ONLY x is the odd one out (axpy, copy, out-of-place scal; dot, sdsdot): 16-byte
+       aligned packs of x + a lane shift (lbk_kernels.cuh, shift_pack).  The variant gives the unroll (its packs must be 16
+       bytes); a one-element variant here turns the shifted path off (A/B against the shapes above). */
+    /* map */ {19, 256, kOneTilePerBlock}, /* reduce */ {0, 256, 16},
 };
 
 constexpr int kMaxGrid = 148 * 32 * 2;   // partial-record scratch (blocks)
@@ -133,6 +137,7 @@ struct lbk_ctx {
     lbk_pdl::State pdl;               // which kernels of the stream may overlap: see lbk_pdl.hpp
     int64_t launches = 0;
     int64_t pdl_launches = 0;
+    int64_t shifted_launches = 0;     // unit-stride kernels that read x through shifted loads (lbk_shifted_count)
     std::string err;
 };
 
@@ -633,6 +638,14 @@ extern "C" int lbk_pdl_count(lbk_ctx *c, int64_t *launches)
     if (!c || !launches) return fail(c, LBK_ERR_ARG, "lbk_pdl_count: null argument");
     *launches = c->pdl_launches;
     for (lbk_ctx *s : c->subs) *launches += s->pdl_launches;
+    return LBK_OK;
+}
+
+extern "C" int lbk_shifted_count(lbk_ctx *c, int64_t *launches)
+{
+    if (!c || !launches) return fail(c, LBK_ERR_ARG, "lbk_shifted_count: null argument");
+    *launches = c->shifted_launches;
+    for (lbk_ctx *s : c->subs) *launches += s->shifted_launches;
     return LBK_OK;
 }
 
@@ -1371,6 +1384,62 @@ static const void *map_kernel_ptr_rev(int variant)
     return variant == kScalarVariant ? (const void *)lbk::map_unit_kernel<F, 1, 4, 1, true>
                                      : (const void *)lbk::map_unit_kernel<F, vec_t<T>(4), 4, 1, true>;
 }
+// shifted loads of x (lbk_kernels.cuh, shift_pack): 16-byte packs, unroll 2 or 4, shift 1..VEC-1 elements
+template <class F, int UNROLL>
+static const void *map_kernel_ptr_shifted_u(int shift)
+{
+    using T = typename F::Scalar;
+    if constexpr (F::XSHIFT) {
+        constexpr int V = vec_t<T>(4);
+        if (shift == 1) return (const void *)lbk::map_unit_kernel<F, V, UNROLL, 6, false, 1>;
+        if constexpr (V == 4) {
+            if (shift == 2) return (const void *)lbk::map_unit_kernel<F, V, UNROLL, 6, false, 2>;
+            if (shift == 3) return (const void *)lbk::map_unit_kernel<F, V, UNROLL, 6, false, 3>;
+        }
+    }
+    return nullptr;
+}
+template <class F>
+static const void *map_kernel_ptr_shifted(int unroll, int shift)
+{
+    return unroll == 2 ? map_kernel_ptr_shifted_u<F, 2>(shift) : unroll == 4 ? map_kernel_ptr_shifted_u<F, 4>(shift) : nullptr;
+}
+template <class Op, int UNROLL>
+static const void *reduce_kernel_ptr_shifted_u(int shift)
+{
+    using T = typename Op::Scalar;
+    if constexpr (Op::TWO) {
+        constexpr int V = vec_t<T>(4);
+        if (shift == 1) return (const void *)lbk::reduce_unit_kernel<Op, V, UNROLL, 1, false, 1>;
+        if constexpr (V == 4) {
+            if (shift == 2) return (const void *)lbk::reduce_unit_kernel<Op, V, UNROLL, 1, false, 2>;
+            if (shift == 3) return (const void *)lbk::reduce_unit_kernel<Op, V, UNROLL, 1, false, 3>;
+        }
+    }
+    return nullptr;
+}
+template <class Op>
+static const void *reduce_kernel_ptr_shifted(int unroll, int shift)
+{
+    return unroll == 2 ? reduce_kernel_ptr_shifted_u<Op, 2>(shift) : unroll == 4 ? reduce_kernel_ptr_shifted_u<Op, 4>(shift) : nullptr;
+}
+// x is the only pointer whose offset inside a 16-byte pack differs from the others' (which agree): the body is laid out on
+// the others' boundaries and x is read through shifted loads.  Returns the shift (0: not this case) and the head to peel.
+template <class T>
+static int shifted_layout(const T *x, const T *const *others, int nothers, i64 n, i64 *head)
+{
+    const int vec = variant_vec<T>(kVec4Fallback);
+    if (nothers < 1 || n < 16 * vec) return 0;
+    const int m = misalign(others[0], vec);
+    for (int i = 1; i < nothers; ++i) if (misalign(others[i], vec) != m) return 0;
+    i64 h = (vec - m) % vec;
+    const int shift = (int)((misalign(x, vec) + h) % vec);
+    if (shift == 0) return 0;
+    if (h < shift) h += vec;            // the first aligned pack of x that is touched starts inside the vector
+    *head = h;
+    return shift;
+}
+
 static int variant_unroll(int variant)
 {
     switch (variant) {
@@ -1436,6 +1505,7 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
     // the reversed pairing has one shape: 16-byte packs x 4, 128 threads, no fence (config-4 sweep, profiles/)
     int threads = rev ? 128 : (cfg.threads > 0 ? cfg.threads : 256);
     i64 head = 0;
+    int xshift = 0;             // > 0: x is read through shifted loads (lbk_kernels.cuh, shift_pack)
     const void *k;
     if (rev) {
         const T *xp[2], *yp[2]; int nx = 0, ny = 0;
@@ -1455,13 +1525,24 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
         // both vectors; 256 threads (profiles/r02_misaligned.md)
         LaunchCfg mis = c->cfg[R_MAPMISALIGNED];
         if (mis.variant == kDefaultCfg[R_MAPMISALIGNED].variant && F::WX && F::WY) mis.variant = kScalarVariant;
-        if (resolve_alignment<T>(&variant, &head, ptrs, np, n, kVariantVec[mis.variant] == 1 ? mis.variant : kScalarVariant) && variant == mis.variant) {
+        const bool aligned = !resolve_alignment<T>(&variant, &head, ptrs, np, n, kVariantVec[mis.variant] == 1 ? mis.variant : kScalarVariant);
+        if (!aligned && variant == mis.variant) {
             pcfg = &c->cfg[R_MAPMISALIGNED];
             if (mis.threads > 0) threads = mis.threads;
         }
         k = map_kernel_ptr<F>(variant);
+        if constexpr (F::XSHIFT) {
+            const LaunchCfg &sh = c->cfg[R_MAPSHIFTED];
+            if (variant_vec<T>(variant) == 1 && kVariantVec[sh.variant] == 4) {      // only x is the odd one out?
+                i64 h = 0;
+                const int shift = shifted_layout<T>(xr, ptrs + 1, np - 1, n, &h);
+                const void *ks = shift ? map_kernel_ptr_shifted<F>(variant_unroll(sh.variant), shift) : nullptr;
+                if (ks) { k = ks; head = h; variant = sh.variant; pcfg = &sh; threads = std::min(sh.threads > 0 ? sh.threads : 256, lbk::kShiftThreads); xshift = shift; }
+            }
+        }
     }
-    const i64 npack = (n - head) / variant_vec<T>(variant);
+    const i64 npack = xshift ? std::max<i64>(0, (n - head - (variant_vec<T>(variant) - xshift)) / variant_vec<T>(variant))
+                             : (n - head) / variant_vec<T>(variant);
     const i64 per_tile = (i64)variant_unroll(variant) * threads;
     int grid;
     int s = grid_for(c, k, *pcfg, threads, (npack + per_tile - 1) / per_tile, &grid, 0x7fffffff);   // maps keep no per-block scratch
@@ -1478,6 +1559,7 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
     int wait_mode = plan.mode == lbk_pdl::WAIT_BEFORE_STORE ? 1 : plan.mode == lbk_pdl::WAIT_BEFORE_LOAD ? 2 : 0;
     void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n,
                     (void *)&fence_mask, (void *)&wait_mode};
+    if (xshift) c->shifted_launches++;
     return launch_stream_kernel(c, k, grid, threads, args, op, plan);
 }
 
@@ -1704,6 +1786,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         int threads = cfg.threads > 0 ? cfg.threads : 256;
         const T *ptrs[2] = {x, y};
         i64 head = 0;
+        int xshift = 0;
         const void *k;
         if (rev) {
             resolve_alignment_rev<T>(&variant, &head, &x, 1, &y, 1, nl);
@@ -1716,8 +1799,21 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
                 if (mis.threads > 0) threads = mis.threads;
             }
             k = reduce_kernel_ptr<Op>(variant);
+            if constexpr (Op::TWO) {
+                const LaunchCfg &sh = c->cfg[R_REDSHIFTED];
+                if (Y && variant_vec<T>(variant) == 1 && kVariantVec[sh.variant] == 4) {     // x and y misaligned differently
+                    i64 h = 0;
+                    const int shift = shifted_layout<T>(x, &y, 1, nl, &h);
+                    // the Double instance of the default shape runs unroll 2: ptxas cannot fit unroll 4 of 8-byte elements
+                    // plus the shifted lanes into 64 registers (variant 1 = 16-byte packs x 2)
+                    const int sv = (sizeof(T) == 8 && sh.variant == kDefaultCfg[R_REDSHIFTED].variant) ? 1 : sh.variant;
+                    const void *ks = shift ? reduce_kernel_ptr_shifted<Op>(variant_unroll(sv), shift) : nullptr;
+                    if (ks) { k = ks; head = h; variant = sv; pcfg = &sh; threads = std::min(sh.threads > 0 ? sh.threads : 256, lbk::kShiftThreads); xshift = shift; }
+                }
+            }
         }
-        const i64 npack = (nl - head) / variant_vec<T>(variant);
+        const i64 npack = xshift ? std::max<i64>(0, (nl - head - (variant_vec<T>(variant) - xshift)) / variant_vec<T>(variant))
+                                 : (nl - head) / variant_vec<T>(variant);
         const i64 per_tile = (i64)variant_unroll(variant) * threads;
         int grid;
         int s = grid_for(c, k, *pcfg, threads, (npack + per_tile - 1) / per_tile, &grid, kMaxGrid, pcfg->pinned ? 0 : per_tile * variant_vec<T>(variant) * (i64)sizeof(T));
@@ -1733,6 +1829,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         int late_trigger = plan.late ? 1 : 0, wait_first = plan.mode == lbk_pdl::WAIT_BEFORE_LOAD ? 1 : 0;
         void *args[] = {(void *)&x, (void *)&y, (void *)&head, (void *)&nn, (void *)&ib, (void *)&c->partials, (void *)&c->ticket,
                         (void *)&fa, (void *)&late_trigger, (void *)&wait_first};
+        if (xshift) c->shifted_launches++;
         s = launch_stream_kernel(c, k, grid, threads, args, op, plan);
         if (s) return s;
         // with the NCCL transport the all-gather and the finish kernel follow on the stream: no chain through them

@@ -70,6 +70,12 @@ class Context:
         _ffi.check(_ffi.lib().lbk_pdl_count(self.handle, C.byref(v)), self.handle)
         return v.value
 
+    def shifted_count(self) -> int:
+        """Launches that read a differently-misaligned x through aligned packs + a lane shift (lbk_shifted_count)."""
+        v = C.c_int64()
+        _ffi.check(_ffi.lib().lbk_shifted_count(self.handle, C.byref(v)), self.handle)
+        return v.value
+
     def set_pdl(self, enabled: bool) -> None:
         _ffi.check(_ffi.lib().lbk_set_pdl(self.handle, int(enabled)), self.handle)
 

@@ -59,3 +59,24 @@ def test_no_tensor_cores_no_tma(sass):
     for name, ins in kernels.items():
         hit = [i for i in ins if banned.match(i)]
         assert not hit, (name, hit[:3])
+
+
+def test_default_shifted_load_shapes_do_not_spill():
+    """The shifted-load kernels (lbk_kernels.cuh, shift_pack) have no local arrays, so a stack frame means register
+    spills -- which cost these shapes 4-20 points of bandwidth (profiles/r02_misaligned.md).  The shapes the library
+    picks by default (maps: 16-byte packs x 4; dot / sdsdot: x 4 for Float, x 2 for Double) must have none."""
+    if not shutil.which("cuobjdump") or not os.path.exists(LIB):
+        pytest.skip("cuobjdump or liblbk.so not available")
+    out = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for m in re.finditer(r"Function (\S+):\s*\n\s*(.*)", out):
+        name, usage = m.group(1), m.group(2)
+        k = re.search(r"(map|reduce)_unit_kernelINS_\d+(\w+?)(I[fd]E)?ELi(\d)ELi(\d)ELi\dELb0ELi([123])E", name)
+        if not k:
+            continue
+        kind, vec, unroll = k.group(1), int(k.group(4)), int(k.group(5))
+        default = unroll == 4 if (kind == "map" or vec == 4) else unroll == 2
+        if default:
+            seen += 1
+            assert re.search(r"STACK:0\b", usage), (name, usage)
+    assert seen >= 3 * 4 + 3 + 1 + 3          # axpy / copy / scal x (3 Float shifts + 1 Double), dot Float x 3 + Double, sdsdot x 3
