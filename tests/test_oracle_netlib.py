@@ -1,10 +1,14 @@
 """The reference's own differential property, replayed on CPU.
 
 test/Main.hs:28-52 asserts `native == netlib BLAS 3.7.0` bit for bit over random inputs.  Here
-`native` is the C restatement of the Haskell code (oracle/lblas_oracle.c) and `netlib` the C
-restatement of the published Fortran (oracle/netlib_l1.c); domains follow Main.hs row by row.
+`netlib` is the C restatement of the published Fortran (oracle/netlib_l1.c) and `native` is, in turn,
+  * "restatement": the C restatement of the Haskell code (oracle/lblas_oracle.c), and
+  * "reference-source": the reference's Haskell SOURCE itself, evaluated by oracle/hs_eval.py (build container
+    only: /root/reference does not exist on the GPU box; fewer cases, it is an interpreter);
+domains follow Main.hs row by row.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -12,6 +16,26 @@ import pytest
 from tests.gen import gen_nice_float, nice_scalar, span
 
 CASES = 300
+
+
+@pytest.fixture(scope="module", params=["restatement", "reference-source"])
+def oracle(request):
+    """shadows conftest's fixture: every property below runs once per `native`"""
+    global CASES
+    from oracle import oracle as o
+    o.build()
+    if request.param == "restatement":
+        yield o
+        return
+    from oracle import hs_eval
+    if not os.path.isdir(hs_eval.REFERENCE_SRC):
+        pytest.skip("/root/reference is only present in the build container")
+    from tests.ref_adapter import ReferenceAsOracle
+    saved, CASES = CASES, 120
+    try:
+        yield ReferenceAsOracle()
+    finally:
+        CASES = saved
 DTYPES = [np.float32, np.float64]            # the reference runs every property for Float and Double (Main.hs:28-52)
 
 
@@ -46,7 +70,7 @@ def nl(oracle, dtype, name):
 
 def test_readme_worked_example(oracle):
     # README.md:57-59: sdot 3 [1,2,3] 1 [4,5,6] 1 == 32
-    assert oracle.sdot(3, [1, 2, 3], 1, [4, 5, 6], 1) == np.float32(32)
+    assert oracle.sdot(3, np.array([1, 2, 3], np.float32), 1, np.array([4, 5, 6], np.float32), 1) == np.float32(32)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
