@@ -131,6 +131,39 @@ def time_cpu(n: int, steps: int, warmup: int):
     return dt, STEP_BYTES_PER_ELEM * n / dt / 1e9
 
 
+def time_cpu_all_cores(log2n_per_thread: int = 24, steps: int = 2):
+    """The same CPU step on EVERY logical CPU at once, one independent copy per thread on its own vectors: what a caller of the
+    (single-threaded, pure) reference could get by splitting the work by hand.  Reported beside the one-core figure, never as
+    `value`: the reference itself uses one core."""
+    import threading
+    T = os.cpu_count() or 1
+    n = 1 << log2n_per_thread
+    steps_fns = [cpu_step_factory(n) for _ in range(T)]
+    for f in steps_fns[:1]:
+        f()
+    start = threading.Barrier(T + 1)
+    done = threading.Barrier(T + 1)
+
+    def work(f):
+        f()                                 # warm: touch this thread's pages
+        start.wait()
+        for _ in range(steps):
+            f()                             # ctypes releases the GIL for the duration of each call
+        done.wait()
+    ths = [threading.Thread(target=work, args=(f,)) for f in steps_fns]
+    for t in ths:
+        t.start()
+    start.wait()
+    t0 = time.perf_counter()
+    done.wait()
+    dt = time.perf_counter() - t0
+    for t in ths:
+        t.join()
+    return {"value": round(STEP_BYTES_PER_ELEM * n * T * steps / dt / 1e9, 2), "unit": "GB/s", "threads": T,
+            "sample": f"one copy of the step per logical CPU, 2^{log2n_per_thread} elements each, {steps} steps",
+            "note": "hand-split over all cores; the reference is single-threaded, so `value` stays the one-core figure"}
+
+
 def cpu_info():
     model = "unknown"
     try:
@@ -167,7 +200,8 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
+                         "all_cores": time_cpu_all_cores()},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "reference_toolchain": tools,
     }
