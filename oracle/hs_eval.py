@@ -154,6 +154,12 @@ def lex(src: str):
                 j += 1
             emit("op", src[i:j], j - i)
             continue
+        if c == "'":                                     # a character literal (an identifier's primes were consumed above)
+            m = re.compile(r"'(?:\\[^']+|\\'|[^'\\])'").match(src, i)
+            if not m:
+                raise HsError(f"lex: stray quote at {line}:{col}")
+            emit("char", m.group(0)[1:-1], len(m.group(0)))
+            continue
         if c == '"':
             j = i + 1
             while src[j] != '"':
@@ -171,39 +177,58 @@ def lex(src: str):
 def layout(toks):
     out = []
     ctx = []            # implicit blocks: dict(col, depth, kind); explicit braces only count as bracket depth
-    lets = []           # the blocks of the `let`s whose `in` has not been seen yet
+    pend = []           # `if` / `case` keywords whose `else` / `of` has not been seen: [keyword, len(ctx) then, bracket depth]
     depth = 0
     expect = None
 
     def close():
         b = ctx.pop()
         out.append(Tok("special", "}", out[-1].line if out else 0, 0, extra="virtual"))
+        for q in pend:
+            q[1] = min(q[1], len(ctx))
         return b
 
     for t in toks:
+        closed_let = False
         if expect is not None:
             kind, expect = expect, None
             if t.kind == "special" and t.val == "{":
                 raise HsError("explicit layout braces are outside the subset")
             out.append(Tok("special", "{", t.line, t.col, extra="virtual"))
-            ctx.append({"col": t.col, "depth": depth, "kind": kind})
-            if kind == "let":
-                lets.append(ctx[-1])
-        elif t.first:
-            while ctx and (t.col < ctx[-1]["col"] or (t.kind == "kw" and t.val == "where" and ctx[-1]["kind"] == "of"
-                                                      and t.col == ctx[-1]["col"])):      # parse-error(t): no alternative starts with `where`
-                close()
+            if ctx and t.first and t.col <= ctx[-1]["col"]:          # an empty block: `where` followed by a less indented line
+                out.append(Tok("special", "}", t.line, t.col, extra="virtual"))
+            else:
+                ctx.append({"col": t.col, "depth": depth, "kind": kind})
+                t = Tok(t.kind, t.val, t.line, t.col, False, t.extra)      # the block's first token: no `;` before it
+        if t.first:
+            while ctx and (t.col < ctx[-1]["col"] or (t.kind == "kw" and t.val == "where" and ctx[-1]["kind"] in ("of", "do")
+                                                      and t.col == ctx[-1]["col"])):      # parse-error(t): no alternative / statement starts with `where`
+                closed_let = closed_let or close()["kind"] == "let"
             if ctx and t.col == ctx[-1]["col"]:
                 out.append(Tok("special", ";", t.line, t.col, extra="virtual"))
-        if t.kind == "kw" and t.val == "in":
-            # ends its `let`: if that block is still open (not closed by indentation), close it and what it holds
-            if not lets:
-                raise HsError(f"`in` without `let` at {t.line}:{t.col}")
-            blk = lets.pop()
-            if any(b is blk for b in ctx):
-                while ctx[-1] is not blk:
+        if t.kind == "kw" and t.val == "in" and not closed_let:
+            # parse-error(t): ends the innermost `let` block that is still open inside the current brackets (a `let` whose
+            # block the indentation of this very token has just closed needs nothing more; `let` statements of a
+            # do block never meet an `in`)
+            k = len(ctx) - 1
+            while k >= 0 and ctx[k]["depth"] == depth and ctx[k]["kind"] != "let":
+                k -= 1
+            if k >= 0 and ctx[k]["depth"] == depth and ctx[k]["kind"] == "let":
+                while len(ctx) > k:
                     close()
-                close()
+        if t.kind == "kw" and t.val in ("if", "case"):
+            pend.append([t.val, len(ctx), depth])
+        elif t.kind == "kw" and t.val in ("then", "else", "of"):
+            # parse-error(t): implicit blocks opened since the matching `if` / `case` (a one-line `do` inside a branch, a
+            # `case` inside a scrutinee) end here
+            want = "case" if t.val == "of" else "if"
+            while pend and (pend[-1][0] != want or pend[-1][2] > depth):
+                pend.pop()
+            if pend:
+                while len(ctx) > pend[-1][1] and ctx[-1]["depth"] == depth:
+                    close()
+                if t.val != "then":
+                    pend.pop()
         if t.kind == "special" and t.val in ")]":
             while ctx and ctx[-1]["depth"] == depth:
                 close()
