@@ -737,7 +737,7 @@ def run_ours(args) -> None:
 
     if rank == 0:
         saxpy_gbs_gpu = BYTES_PER_ELEM["saxpy"] * n / saxpy_ms_in_step / 1e6
-        roofline = {"bound": "hbm", "kernel": f"lbk::{ncu_traffic('saxpy_kernel') or 'map_unit_kernel<AxpyF<float>, 8, 2, 6, 0>'} (saxpy, the largest share of the step)",
+        roofline = {"bound": "hbm", "kernel": f"lbk::{ncu_traffic('saxpy_kernel') or 'map_unit_kernel<AxpyF<float>, 8, 2, 6, 0, 0>'} (saxpy, the largest share of the step)",
                     "achieved": round(saxpy_gbs_gpu, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": round(saxpy_gbs_gpu / peak, 4), "frac_of_nominal_8TBs": round(saxpy_gbs_gpu / NOMINAL_HBM_GBS, 4),
                     "algorithmic_bytes_per_launch": BYTES_PER_ELEM["saxpy"] * n, "launch_ms": round(saxpy_ms_in_step, 4),
