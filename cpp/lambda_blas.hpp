@@ -49,6 +49,28 @@ class Context {
     lbk_ctx *c_ = nullptr;
 };
 
+// A recorded sequence of calls (lbk_capture_begin / lbk_capture_end): everything the callable enqueues on the context is
+// recorded into a CUDA graph instead of running; launch() replays it with one host call.  Only calls that neither allocate
+// nor return a scalar to the host can be recorded (the in-place / *_oop routines of the C ABI, the *_async reductions).
+class Graph {
+  public:
+    template <class F> Graph(const Context &ctx, F &&record) : ctx_(&ctx)
+    {
+        ctx.check(lbk_capture_begin(ctx.get()));
+        try { record(); } catch (...) { lbk_graph *g = nullptr; if (!lbk_capture_end(ctx.get(), &g)) lbk_graph_destroy(g); throw; }
+        ctx.check(lbk_capture_end(ctx.get(), &g_));
+    }
+    ~Graph() { lbk_graph_destroy(g_); }
+    Graph(const Graph &) = delete;
+    Graph &operator=(const Graph &) = delete;
+    void launch() const { ctx_->check(lbk_graph_launch(g_)); }
+    int64_t kernels() const { int64_t k = 0; ctx_->check(lbk_graph_kernels(g_, &k)); return k; }
+
+  private:
+    const Context *ctx_;
+    lbk_graph *g_ = nullptr;
+};
+
 // The entry points of one instance (Float: lbk_s*, Double: lbk_d*) -- what the reference's type class
 // resolves for `dot :: (Num a, Storable a) => ...` (Single.hs:73) at Float and at Double.
 template <class T> struct Abi;

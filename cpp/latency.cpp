@@ -77,6 +77,34 @@ int main()
             }
         }
         ctx.check(lbk_set_pdl(ctx.get(), 1));
+        // The same chains recorded ONCE into a CUDA graph (lambda_blas::Graph = lbk_capture_begin / lbk_capture_end) and
+        // replayed: one host call per replay, the GPU's node-to-node latency per kernel.
+        std::printf("graph_chain,n,kernels,eager_us_per_call,replay_us_per_call,host_us_per_replay\n");
+        for (long long n : {1LL << 10, 1LL << 14, 1LL << 16, 1LL << 18, 1LL << 20}) {
+            const int K = 200, R = 20;
+            DVector bx(ctx, n), by(ctx, n);
+            ctx.check(lbk_vec_fill(bx.get(), 0.25)); ctx.check(lbk_vec_fill(by.get(), 0.5));
+            auto both = [&](const char *name, int per, const std::function<void()> &f) {
+                for (int i = 0; i < 20; ++i) f();
+                ctx.sync();
+                auto t0 = clk::now();
+                for (int i = 0; i < K; ++i) f();
+                ctx.sync();
+                const double eager = std::chrono::duration<double, std::micro>(clk::now() - t0).count() / (K * per);
+                Graph g(ctx, [&] { for (int i = 0; i < K; ++i) f(); });
+                for (int i = 0; i < 3; ++i) g.launch();
+                ctx.sync();
+                t0 = clk::now();
+                for (int i = 0; i < R; ++i) g.launch();
+                const double host = std::chrono::duration<double, std::micro>(clk::now() - t0).count() / R;
+                ctx.sync();
+                const double replay = std::chrono::duration<double, std::micro>(clk::now() - t0).count() / ((double)R * (double)g.kernels());
+                std::printf("%s,%lld,%lld,%.2f,%.2f,%.1f\n", name, n, (long long)g.kernels(), eager, replay, host);
+            };
+            both("saxpy y+=a*x (in place; dependent)", 1, [&] { ctx.check(lbk_saxpy(ctx.get(), n, 1e-3f, bx.get(), 1, by.get(), 1)); });
+            both("sscal then sdot_async", 2, [&] { ctx.check(lbk_sscal(ctx.get(), n, 1.0f, bx.get(), 1));
+                                                   ctx.check(lbk_sdot_async(ctx.get(), n, bx.get(), 1, by.get(), 1, res.get())); });
+        }
         return 0;
     } catch (const Error &e) {
         std::fprintf(stderr, "lbk error %d: %s\n", e.status, e.what());

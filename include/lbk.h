@@ -125,6 +125,22 @@ int lbk_pdl_count(lbk_ctx *ctx, int64_t *launches);
  * "redshifted" of lbk_set_launch choose their shape (a one-element variant turns the path off). */
 int lbk_shifted_count(lbk_ctx *ctx, int64_t *launches);
 
+/* CUDA graphs: record a fixed sequence of calls once, replay it with one host call.  The reference's own benchmark
+ * (test/Bench.hs:17-132) lives at n <= 30 000, where a GPU call is all launch latency; a captured chain runs at the GPU's
+ * node-to-node latency instead (profiles/r02_graph_latency.md).  Between lbk_capture_begin and lbk_capture_end every call on the
+ * context is RECORDED, not executed: the in-place and *_oop elementwise routines, the *_async reductions, lbk_vec_fill*,
+ * lbk_vec_upload_async / lbk_vec_download_async (pinned buffers).  Calls that cannot be recorded return
+ * LBK_ERR_UNSUPPORTED and leave the capture intact: anything that allocates (the pure host mirrors, lbk_vec_alloc*,
+ * lbk_vec_clone), reductions that return their scalar to the host, synchronous transfers, lbk_sync, events, reductions
+ * over sharded vectors.  lbk_vec_free is allowed (the buffer is released when the capture ends).  Single-device contexts only.
+ * A replay repeats the recorded calls on the recorded addresses with the recorded scalars; it is enqueue-only. */
+typedef struct lbk_graph lbk_graph;
+int lbk_capture_begin(lbk_ctx *ctx);
+int lbk_capture_end(lbk_ctx *ctx, lbk_graph **graph);
+int lbk_graph_launch(lbk_graph *graph);
+int lbk_graph_kernels(const lbk_graph *graph, int64_t *kernels);   /* kernels one replay runs (added to lbk_launch_count per launch) */
+int lbk_graph_destroy(lbk_graph *graph);                          /* safe after lbk_shutdown, like lbk_vec_free */
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink -------------------------------------- */
 /* Rank 0 makes an id and hands the 128 bytes to every rank (any transport; the host layer uses
  * torch.distributed); then every rank calls lbk_comm_init.  After that, vectors made with

@@ -51,6 +51,11 @@ PROTOTYPES = {
     "lbk_set_pdl": (_int, [_vp, _int]),
     "lbk_pdl_count": (_int, [_vp, _pi64]),
     "lbk_shifted_count": (_int, [_vp, _pi64]),
+    "lbk_capture_begin": (_int, [_vp]),
+    "lbk_capture_end": (_int, [_vp, _pvp]),
+    "lbk_graph_launch": (_int, [_vp]),
+    "lbk_graph_kernels": (_int, [_vp, _pi64]),
+    "lbk_graph_destroy": (_int, [_vp]),
     "lbk_comm_unique_id": (_int, [C.c_char_p]),
     "lbk_comm_init": (_int, [_vp, _int, _int, C.c_char_p]),
     "lbk_comm_info": (_int, [_vp, _pint, _pint]),

@@ -138,6 +138,11 @@ struct lbk_ctx {
     int64_t launches = 0;
     int64_t pdl_launches = 0;
     int64_t shifted_launches = 0;     // unit-stride kernels that read x through shifted loads (lbk_shifted_count)
+    // stream capture (lbk_capture_begin .. lbk_capture_end): kernels and asynchronous copies are recorded into a CUDA
+    // graph instead of running; whatever cannot be recorded is refused, and buffers released meanwhile are freed at the end
+    bool capturing = false;
+    int64_t capture_launches0 = 0;
+    std::vector<void *> deferred_free;
     std::string err;
 };
 
@@ -158,6 +163,7 @@ struct lbk_vec {
 static inline int esz(int dtype) { return dtype ? 8 : 4; }
 
 struct lbk_event { lbk_ctx *ctx; cudaEvent_t ev; std::vector<lbk_event *> parts; };
+struct lbk_graph { lbk_ctx *ctx; cudaGraph_t graph; cudaGraphExec_t exec; int64_t kernels; };
 
 static thread_local std::string g_err;   // failures before a context exists
 
@@ -249,6 +255,9 @@ struct DevGuard {
 static inline bool is_multi(const lbk_ctx *c) { return c && !c->subs.empty(); }
 #define LIVE(ctx, who)                                                                             \
     if ((ctx)->closed) return fail((ctx), LBK_ERR_ARG, std::string(who) + ": the context has been shut down")
+
+#define NOT_CAPTURING(ctx, who)                                                                    \
+    if ((ctx)->capturing) return fail((ctx), LBK_ERR_UNSUPPORTED, std::string(who) + ": not while the context is capturing a graph (lbk_capture_begin)")
 
 static inline i64 first_index(i64 n, i64 inc) { return inc > 0 ? 0 : (1 - n) * inc; }   // Single.hs:91-96
 
@@ -572,6 +581,7 @@ extern "C" int lbk_sync(lbk_ctx *c)
     if (!c) return fail(nullptr, LBK_ERR_ARG, "lbk_sync: null context");
     LIVE(c, "lbk_sync");
     if (is_multi(c)) return all_ranks(c, [](lbk_ctx *s, int) { return lbk_sync(s); });
+    NOT_CAPTURING(c, "lbk_sync");
     ON_DEVICE(c);
     CU(c, cudaStreamSynchronize(c->stream));
     return check_exchange_error(c);
@@ -638,6 +648,89 @@ extern "C" int lbk_pdl_count(lbk_ctx *c, int64_t *launches)
     if (!c || !launches) return fail(c, LBK_ERR_ARG, "lbk_pdl_count: null argument");
     *launches = c->pdl_launches;
     for (lbk_ctx *s : c->subs) *launches += s->pdl_launches;
+    return LBK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA graphs.  A fixed sequence of small calls (the regime of the reference's own benchmark, test/Bench.hs: n <= 30 000)
+// is bound by launch latency; recorded once into a graph it replays with one host call and the GPU's own node-to-node
+// latency (profiles/r02_graph_latency.md).  Between begin and end every call on the context is RECORDED, not run: kernels (with
+// their programmatic-dependent-launch edges -- the hazard planner works as usual, capture starts and ends a chain) and
+// asynchronous copies.  Whatever cannot be recorded is refused with LBK_ERR_UNSUPPORTED before anything reaches the stream:
+// allocation (pure forms: use the in-place / *_oop forms on vectors that exist), scalars returned to the host (use the _async
+// reductions), synchronous transfers, lbk_sync, events, sharded reductions.  A replay repeats the recorded calls on the
+// recorded addresses with the recorded scalars.
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbk_capture_begin(lbk_ctx *c)
+{
+    if (!c) return fail(c, LBK_ERR_ARG, "lbk_capture_begin: null context");
+    LIVE(c, "lbk_capture_begin");
+    if (is_multi(c) || c->parent) return fail(c, LBK_ERR_UNSUPPORTED, "lbk_capture_begin: single-device contexts only");
+    NOT_CAPTURING(c, "lbk_capture_begin");
+    ON_DEVICE(c);
+    lbk_pdl::interrupt(c->pdl);
+    // relaxed: the library itself keeps everything it cannot record off the capturing stream, and a host language's finalisers
+    // (cudaEventDestroy, cudaFreeHost, another graph's destruction ...) may run on this thread at any time
+    CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
+    c->capture_launches0 = c->launches;
+    return LBK_OK;
+}
+
+extern "C" int lbk_capture_end(lbk_ctx *c, lbk_graph **out)
+{
+    if (!c || !out) return fail(c, LBK_ERR_ARG, "lbk_capture_end: null argument");
+    if (!c->capturing) return fail(c, LBK_ERR_ARG, "lbk_capture_end: the context is not capturing");
+    ON_DEVICE(c);
+    c->capturing = false;
+    lbk_pdl::interrupt(c->pdl);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    for (void *p : c->deferred_free) cudaFreeAsync(p, c->stream);      // finalisers that ran during the capture
+    c->deferred_free.clear();
+    if (e != cudaSuccess || !g) { cudaGetLastError(); return fail(c, LBK_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); }
+    cudaGraphExec_t x = nullptr;
+    e = cudaGraphInstantiate(&x, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); cudaGetLastError(); return fail(c, LBK_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    lbk_graph *h = new (std::nothrow) lbk_graph{c, g, x, c->launches - c->capture_launches0};
+    if (!h) { cudaGraphExecDestroy(x); cudaGraphDestroy(g); return fail(c, LBK_ERR_NOMEM, "out of host memory"); }
+    c->launches = c->capture_launches0;        // recorded, not launched
+    ctx_ref(c);
+    *out = h;
+    return LBK_OK;
+}
+
+extern "C" int lbk_graph_launch(lbk_graph *g)
+{
+    if (!g) return fail(nullptr, LBK_ERR_ARG, "lbk_graph_launch: null graph");
+    lbk_ctx *c = g->ctx;
+    LIVE(c, "lbk_graph_launch");
+    NOT_CAPTURING(c, "lbk_graph_launch");
+    ON_DEVICE(c);
+    lbk_pdl::interrupt(c->pdl);                // the graph is an ordinary stream operation: what follows is launched the ordinary way
+    CU(c, cudaGraphLaunch(g->exec, c->stream));
+    c->launches += g->kernels;
+    return LBK_OK;
+}
+
+extern "C" int lbk_graph_kernels(const lbk_graph *g, int64_t *kernels)
+{
+    if (!g || !kernels) return fail(nullptr, LBK_ERR_ARG, "lbk_graph_kernels: null argument");
+    *kernels = g->kernels;
+    return LBK_OK;
+}
+
+extern "C" int lbk_graph_destroy(lbk_graph *g)
+{
+    if (!g) return LBK_OK;
+    lbk_ctx *c = g->ctx;
+    {
+        DevGuard guard(c->device);
+        cudaGraphExecDestroy(g->exec);         // a launch still in flight keeps what it needs (CUDA defers the release)
+        cudaGraphDestroy(g->graph);
+    }
+    delete g;
+    ctx_unref(c);
     return LBK_OK;
 }
 
@@ -790,6 +883,7 @@ static int make_vec(lbk_ctx *c, void *ptr, i64 len, i64 glen, i64 off, bool owne
 static int alloc_common(lbk_ctx *c, const char *who, i64 len, i64 glen, i64 off, bool sharded, int dtype, lbk_vec **out)
 {
     LIVE(c, who);
+    if (len > 0) NOT_CAPTURING(c, who);        // allocate before capturing: a replay reuses the recorded addresses
     ON_DEVICE(c);
     void *p = nullptr;
     if (len > 0) {
@@ -916,7 +1010,8 @@ extern "C" int lbk_vec_free(lbk_vec *v)
         cudaStreamSynchronize(c->stream);
         cudaFree(v->ptr);
 #else
-        cudaFreeAsync(v->ptr, c->stream);
+        if (c->capturing) c->deferred_free.push_back(v->ptr);      // a finaliser ran inside a capture: released at its end
+        else cudaFreeAsync(v->ptr, c->stream);
 #endif
     }
     delete v;
@@ -1045,6 +1140,7 @@ static int staged_transfer(lbk_ctx *c, char *dev, char *host, size_t bytes, bool
 static int sync_transfer_one(lbk_vec *v, char *host, int64_t len, bool up)
 {
     lbk_ctx *c = v->ctx;
+    NOT_CAPTURING(c, up ? "lbk_vec_upload" : "lbk_vec_download");
     const size_t bytes = (size_t)esz(v->dtype) * (size_t)len;
     int s;
     if (bytes >= kStageMinBytes && is_pageable(host)) s = staged_transfer(c, v->ptr, host, bytes, up);
@@ -1184,6 +1280,7 @@ extern "C" int lbk_event_record(lbk_event *e)
     if (!e) return fail(nullptr, LBK_ERR_ARG, "lbk_event_record: null event");
     LIVE(e->ctx, "lbk_event_record");
     if (!e->parts.empty()) return all_ranks(e->ctx, [&](lbk_ctx *, int r) { return lbk_event_record(e->parts[r]); });
+    NOT_CAPTURING(e->ctx, "lbk_event_record");
     ON_DEVICE(e->ctx);
     lbk_pdl::interrupt(e->ctx->pdl);
     CU(e->ctx, cudaEventRecord(e->ev, e->ctx->stream));
@@ -1198,6 +1295,7 @@ extern "C" int lbk_wait_event(lbk_ctx *c, lbk_event *e)
     if (is_multi(c) != !e->parts.empty() || (is_multi(c) && c->subs.size() != e->parts.size()))
         return fail(c, LBK_ERR_ARG, "lbk_wait_event: context and event must both be single-device, or multi-device over the same ranks");
     if (is_multi(c)) return all_ranks(c, [&](lbk_ctx *s, int r) { return lbk_wait_event(s, e->parts[r]); });
+    NOT_CAPTURING(c, "lbk_wait_event");
     ON_DEVICE(c);
     lbk_pdl::interrupt(c->pdl);
     CU(c, cudaStreamWaitEvent(c->stream, e->ev, 0));
@@ -1746,6 +1844,9 @@ template <class Op>
 static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &X, const Operand *Y, double sb, void *out)
 {
     using T = typename Op::Scalar;
+    if (c->capturing && (out == c->result_dev || (c->nranks > 1 && X.v->sharded)))
+        return fail(c, LBK_ERR_UNSUPPORTED, "a reduction that returns its scalar to the host, or exchanges records between GPUs, cannot be captured: "
+                                            "use the _async form on unsharded vectors (lbk_capture_begin)");
     ON_DEVICE(c);
     const bool exchange = c->nranks > 1 && X.v->sharded;
     const bool fused = exchange && c->fused_exchange;
@@ -1879,6 +1980,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
 template <class T>
 static int store_value(lbk_ctx *c, void *out, T v)
 {
+    if (out == c->result_dev) NOT_CAPTURING(c, "a reduction that returns its scalar to the host");
     ON_DEVICE(c);
     lbk_pdl::interrupt(c->pdl);
     unsigned *flag = nullptr;

@@ -139,6 +139,12 @@ class Context:
             _ffi.check(_ffi.lib().lbk_vec_upload(v.handle, a.ctypes.data_as(C.c_void_p), a.size), self.handle)
         return v
 
+    # ---- CUDA graphs ----
+    def capture(self) -> "_Capture":
+        """`with ctx.capture() as cap: ...calls...` records the calls instead of running them; `cap.graph.launch()` replays them
+        (lbk_capture_begin / lbk_capture_end: in-place and *_oop routines, *_async reductions, asynchronous copies)."""
+        return _Capture(self)
+
     # ---- events ----
     def event(self) -> "Event":
         return Event(self)
@@ -205,6 +211,50 @@ class MultiContext(Context):
         if a.size:
             _ffi.check(_ffi.lib().lbk_vec_upload(v.handle, a.ctypes.data_as(C.c_void_p), a.size), self.handle)
         return v
+
+
+class Graph:
+    """A recorded sequence of calls (lbk_graph): `launch()` enqueues one replay on the context's stream."""
+
+    def __init__(self, ctx: Context, handle):
+        self._h, self.ctx = handle, ctx
+
+    def launch(self) -> "Graph":
+        _ffi.check(_ffi.lib().lbk_graph_launch(self._h), self.ctx.handle)
+        return self
+
+    @property
+    def kernels(self) -> int:
+        v = C.c_int64()
+        _ffi.check(_ffi.lib().lbk_graph_kernels(self._h, C.byref(v)), self.ctx.handle)
+        return v.value
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _ffi.lib().lbk_graph_destroy(self._h)
+        except Exception:
+            pass
+        self._h = None
+
+
+class _Capture:
+    def __init__(self, ctx: Context):
+        self.ctx, self.graph = ctx, None
+
+    def __enter__(self) -> "_Capture":
+        _ffi.check(_ffi.lib().lbk_capture_begin(self.ctx.handle), self.ctx.handle)
+        return self
+
+    def __exit__(self, et, ev, tb):
+        h = C.c_void_p()
+        st = _ffi.lib().lbk_capture_end(self.ctx.handle, C.byref(h))
+        if et is None:
+            _ffi.check(st, self.ctx.handle)
+            self.graph = Graph(self.ctx, h)
+        elif st == 0:
+            _ffi.lib().lbk_graph_destroy(h)       # the body raised: drop what was recorded
+        return False
 
 
 class Event:
