@@ -34,6 +34,8 @@ module Numerical.BLAS.Device
       -- * One host thread, many GPUs: sharded vectors (lbk_init_multi)
     , withContextMulti, newContextMulti, toDeviceSharded, allocSharded, setMultiThreads, setFusedExchange
     , setExchangeTimeout
+      -- * Recorded chains of calls (CUDA graphs)
+    , Graph, capture, launchGraph
       -- * Asynchronous and pinned transfers
     , withRegistered, toDeviceAsync, fromDeviceAsync
       -- * Enqueue-only reductions (the result lands in a device vector)
@@ -51,7 +53,7 @@ module Numerical.BLAS.Device
     , LbkError(..)
     ) where
 
-import Control.Exception (bracket, bracket_, throwIO)
+import Control.Exception (bracket, bracket_, onException, throwIO)
 import Control.Monad (when)
 import Data.Word (Word8)
 import qualified Data.Vector.Storable as V
@@ -85,6 +87,10 @@ foreign import ccall        "lbk_shutdown"    c_shutdown    :: Ptr LbkCtx -> IO 
 foreign import ccall        "lbk_sync"        c_sync        :: Ptr LbkCtx -> IO CInt
 foreign import ccall unsafe "lbk_last_error"  c_last_error  :: Ptr LbkCtx -> IO CString
 foreign import ccall        "&lbk_vec_free"   p_vec_free    :: FunPtr (Ptr () -> IO ())
+foreign import ccall        "lbk_capture_begin" c_capture_begin :: Ptr LbkCtx -> IO CInt
+foreign import ccall        "lbk_capture_end"   c_capture_end   :: Ptr LbkCtx -> Ptr (Ptr LbkGraph) -> IO CInt
+foreign import ccall unsafe "lbk_graph_launch"  c_graph_launch  :: Ptr LbkGraph -> IO CInt
+foreign import ccall        "&lbk_graph_destroy" p_graph_destroy :: FunPtr (Ptr LbkGraph -> IO ())
 
 -- Float instance (s / is prefix)
 foreign import ccall        "lbk_vec_alloc"    s_vec_alloc    :: Ptr LbkCtx -> Int -> Ptr (V Float) -> IO CInt
@@ -256,6 +262,29 @@ setFusedExchange ctx on = c_set_fused_exchange (ctxPtr ctx) (if on then 1 else 0
 -- | Milliseconds a sharded reduction waits for its peers' records before it fails with @LBK_ERR_NCCL@.
 setExchangeTimeout :: Context -> Int -> IO ()
 setExchangeTimeout ctx ms = c_set_exchange_timeout (ctxPtr ctx) ms >>= check ctx
+
+-- | A recorded chain of calls (@lbk_graph@).  Opaque; the finaliser is @lbk_graph_destroy@.
+data LbkGraph
+data Graph = Graph !Context !(ForeignPtr LbkGraph)
+
+-- | @capture ctx act@ RECORDS what @act@ enqueues on @ctx@ instead of running it (@lbk_capture_begin@ /
+-- @lbk_capture_end@): the in-place forms ('axpy_', 'scal_', ...), the enqueue-only reductions ('dotAsync', ...) and the
+-- asynchronous transfers.  Whatever cannot be recorded -- the pure forms (they allocate), scalars returned to the
+-- host, 'sync' -- throws 'LbkError' with @LBK_ERR_UNSUPPORTED@ and leaves the recording intact.  'launchGraph' replays
+-- the chain with one host call: the regime of the reference's own benchmark (test/Bench.hs:113, n <= 30 000) is
+-- bound by launch latency, not by bandwidth.
+capture :: Context -> IO () -> IO Graph
+capture ctx act = alloca $ \ pg -> do
+    c_capture_begin (ctxPtr ctx) >>= check ctx
+    act `onException` c_capture_end (ctxPtr ctx) pg
+    c_capture_end (ctxPtr ctx) pg >>= check ctx
+    g <- peek pg
+    fp <- newForeignPtr p_graph_destroy g
+    return (Graph ctx fp)
+
+-- | One replay of a recorded chain, enqueue-only (@lbk_graph_launch@).
+launchGraph :: Graph -> IO ()
+launchGraph (Graph ctx fp) = withForeignPtr fp $ \ g -> c_graph_launch g >>= check ctx
 
 adopt :: Context -> Int -> Layout -> V a -> IO (DVector a)
 adopt ctx n lay p = do fp <- newForeignPtr (castFunPtr p_vec_free) p

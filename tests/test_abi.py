@@ -134,7 +134,7 @@ def test_haskell_shim_binds_declared_symbols_with_matching_arity():
         if addr:
             continue                                  # an address import (the finaliser), not a call
         nargs = len(re.split(r"\s->\s", ty)) - 1      # every "->" outside parentheses separates an argument
-        assert "(" not in ty.replace("Ptr (V Float)", "").replace("Ptr (V Double)", "").replace("Ptr (Ptr LbkCtx)", ""), ty
+        assert "(" not in ty.replace("Ptr (V Float)", "").replace("Ptr (V Double)", "").replace("Ptr (Ptr LbkCtx)", "").replace("Ptr (Ptr LbkGraph)", ""), ty
         assert nargs == arity[name], f"{name}: Device.hs passes {nargs} arguments, include/lbk.h takes {arity[name]}"
     names = {n for _, n, _ in imports}
     for r in ("dot", "asum", "nrm2", "axpy", "scal", "copy", "swap", "rot", "rotm", "rotg", "rotmg",
