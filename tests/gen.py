@@ -41,3 +41,17 @@ def gen_unit(rng: np.random.Generator, size, dtype=np.float32) -> np.ndarray:
 def span(n: int, inc: int, extra: int = 0) -> int:
     """Vector length the reference's tests allocate: extra + 1 + (n-1)|inc| (Main.hs:72,122,251)."""
     return extra + 1 + max(n - 1, 0) * abs(inc)
+
+
+def counter_hash(n: int, seed: int, lo: float = -1.0, hi: float = 1.0, dtype=np.float32) -> np.ndarray:
+    """v[i] = lo + (hi-lo) * (top 24 bits of splitmix64(seed * 2^40 + i)) * 2^-24 in `dtype`: the values lbk_vec_fill_hash puts on
+    the device (inputs from a counter-based hash, so that fixtures need only carry the seed)."""
+    R = np.dtype(dtype).type
+    z = np.arange(n, dtype=np.uint64) + (np.uint64(seed) << np.uint64(40))
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(40)).astype(R) * R(2.0 ** -24)
+    return (R(lo) + R(R(hi) - R(lo)) * u).astype(R)
