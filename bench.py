@@ -478,6 +478,11 @@ def run_ours(args) -> None:
     value = STEP_BYTES_PER_ELEM * ng * P / ms_step / 1e6
 
     # ---- every routine alone (KR launches back to back), for the per-routine table ----
+    # These tables are about the HBM roofline of each kernel, so the elementwise kernels walk FORWARDS here (lbk_set_traversal 0):
+    # by default they start at the end of the vectors the previous kernel left in the 126 MB L2, and back-to-back launches of one
+    # routine on the same two vectors would then find ~3 % of their reads cached (`routines_l2_walk` below has those figures).
+    # The timed step above ran with the library's default.
+    ctx.set_traversal(0)
     KR = max(K, 20)
     peak, peak_src = measured_peak()
 
@@ -587,6 +592,14 @@ def run_ours(args) -> None:
         strong["limiter"] = ("at n_global = 2^28 a rank streams 2^28/N elements in tens of microseconds, so the fixed per-call cost shows: the in-kernel "
                              "record exchange (one NVLink round trip, ~3-5 us), the skew between the ranks' independent launches, and the kernel's own "
                              "ramp-up / tail (t0 ~2.5 us on one GPU); at 2^30 the same costs are ~4x smaller relative to the streaming time")
+
+    # ---- the library's default walk (adaptive: from the end the previous kernel left in the L2) on the same back-to-back launches ----
+    ctx.set_traversal(1)
+    walk_order = ["saxpy", "sscal", "scopy", "sswap", "srot"]
+    routines_l2_walk = {r: {"ms": v["ms"], "GBps": v["GBps"], "pct_of_8TBs_per_gpu": v["pct_of_8TBs_per_gpu"]}
+                        for r, v in table(calls, walk_order, ng, lambda r: BYTES_PER_ELEM[r]).items()}
+    routines_l2_walk["note"] = ("lbk_set_traversal(1), the default: every other launch of a back-to-back chain walks the vectors backwards and finds "
+                                "the tail of its predecessor's stream in the L2; algorithmic bytes / time, so part of these bytes never left the L2")
 
     # ---- end to end: host buffers in, host results out, copies inside the timed region ----
     # The caller's x, y live in pinned HOST memory.  Per step: upload x and y in chunks; each chunk's saxpy goes
@@ -761,7 +774,7 @@ def run_ours(args) -> None:
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "pdl_launches": int(pdl_launches), "clocks": clocks, "parity_check": parity["status"] if parity else None, "parity": parity,
             "strong": strong, "single_process": single, "transfers": transfers,
-            "routines": routines, "routines_everyday": routines_everyday, "routines_f64": routines_f64,
+            "routines": routines, "routines_l2_walk": routines_l2_walk, "routines_everyday": routines_everyday, "routines_f64": routines_f64,
             "step_routines_ms": {r: round(v, 4) for r, v in per_routine_in_step.items()},
             "last_snrm2": float(step_check[0]),
         }

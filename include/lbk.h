@@ -124,6 +124,11 @@ int lbk_pdl_count(lbk_ctx *ctx, int64_t *launches);
  * one element per access.  lbk_shifted_count reports how many launches read x that way; the routines "mapshifted" /
  * "redshifted" of lbk_set_launch choose their shape (a one-element variant turns the path off). */
 int lbk_shifted_count(lbk_ctx *ctx, int64_t *launches);
+/* Walk direction of the unit-stride ELEMENTWISE kernels over vectors larger than the L2 cache.  What the 126 MB L2 still holds
+ * of such a vector is the end the previous kernel streamed last, so by default (1, adaptive) an elementwise kernel starts its
+ * walk there -- backwards after a kernel that walked forwards, as every reduction does -- and ~100 MB of its reads hit the
+ * L2.  Results cannot depend on it.  0 = always forwards, 2 = always backwards (experiments). */
+int lbk_set_traversal(lbk_ctx *ctx, int mode);
 
 /* CUDA graphs: record a fixed sequence of calls once, replay it with one host call.  The reference's own benchmark
  * (test/Bench.hs:17-132) lives at n <= 30 000, where a GPU call is all launch latency; a captured chain runs at the GPU's

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "lbk_set_pdl": (_int, [_vp, _int]),
     "lbk_pdl_count": (_int, [_vp, _pi64]),
     "lbk_shifted_count": (_int, [_vp, _pi64]),
+    "lbk_set_traversal": (_int, [_vp, _int]),
     "lbk_capture_begin": (_int, [_vp]),
     "lbk_capture_end": (_int, [_vp, _pvp]),
     "lbk_graph_launch": (_int, [_vp]),

@@ -377,8 +377,13 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
     using T = typename F::Scalar;
     static_assert(XSH == 0 || (XSH > 0 && XSH < VEC && !REV && F::RX), "shifted loads: 0 < XSH < VEC, forward pairing, x is read");
     constexpr bool FENCE = POLICY == 6 && (F::RX || F::RY);
-    // wait_mode (lbk_pdl.hpp): 0 wait for the predecessors only before exiting, 1 before the first store,
-    // 2 before the first load -- and in that case release the dependents only afterwards
+    // wait_mode, low two bits (lbk_pdl.hpp): 0 wait for the predecessors only before exiting, 1 before the first store,
+    // 2 before the first load -- and in that case release the dependents only afterwards.  Bit 2: walk the tiles from the
+    // BACK of the vectors to the front.  An elementwise result cannot depend on the order, and the tail of what the previous
+    // kernel streamed is what the 126 MB L2 still holds: starting there turns ~100 MB of a 2^28-element saxpy's DRAM reads
+    // into L2 hits (lbk_lib.cu, Traversal; profiles/r02_serpentine.md).
+    const bool backwards = (wait_mode & 4) != 0;
+    wait_mode &= 3;
     const int wait_before_store = wait_mode == 1;
     if (wait_mode == 2) pdl_wait();
     pdl_launch_dependents();
@@ -395,7 +400,8 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
     const bool edge_lane = (threadIdx.x & 31) == Shift<VEC, XSH>::EDGE_LANE;
     const unsigned edge = XSH > 0 ? (threadIdx.x | 31u) : threadIdx.x;
 
-    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const i64 tile = backwards ? ntiles - 1 - t : t;
         const i64 p0 = tile * per_tile + threadIdx.x;
         Pack<T, VEC> xv[UNROLL], yv[UNROLL];
         if (tile * per_tile + edge + (i64)(UNROLL - 1) * blockDim.x < npack) {   // whole tile in range for this thread (warp)

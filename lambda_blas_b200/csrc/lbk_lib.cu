@@ -138,6 +138,14 @@ struct lbk_ctx {
     int64_t launches = 0;
     int64_t pdl_launches = 0;
     int64_t shifted_launches = 0;     // unit-stride kernels that read x through shifted loads (lbk_shifted_count)
+    // Where did the last unit-stride kernel that streamed a vector END?  What the 126 MB L2 still holds of a vector much larger
+    // than itself is the part streamed last, so an elementwise kernel (whose result cannot depend on the order) starts its walk
+    // there: backwards after a kernel that walked forwards (every reduction does: their summation order is part of the result),
+    // forwards after one that walked backwards.  traversal: 0 always forwards, 1 adaptive (default), 2 always backwards (A/B).
+    struct Walk { const void *ptr; bool ended_at_head; };
+    Walk walks[8] = {};
+    int walk_next = 0;
+    int traversal = 1;
     // stream capture (lbk_capture_begin .. lbk_capture_end): kernels and asynchronous copies are recorded into a CUDA
     // graph instead of running; whatever cannot be recorded is refused, and buffers released meanwhile are freed at the end
     bool capturing = false;
@@ -731,6 +739,30 @@ extern "C" int lbk_graph_destroy(lbk_graph *g)
     }
     delete g;
     ctx_unref(c);
+    return LBK_OK;
+}
+
+constexpr i64 kWalkMinBytes = (i64)32 << 20;     // below this an operand fits the L2 whole and the direction is moot
+static int walk_vote(const lbk_ctx *c, const void *p)
+{
+    for (const auto &w : c->walks) if (w.ptr == p && p) return w.ended_at_head ? -1 : +1;
+    return 0;
+}
+static void walk_note(lbk_ctx *c, const void *p, bool ended_at_head)
+{
+    if (!p) return;
+    for (auto &w : c->walks) if (w.ptr == p) { w.ended_at_head = ended_at_head; return; }
+    c->walks[c->walk_next] = {p, ended_at_head};
+    c->walk_next = (c->walk_next + 1) % (int)(sizeof c->walks / sizeof c->walks[0]);
+}
+static void walk_forget(lbk_ctx *c) { for (auto &w : c->walks) w.ptr = nullptr; }
+
+extern "C" int lbk_set_traversal(lbk_ctx *c, int mode)
+{
+    if (!c || mode < 0 || mode > 2) return fail(c, LBK_ERR_ARG, "lbk_set_traversal: mode is 0 (forwards), 1 (adaptive) or 2 (backwards)");
+    for (lbk_ctx *s : c->subs) lbk_set_traversal(s, mode);
+    c->traversal = mode;
+    walk_forget(c);
     return LBK_OK;
 }
 
@@ -1655,6 +1687,15 @@ static int launch_map_unit(lbk_ctx *c, int rid, const F &f, const typename F::Sc
     if (F::WY) { op.wr[op.nwr] = yw; op.wrn[op.nwr++] = nb; }
     const lbk_pdl::Plan plan = lbk_pdl::plan(c->pdl, op);
     int wait_mode = plan.mode == lbk_pdl::WAIT_BEFORE_STORE ? 1 : plan.mode == lbk_pdl::WAIT_BEFORE_LOAD ? 2 : 0;
+    // walk the vectors from the end the previous kernel left in the L2 (see lbk_ctx::walks)
+    bool backwards = c->traversal == 2;
+    if (c->traversal == 1 && nb >= kWalkMinBytes && !rev)
+        backwards = (F::RX ? walk_vote(c, xr) : 0) + (F::RY ? walk_vote(c, yr) : 0) > 0;
+    if (backwards) wait_mode |= 4;
+    if (F::RX) walk_note(c, xr, backwards);
+    if (F::RY) walk_note(c, yr, backwards);
+    if (F::WX) walk_note(c, xw, backwards);
+    if (F::WY) walk_note(c, yw, backwards);
     void *args[] = {(void *)&fc, (void *)&xr, (void *)&yr, (void *)&xw, (void *)&yw, (void *)&head, (void *)&n,
                     (void *)&fence_mask, (void *)&wait_mode};
     if (xshift) c->shifted_launches++;
@@ -1931,6 +1972,7 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         void *args[] = {(void *)&x, (void *)&y, (void *)&head, (void *)&nn, (void *)&ib, (void *)&c->partials, (void *)&c->ticket,
                         (void *)&fa, (void *)&late_trigger, (void *)&wait_first};
         if (xshift) c->shifted_launches++;
+        walk_note(c, x, false); walk_note(c, y, false);        // a reduction walks forwards: its summation order is part of its result
         s = launch_stream_kernel(c, k, grid, threads, args, op, plan);
         if (s) return s;
         // with the NCCL transport the all-gather and the finish kernel follow on the stream: no chain through them

@@ -76,6 +76,10 @@ class Context:
         _ffi.check(_ffi.lib().lbk_shifted_count(self.handle, C.byref(v)), self.handle)
         return v.value
 
+    def set_traversal(self, mode: int) -> None:
+        """0: elementwise kernels always walk forwards; 1 (default): from the end the previous kernel left in the L2; 2: backwards."""
+        _ffi.check(_ffi.lib().lbk_set_traversal(self.handle, int(mode)), self.handle)
+
     def set_pdl(self, enabled: bool) -> None:
         _ffi.check(_ffi.lib().lbk_set_pdl(self.handle, int(enabled)), self.handle)
 

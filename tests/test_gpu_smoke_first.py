@@ -236,3 +236,36 @@ def test_general_stride_kernels_under_every_launch_shape(blas, ctx, oracle, fenc
     finally:
         ctx.set_launch("mapstrided", -1, 0, 0)
         ctx.set_launch("redstrided", -1, 0, 0)
+
+
+@pytest.mark.parametrize("dtype", P.DTYPES)
+def test_walk_direction_is_invisible(blas, ctx, oracle, dtype):
+    """lbk_set_traversal: elementwise kernels walk large vectors forwards, backwards, or from the end the previous kernel left in
+    the L2 -- the results are the same bits, for every shape (aligned, reversed lanes, shifted loads, one element per access)"""
+    from lambda_blas_b200 import inplace as ip
+    n = (12 << 20) + 5                                  # 48 MiB of floats per operand: above the adaptive threshold
+    rng = np.random.default_rng(17)
+    hx, hy = gen_unit(rng, n + 4, dtype), gen_unit(rng, n + 4, dtype)
+    fl = (blas.srotmg if dtype == np.float32 else blas.drotmg)(1.0, 2.0, 0.5, 3.0)
+    outs = []
+    for mode in (0, 1, 2):
+        ctx.set_traversal(mode)
+        try:
+            x, y, res = ctx.to_device(hx), ctx.to_device(hy), ctx.alloc(4, dtype).fill(0.0)
+            for _ in range(2):                          # twice: the adaptive mode alternates
+                ip.sdot_async(n, x, 1, y, 1, res)       # a reduction in between: it always walks forwards
+                ip.saxpy_(n, 0.5, x, 1, y, 1)
+                ip.sscal_(n, 1.0009765625, x, 1)
+                ip.srot_(n, x, 1, y, 1, 0.6, 0.8)
+                ip.srotm_(fl, n, x, 1, y, 1)
+                ip.sswap_(n, x, 1, y, 1)
+                ip.saxpy_(n, 0.25, x, 1, y, -1)         # reversed lanes
+                ip.saxpy_(n, 0.125, x.view(1, n), 1, y.view(0, n), 1)      # shifted loads
+                ip.sswap_(n, x.view(3, n), 1, y.view(2, n), 1)             # one element per access
+                ip.scopy_(n // 2, x, 1, y.view(n // 2, n // 2), 1)
+            outs.append((x.to_host(), y.to_host(), res.to_host()))
+        finally:
+            ctx.set_traversal(1)
+    for got in outs[1:]:
+        for a, b in zip(got, outs[0]):
+            P.assert_same(a, b)
