@@ -387,7 +387,7 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
     const int wait_before_store = wait_mode == 1;
     if (wait_mode == 2) pdl_wait();
     pdl_launch_dependents();
-    const i64 npack = body_packs<VEC, XSH>(n, head);
+    const i64 npack = XSH > 0 ? body_packs<VEC, XSH>(n, head) : (n - head) / VEC;
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
     const T *bxr = xr + head;
@@ -398,13 +398,15 @@ map_unit_kernel(F f, const typename F::Scalar *xr, const typename F::Scalar *yr,
     constexpr int YS = REV ? -1 : 1;
     // shifted loads of x: a whole warp takes the fast path together (its last lane decides), the shuffles need every lane
     const bool edge_lane = (threadIdx.x & 31) == Shift<VEC, XSH>::EDGE_LANE;
-    const unsigned edge = XSH > 0 ? (threadIdx.x | 31u) : threadIdx.x;
 
     for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const i64 tile = backwards ? ntiles - 1 - t : t;
         const i64 p0 = tile * per_tile + threadIdx.x;
         Pack<T, VEC> xv[UNROLL], yv[UNROLL];
-        if (tile * per_tile + edge + (i64)(UNROLL - 1) * blockDim.x < npack) {   // whole tile in range for this thread (warp)
+        bool whole;                                          // whole tile in range for this thread (XSH: for its warp)
+        if constexpr (XSH > 0) whole = (p0 | 31) + (i64)(UNROLL - 1) * blockDim.x < npack;
+        else whole = p0 + (i64)(UNROLL - 1) * blockDim.x < npack;
+        if (whole) {
             if constexpr (XSH > 0) {
                 T ex[UNROLL][Shift<VEC, XSH>::E];
 #pragma unroll
@@ -980,9 +982,8 @@ reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i
     using T = typename Op::Scalar;
     static_assert(XSH == 0 || (XSH > 0 && XSH < VEC && !REV && Op::TWO), "shifted loads of x: two operands, forward pairing");
     constexpr int YS = REV ? -1 : 1;     // REV: element i pairs x[i] with y[n-1-i] (see map_unit_kernel)
-    const i64 npack = body_packs<VEC, XSH>(n, head);
+    const i64 npack = XSH > 0 ? body_packs<VEC, XSH>(n, head) : (n - head) / VEC;
     const bool edge_lane = (threadIdx.x & 31) == Shift<VEC, XSH>::EDGE_LANE;
-    const unsigned edge = XSH > 0 ? (threadIdx.x | 31u) : threadIdx.x;      // shifted loads: a warp takes the fast path together
     const i64 per_tile = (i64)UNROLL * blockDim.x;
     const i64 ntiles = (npack + per_tile - 1) / per_tile;
     const T *bx = x + head, *by = REV ? y + (n - head) - VEC : y + head;
@@ -998,7 +999,10 @@ reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const i64 p0 = tile * per_tile + threadIdx.x;
         Pack<T, VEC> xv[UNROLL], yv[UNROLL];
-        if (tile * per_tile + edge + (i64)(UNROLL - 1) * blockDim.x < npack) {
+        bool whole;                                          // whole tile in range for this thread (shifted loads: for its warp)
+        if constexpr (XSH > 0) whole = (p0 | 31) + (i64)(UNROLL - 1) * blockDim.x < npack;
+        else whole = p0 + (i64)(UNROLL - 1) * blockDim.x < npack;
+        if (whole) {
             if constexpr (XSH > 0) {
                 T ex[UNROLL][Shift<VEC, XSH>::E];
 #pragma unroll

@@ -80,3 +80,28 @@ def test_default_shifted_load_shapes_do_not_spill():
             seen += 1
             assert re.search(r"STACK:0\b", usage), (name, usage)
     assert seen >= 3 * 4 + 3 + 1 + 3          # axpy / copy / scal x (3 Float shifts + 1 Double), dot Float x 3 + Double, sdsdot x 3
+
+
+def test_default_kernels_do_not_spill():
+    """Every shape kDefaultCfg (lbk_lib.cu) picks for the unit-stride routines, Float and Double: no stack frame.  (A change to
+    the kernel templates once cost idamax 4 % through a 12-byte spill that no functional test could see.)"""
+    if not shutil.which("cuobjdump") or not os.path.exists(LIB):
+        pytest.skip("cuobjdump or liblbk.so not available")
+    out = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True, check=True).stdout
+    usage = {m.group(1): m.group(2) for m in re.finditer(r"Function (\S+):\s*\n\s*(.*)", out)}
+    # (kernel, functor / op, float packs, unroll, policy) as in kDefaultCfg; Double instances halve the pack
+    defaults = [("reduce", "5DotOp", 8, 4, 1), ("reduce", "6AsumOp", 8, 2, 1), ("reduce", "6Nrm2Op", 8, 2, 1), ("reduce", "7IamaxOp", 8, 2, 1),
+                ("map", "5AxpyF", 8, 2, 6), ("map", "5ScalF", 4, 2, 6), ("map", "5CopyF", 4, 2, 6), ("map", "5SwapF", 4, 1, 6),
+                ("map", "4RotF", 4, 1, 6), ("map", "6Rotm0F", 4, 1, 6), ("map", "9RotmNeg1F", 4, 1, 6), ("map", "6Rotm1F", 4, 1, 6),
+                ("map", "5FillF", 8, 4, 1)]
+    seen = 0
+    for kind, who, vec, unroll, policy in defaults:
+        for ty, v in (("f", vec), ("d", vec // 2)):
+            pat = f"{kind}_unit_kernelINS_{who}I{ty}EELi{v}ELi{unroll}ELi{policy}ELb0ELi0E"
+            hits = [n for n in usage if pat in n]
+            assert len(hits) == 1, (pat, hits)
+            assert re.search(r"STACK:0\b", usage[hits[0]]), (hits[0], usage[hits[0]])
+            seen += 1
+    hits = [n for n in usage if "reduce_unit_kernelINS_7DsdotOpELi8ELi2ELi1ELb0ELi0E" in n]
+    assert len(hits) == 1 and re.search(r"STACK:0\b", usage[hits[0]])
+    assert seen == 26
