@@ -571,6 +571,7 @@ def run_ours(args) -> None:
             t1 = [0.0] * len(STRONG_R)
             if rank == 0:
                 solo = lb.Context(local)
+                solo.set_traversal(0)                # like the sharded runs it is compared with: HBM streaming, no L2 walk
                 S1 = 2 if 4 * N <= 4 * 126_000_000 else 1
                 sx = [solo.alloc(N).fill_hash(31 + i) for i in range(S1)]
                 sy = [solo.alloc(N).fill_hash(41 + i) for i in range(S1)]
