@@ -499,11 +499,15 @@ template <class F, bool FENCED>
 __global__ void __launch_bounds__(256)
 map_strided_kernel(F f, const typename F::Scalar *xr, typename F::Scalar *xw, i64 incx_r, i64 incx_w, i64 kx0_r, i64 kx0_w,
                    const typename F::Scalar *yr, typename F::Scalar *yw, i64 incy_r, i64 incy_w, i64 ky0_r, i64 ky0_w,
-                   i64 i_begin, i64 n, int x_last_only, int y_last_only, unsigned fence_mask)
+                   i64 i_begin, i64 n, int x_last_only, int y_last_only, unsigned fence_mask, int wait_mode)
 {
     using T = typename F::Scalar;
     constexpr int U = kStridedUnroll;
     constexpr bool FENCE = FENCED && (F::RX || F::RY);      // the load fence of map_unit_kernel: stores wait for all loads
+    // programmatic dependent launch, as in map_unit_kernel: 0 wait only before exiting, 1 before the first store, 2 before the first load
+    const int wait_before_store = wait_mode == 1;
+    if (wait_mode == 2) pdl_wait();
+    pdl_launch_dependents();
     const i64 per_tile = (i64)U * blockDim.x;
     const i64 count = n - i_begin;
     const i64 ntiles = (count + per_tile - 1) / per_tile;
@@ -527,6 +531,7 @@ map_strided_kernel(F f, const typename F::Scalar *xr, typename F::Scalar *xw, i6
             for (int u = 0; u < U; ++u) dep |= low_bits(xs[u]) | low_bits(ys[u]);
             held = (i64)(dep & fence_mask);      // 0: fence_mask is 0 at run time
         }
+        if (wait_before_store) pdl_wait();       // a predecessor may still be reading / writing these addresses
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const i64 i = i0 + (i64)u * blockDim.x;
@@ -537,6 +542,7 @@ map_strided_kernel(F f, const typename F::Scalar *xr, typename F::Scalar *xw, i6
             }
         }
     }
+    pdl_wait();     // completion stays in stream order
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1067,9 +1073,11 @@ reduce_unit_kernel(const typename Op::Scalar *x, const typename Op::Scalar *y, i
 template <class Op>
 __global__ void __launch_bounds__(256)
 reduce_strided_kernel(const typename Op::Scalar *x, i64 incx, i64 kx0, const typename Op::Scalar *y, i64 incy, i64 ky0, i64 n,
-                      i64 idx_base, Record *partials, unsigned *ticket, FinishArgs fa)
+                      i64 idx_base, Record *partials, unsigned *ticket, FinishArgs fa, int late_trigger, int wait_first)
 {
     using T = typename Op::Scalar;
+    if (wait_first) pdl_wait();                      // as in reduce_unit_kernel
+    if (!late_trigger) pdl_launch_dependents();
     // A grid-stride loop in groups of kStridedUnroll elements: all loads of a group are issued before the first is used.
     // The loads are volatile asm (load_pack), which keeps them in that order: written as plain C++ loads the compiler
     // hoists them for the sums but serialises them for iamax -- LDG, FSETP, FSEL, LDG, ... on one register, one load in
@@ -1101,6 +1109,7 @@ reduce_strided_kernel(const typename Op::Scalar *x, i64 incx, i64 kx0, const typ
         Op::step(acc, x[kx0 + i * incx], Op::TWO ? y[ky0 + i * incy] : T(0), ord);
     typename Op::Partial p = Op::empty();
     const u64 x0_bits = apply_x0<Op>(p, fa);
+    if (late_trigger) { pdl_wait(); pdl_launch_dependents(); }      // every load of this block has been consumed
     if constexpr (Op::IS_IAMAX) {
         if (acc.val >= T(0)) p = Op::merge(Op::candidate(acc.val, idx_base + first + (i64)acc.ord * stride), p);
     } else {

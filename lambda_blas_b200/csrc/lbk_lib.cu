@@ -1737,15 +1737,30 @@ static int launch_map_strided(lbk_ctx *c, const F &f, const typename F::Scalar *
     const i64 ntiles = (n - i_begin + per_tile - 1) / per_tile;
     const i64 cap = cfg.blocks_per_sm > 0 ? (i64)c->sms * cfg.blocks_per_sm : (wide ? ntiles : (i64)c->sms * 256);
     const int grid = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(ntiles, cap), 0x7fffffff));
-    lbk_pdl::interrupt(c->pdl);
-    if (cfg.variant == 0)
-        lbk::map_strided_kernel<F, false><<<grid, threads, 0, c->stream>>>(f, xr, xw, incx_r, incx_w, kx0_r, kx0_w,
-                                                                            yr, yw, incy_r, incy_w, ky0_r, ky0_w, i_begin, n, x_last, y_last, 0u);
-    else
-        lbk::map_strided_kernel<F, true><<<grid, threads, 0, c->stream>>>(f, xr, xw, incx_r, incx_w, kx0_r, kx0_w,
-                                                                           yr, yw, incy_r, incy_w, ky0_r, ky0_w, i_begin, n, x_last, y_last, 0u);
-    KERNEL_CHECK(c);
-    return LBK_OK;
+    // The general-stride kernels join the chain of overlapping kernels like the unit-stride ones (lbk_pdl.hpp); what they touch
+    // is stated as the whole span of each operand, 1 + (n-1)|inc| elements from its first touched one.
+    using T = typename F::Scalar;
+    auto span_of = [&](const T *base, i64 k0, i64 inc, const T **lo) -> i64 {
+        const i64 a = inc < 0 ? k0 + (n - 1) * inc : k0, b = inc < 0 ? k0 : k0 + (n - 1) * inc;     // lowest / highest index touched
+        *lo = base + a;
+        return (b - a + 1) * (i64)sizeof(T);
+    };
+    lbk_pdl::Op op;
+    const T *lo;
+    if (F::RX) { op.rdn[op.nrd] = span_of(xr, kx0_r, incx_r, &lo); op.rd[op.nrd++] = lo; }
+    if (F::RY) { op.rdn[op.nrd] = span_of(yr, ky0_r, incy_r, &lo); op.rd[op.nrd++] = lo; }
+    if (F::WX) { op.wrn[op.nwr] = span_of(xw, kx0_w, incx_w, &lo); op.wr[op.nwr++] = lo; }
+    if (F::WY) { op.wrn[op.nwr] = span_of(yw, ky0_w, incy_w, &lo); op.wr[op.nwr++] = lo; }
+    const lbk_pdl::Plan plan = lbk_pdl::plan(c->pdl, op);
+    int wait_mode = plan.mode == lbk_pdl::WAIT_BEFORE_STORE ? 1 : plan.mode == lbk_pdl::WAIT_BEFORE_LOAD ? 2 : 0;
+    F fc = f;
+    unsigned fence_mask = 0;
+    const void *k = cfg.variant == 0 ? (const void *)lbk::map_strided_kernel<F, false> : (const void *)lbk::map_strided_kernel<F, true>;
+    void *args[] = {(void *)&fc, (void *)&xr, (void *)&xw, (void *)&incx_r, (void *)&incx_w, (void *)&kx0_r, (void *)&kx0_w,
+                    (void *)&yr, (void *)&yw, (void *)&incy_r, (void *)&incy_w, (void *)&ky0_r, (void *)&ky0_w,
+                    (void *)&i_begin, (void *)&n, (void *)&x_last, (void *)&y_last, (void *)&fence_mask, (void *)&wait_mode};
+    walk_forget(c);          // which end of these vectors the L2 holds is anybody's guess now
+    return launch_stream_kernel(c, k, grid, threads, args, op, plan);
 }
 
 // In-place (xw == xr, yw == yr) or out-of-place update of n logical elements.  A destination that
@@ -1997,10 +2012,22 @@ static int reduce_dispatch(lbk_ctx *c, int rid, int kind, i64 n, const Operand &
         resident &= 255;
         const i64 cap = (i64)c->sms * (scfg.blocks_per_sm > 0 ? scfg.blocks_per_sm : (wide ? 4 * resident : resident));
         const int grid = (int)std::max<i64>(1, std::min<i64>(std::min<i64>((std::max<i64>(nl, 1) + threads - 1) / threads, cap), kMaxGrid));
-        lbk_pdl::interrupt(c->pdl);
-        lbk::reduce_strided_kernel<Op><<<grid, threads, 0, c->stream>>>(x, incx, first_index(nl, incx), y, incy,
-                                                                          first_index(nl, incy), nl, idx_base, c->partials, c->ticket, fa);
-        KERNEL_CHECK(c);
+        // joins the chain of overlapping kernels like the unit-stride reductions (spans of the operands, lbk_pdl.hpp)
+        i64 kx0 = first_index(nl, incx), ky0 = first_index(nl, incy), nn = nl, ib = idx_base, ix = incx, iy = incy;
+        lbk_pdl::Op op;
+        op.reduction = true; op.rid = R_REDSTRIDED;
+        op.rd[0] = x; op.rdn[0] = (1 + (nl - 1) * iabs64(incx)) * (i64)sizeof(T);
+        op.rd[1] = y; op.rdn[1] = y ? (1 + (nl - 1) * iabs64(incy)) * (i64)sizeof(T) : 0;
+        op.nrd = 2;
+        op.wr[0] = out; op.wrn[0] = 8; op.nwr = 1;
+        const lbk_pdl::Plan plan = lbk_pdl::plan(c->pdl, op);
+        int late_trigger = plan.late ? 1 : 0, wait_first = plan.mode == lbk_pdl::WAIT_BEFORE_LOAD ? 1 : 0;
+        void *args[] = {(void *)&x, (void *)&ix, (void *)&kx0, (void *)&y, (void *)&iy, (void *)&ky0, (void *)&nn, (void *)&ib,
+                        (void *)&c->partials, (void *)&c->ticket, (void *)&fa, (void *)&late_trigger, (void *)&wait_first};
+        walk_forget(c);
+        int s = launch_stream_kernel(c, (const void *)lbk::reduce_strided_kernel<Op>, grid, threads, args, op, plan);
+        if (s) return s;
+        if (exchange && !fused) lbk_pdl::interrupt(c->pdl);
     }
     if (by_events) {           // the record is in this rank's ring slot once this event has fired
         lbk_pdl::interrupt(c->pdl);

@@ -42,8 +42,13 @@ def run_sequence(blas, ctx, seed, pdl, dtype):
             if lo_a + m * esz <= lo_b or lo_b + m * esz <= lo_a:       # in-place two-vector updates must not alias
                 return a, b, m
 
+    def strided(inc):
+        """a window and the number of elements an increment of `inc` can visit in it"""
+        a, m = window()
+        return a, 1 + (m - 1) // abs(inc)
+
     for step in range(48):
-        op = int(rng.integers(13))
+        op = int(rng.integers(18))
         slot = res.view(2 * int(rng.integers(30)), 2)
         if op == 0:
             a, b, m = two(); ip.sdot_async(m, a, 1, b, 1, slot)
@@ -70,9 +75,25 @@ def run_sequence(blas, ctx, seed, pdl, dtype):
         elif op == 11:                                                  # the pure forms: a NEW vector per call, the old one is
             i, j = (int(v) for v in rng.choice(len(vecs), 2, replace=False))    # released in stream order and its block reused
             vecs[j] = blas.saxpy(n, 0.125, vecs[i], 1, vecs[j], 1)
-        else:
+        elif op == 12:
             j = int(rng.integers(len(vecs)))
             vecs[j] = blas.sscal(n - 5, 0.75, vecs[j], 1)
+        elif op == 13:                                                  # the general-stride kernels are members of the chain too
+            inc = int(rng.choice([2, 3, -2, 7]))
+            a, m = strided(inc); ip.sscal_(m, 1.0 + 0.125 * (rng.random() - 0.5), a, abs(inc))
+        elif op == 14:
+            a, b, m = two(); inc = int(rng.choice([2, -3, 5]))
+            k = 1 + (m - 1) // abs(inc)
+            ip.saxpy_(k, 0.25 - rng.random() / 2, a, inc, b, int(rng.choice([1, -1, 2])) if k * 2 <= m else 1)
+        elif op == 15:
+            a, b, m = two(); inc = int(rng.choice([2, 3, -2]))
+            ip.sdot_async(1 + (m - 1) // abs(inc), a, inc, b, inc, slot)
+        elif op == 16:
+            inc = int(rng.choice([2, 5]))
+            a, m = strided(inc); ip.isamax_async(m, a, inc, slot)
+        else:
+            inc = int(rng.choice([2, 4]))
+            a, m = strided(inc); ip.snrm2_async(m, a, inc, slot)
     out = [v.to_host() for v in vecs] + [res.to_host()]
     return out, ctx.pdl_count() - before
 
