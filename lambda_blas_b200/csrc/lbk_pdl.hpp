@@ -1,6 +1,7 @@
 // lbk_pdl.hpp -- which kernels of a stream may overlap (programmatic dependent launch), decided on the host.
 //
-// Pure host logic, no CUDA types: lbk_lib.cu asks it how to launch each unit-stride kernel, and the CPU
+// Pure host logic, no CUDA types: lbk_lib.cu asks it how to launch each streaming kernel (unit-stride, and since round 2 the
+// general-stride ones, whose operands are stated as whole spans), and the CPU
 // tests drive it directly through the lbk_pdl_sim_* entry points (tests/test_pdl_plan.py).
 //
 // Every unit-stride kernel releases its dependents as its first instruction
@@ -110,8 +111,7 @@ inline int slot_of(int rid, const void *x, const void *y)
     return (int)((((uintptr_t)x >> 8) * 31u + ((uintptr_t)y >> 8) * 17u + (unsigned)rid) % State::kSlots);
 }
 
-// Any other operation on the stream (copy, event, allocation, general-stride kernel, NCCL): the next
-// unit-stride kernel is launched the ordinary way.
+// Any other operation on the stream (copy, event, NCCL, graph launch): the next kernel is launched the ordinary way.
 inline void interrupt(State &s) { s.grp.open = false; }
 
 // How to launch `op` behind everything enqueued so far.  Also teaches the predictor what the last
