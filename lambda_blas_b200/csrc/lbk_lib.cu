@@ -1117,6 +1117,15 @@ static size_t stage_chunk_bytes()
     return bytes;
 }
 
+// the CPU half of a staged transfer: non-temporal stores (lbk_hostcopy.cpp); LBK_STAGE_MEMCPY=1 puts plain memcpy back (A/B)
+extern "C" void lbk_host_stream_copy(void *dst, const void *src, size_t bytes);
+static void stage_copy(void *dst, const void *src, size_t bytes)
+{
+    static const bool plain = [] { const char *e = getenv("LBK_STAGE_MEMCPY"); return e && atoi(e) != 0; }();
+    if (plain) memcpy(dst, src, bytes);
+    else lbk_host_stream_copy(dst, src, bytes);
+}
+
 static bool is_pageable(const void *host)
 {
     cudaPointerAttributes a;
@@ -1146,7 +1155,7 @@ static int staged_transfer(lbk_ctx *c, char *dev, char *host, size_t bytes, bool
             if (up) {
                 if (in_flight) e = cudaEventSynchronize(c->stage_ev[t]);        // this lane's previous chunk has left its buffer
                 if (e == cudaSuccess) {
-                    memcpy(c->stage_buf[t], host + off, len);
+                    stage_copy(c->stage_buf[t], host + off, len);
                     e = cudaMemcpyAsync(dev + off, c->stage_buf[t], len, cudaMemcpyHostToDevice, c->stream);
                 }
                 if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[t], c->stream);
@@ -1155,7 +1164,7 @@ static int staged_transfer(lbk_ctx *c, char *dev, char *host, size_t bytes, bool
                 e = cudaMemcpyAsync(c->stage_buf[t], dev + off, len, cudaMemcpyDeviceToHost, c->stream);
                 if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[t], c->stream);
                 if (e == cudaSuccess) e = cudaEventSynchronize(c->stage_ev[t]);
-                if (e == cudaSuccess) memcpy(host + off, c->stage_buf[t], len);
+                if (e == cudaSuccess) stage_copy(host + off, c->stage_buf[t], len);
             }
             if (e != cudaSuccess) failed.store((int)e);
         }
