@@ -1,4 +1,9 @@
-import sys, os, time
+"""Microseconds per kernel of recorded chains of GENERAL-STRIDE calls (inc 10, as in two thirds of test/Bench.hs), with the overlap
+of programmatic dependent launch off and on; the chains are replayed as CUDA graphs so that the host is out of the picture.
+    python tools/strided_chain.py  ->  CSV: chain,pdl,n,us_per_call
+"""
+import os
+import sys
 sys.path.insert(0, os.getcwd())
 import lambda_blas_b200 as lb
 from lambda_blas_b200 import inplace as ip
