@@ -1118,7 +1118,7 @@ reduce_strided_kernel(const typename Op::Scalar *x, i64 incx, i64 kx0, const typ
     grid_finish<Op>(p, partials, ticket, fa, x0_bits);
 }
 
-__global__ void finish_records_kernel(const Record *recs, int nranks, FinishArgs fa)
+static __global__ void finish_records_kernel(const Record *recs, int nranks, FinishArgs fa)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     finish_record(fold_by_kind(recs, nranks, fa.kind), fa);
@@ -1128,7 +1128,7 @@ __global__ void finish_records_kernel(const Record *recs, int nranks, FinishArgs
 // reduction kernel leaves its record in its own ring slot (mode 1), the host makes every rank's stream wait for
 // the other ranks' "record written" events, and this kernel then reads all ranks' slots -- peer memory, or mapped
 // host memory between devices that are not peers -- and folds them in rank order.
-__global__ void finish_gather_kernel(const Record *const *srcs, int slot, int nranks, FinishArgs fa)
+static __global__ void finish_gather_kernel(const Record *const *srcs, int slot, int nranks, FinishArgs fa)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Record all[kMaxRanks];

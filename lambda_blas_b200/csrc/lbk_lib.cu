@@ -8,6 +8,7 @@
 #include "../../include/lbk.h"
 #include "lbk_kernels.cuh"
 #include "lbk_pdl.hpp"
+#include "lbk_tables.hpp"
 #include "lbk_team.hpp"
 
 #include <cuda_runtime.h>
@@ -38,13 +39,7 @@ static_assert(sizeof(lbk_record) == sizeof(Record), "host and device records sha
 // launch variants: (VEC floats per access = 4/16/32 bytes, UNROLL accesses in flight per operand, cache POLICY);
 // for double vectors the same variant moves the same bytes (VEC/2 elements)
 // ------------------------------------------------------------------------------------------------
-#define LBK_VARIANTS(X) \
-    X(0, 4, 4, 1) X(1, 4, 2, 1) X(2, 4, 8, 1) X(3, 8, 2, 1) X(4, 8, 4, 1) X(5, 4, 4, 0) \
-    X(6, 8, 1, 1) X(7, 4, 1, 1) X(8, 1, 4, 1) X(9, 8, 2, 0) X(10, 8, 8, 1) \
-    X(11, 8, 4, 2) X(12, 8, 4, 3) X(13, 8, 4, 4) X(14, 8, 4, 5) \
-    X(15, 8, 4, 6) X(16, 8, 2, 6) X(17, 8, 1, 6) X(18, 8, 8, 6) X(19, 4, 4, 6) X(20, 4, 2, 6) X(21, 4, 8, 6) X(22, 4, 1, 6) \
-    X(23, 1, 8, 6) X(24, 1, 16, 6) X(25, 1, 16, 1) X(26, 1, 8, 1)
-constexpr int kNumVariants = 27;
+// (the variant table LBK_VARIANTS and the per-variant kernel tables live in lbk_tables.hpp / lbk_tables_*.cu)
 static const int kVariantVec[kNumVariants] = {4, 4, 4, 8, 8, 4, 8, 4, 1, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 4, 4, 4, 4, 1, 1, 1, 1};
 constexpr int kScalarVariant = 8;   // VEC == 1: any alignment (the reversed pairing's any-alignment shape)
 constexpr int kVec4Fallback = 0;    // used when a 256-bit variant meets 16-byte-only alignment
@@ -1502,19 +1497,6 @@ static void resolve_alignment_rev(int *variant, i64 *head, const T *const *xptrs
 // ------------------------------------------------------------------------------------------------
 // map launchers
 // ------------------------------------------------------------------------------------------------
-template <class T> constexpr int vec_t(int vec_f32) { return sizeof(T) == 4 ? vec_f32 : (vec_f32 > 1 ? vec_f32 / 2 : 1); }
-
-template <class F>
-static const void *map_kernel_ptr(int variant)
-{
-    using T = typename F::Scalar;
-    switch (variant) {
-#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::map_unit_kernel<F, vec_t<T>(VEC), UNROLL, POLICY>;
-        LBK_VARIANTS(X)
-#undef X
-    }
-    return nullptr;
-}
 // the reversed pairing is built for two shapes only: 16-byte packs x UNROLL 4, and the any-alignment scalar one
 template <class F>
 static const void *map_kernel_ptr_rev(int variant)
@@ -1891,18 +1873,6 @@ static int map_entry(lbk_ctx *c, const char *who, int rid, const F &f, i64 n,
 // ------------------------------------------------------------------------------------------------
 // reduce launchers
 // ------------------------------------------------------------------------------------------------
-template <class Op>
-static const void *reduce_kernel_ptr(int variant)
-{
-    using T = typename Op::Scalar;
-    switch (variant) {
-#define X(ID, VEC, UNROLL, POLICY) case ID: return (const void *)lbk::reduce_unit_kernel<Op, vec_t<T>(VEC), UNROLL, (POLICY == 6 ? 1 : POLICY)>;   // 6: a map-only policy
-        LBK_VARIANTS(X)
-#undef X
-    }
-    return nullptr;
-}
-
 // Runs the local reduction and, on a communicator with sharded operands, the exchange + finish.
 // `out` is a device-visible address that receives the scalar (T, or the int64 for iamax).
 template <class Op>
