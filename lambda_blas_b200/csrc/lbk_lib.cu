@@ -687,6 +687,8 @@ extern "C" int lbk_capture_end(lbk_ctx *c, lbk_graph **out)
     ON_DEVICE(c);
     c->capturing = false;
     lbk_pdl::interrupt(c->pdl);
+    const int64_t recorded = c->launches - c->capture_launches0;
+    c->launches = c->capture_launches0;        // recorded, not launched -- whatever becomes of the graph
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     for (void *p : c->deferred_free) cudaFreeAsync(p, c->stream);      // finalisers that ran during the capture
@@ -695,9 +697,8 @@ extern "C" int lbk_capture_end(lbk_ctx *c, lbk_graph **out)
     cudaGraphExec_t x = nullptr;
     e = cudaGraphInstantiate(&x, g, 0);
     if (e != cudaSuccess) { cudaGraphDestroy(g); cudaGetLastError(); return fail(c, LBK_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-    lbk_graph *h = new (std::nothrow) lbk_graph{c, g, x, c->launches - c->capture_launches0};
+    lbk_graph *h = new (std::nothrow) lbk_graph{c, g, x, recorded};
     if (!h) { cudaGraphExecDestroy(x); cudaGraphDestroy(g); return fail(c, LBK_ERR_NOMEM, "out of host memory"); }
-    c->launches = c->capture_launches0;        // recorded, not launched
     ctx_ref(c);
     *out = h;
     return LBK_OK;
