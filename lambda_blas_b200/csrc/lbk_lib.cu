@@ -100,8 +100,8 @@ struct lbk_ctx {
     // this rank's record ring (two parities), the table of all ranks' rings, the "record written" event, and the
     // finish this rank still owes for the reduction it launched last (lbk_lib.cu, exchange_finish)
     // pinned staging lanes for synchronous transfers from / to PAGEABLE host memory (staged_transfer), made on first use
-    void *stage_buf[8] = {};
-    cudaEvent_t stage_ev[8] = {};
+    void *stage_buf[16] = {};         // two chunks per lane (lane t: slots t and t + 8): the copy engine works on one while the
+    cudaEvent_t stage_ev[16] = {};    // lane's thread fills / drains the other
     size_t stage_chunk = 0;
     Record *rec_ring = nullptr;
     const Record **ring_table_dev = nullptr;
@@ -362,7 +362,7 @@ static void destroy_one(lbk_ctx *c)
         if (c->rec_ring) { if (c->host_mailbox) cudaFreeHost(c->rec_ring); else cudaFree(c->rec_ring); }
         cudaFree(c->ring_table_dev);
         if (c->xchg_ev) cudaEventDestroy(c->xchg_ev);
-        for (int i = 0; i < 8; ++i) { if (c->stage_buf[i]) cudaFreeHost(c->stage_buf[i]); if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]); }
+        for (int i = 0; i < 16; ++i) { if (c->stage_buf[i]) cudaFreeHost(c->stage_buf[i]); if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]); }
         cudaFree(c->peers_dev);
         if (c->error_flag_host) cudaFreeHost(c->error_flag_host);
         cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->snap); cudaFree(c->sink);
@@ -1135,36 +1135,54 @@ static int staged_transfer(lbk_ctx *c, char *dev, char *host, size_t bytes, bool
     const int kStageLanes = stage_lanes(c);
     const size_t kStageChunk = stage_chunk_bytes();
     c->stage_chunk = kStageChunk;
-    for (int i = 0; i < kStageLanes; ++i) {
-        if (!c->stage_buf[i]) CU(c, cudaHostAlloc(&c->stage_buf[i], kStageChunk, cudaHostAllocDefault));
-        if (!c->stage_ev[i]) CU(c, cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
-    }
+    for (int lane = 0; lane < kStageLanes; ++lane)
+        for (int i : {lane, lane + kMaxStageLanes}) {
+            if (!c->stage_buf[i]) CU(c, cudaHostAlloc(&c->stage_buf[i], kStageChunk, cudaHostAllocDefault));
+            if (!c->stage_ev[i]) CU(c, cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+        }
     lbk_pdl::interrupt(c->pdl);
     const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
     std::atomic<int> failed{0};
+    // Lane t moves chunks t, t + lanes, t + 2 lanes, ... through its two pinned buffers in turn: while the copy engine works on one,
+    // the lane's thread copies the caller's bytes into / out of the other (non-temporal stores, lbk_hostcopy.cpp).
     auto lane = [&](int t) {
         if (cudaSetDevice(c->device) != cudaSuccess) { failed.store(1); return; }
-        bool in_flight = false;
-        for (size_t i = (size_t)t; i < nchunks && !failed.load(std::memory_order_relaxed); i += kStageLanes) {
-            const size_t off = i * kStageChunk, len = std::min(kStageChunk, bytes - off);
-            cudaError_t e = cudaSuccess;
-            if (up) {
-                if (in_flight) e = cudaEventSynchronize(c->stage_ev[t]);        // this lane's previous chunk has left its buffer
+        auto chunk = [&](size_t k, size_t *off, size_t *len) { *off = ((size_t)t + k * (size_t)kStageLanes) * kStageChunk; *len = *off < bytes ? std::min(kStageChunk, bytes - *off) : 0; };
+        auto slot = [&](size_t k) { return t + (int)(k & 1) * kMaxStageLanes; };
+        size_t off, len;
+        cudaError_t e = cudaSuccess;
+        if (up) {
+            for (size_t k = 0; e == cudaSuccess && !failed.load(std::memory_order_relaxed); ++k) {
+                chunk(k, &off, &len);
+                if (!len) break;
+                const int sl = slot(k);
+                if (k >= 2) e = cudaEventSynchronize(c->stage_ev[sl]);          // chunk k-2 has left this buffer
                 if (e == cudaSuccess) {
-                    stage_copy(c->stage_buf[t], host + off, len);
-                    e = cudaMemcpyAsync(dev + off, c->stage_buf[t], len, cudaMemcpyHostToDevice, c->stream);
+                    stage_copy(c->stage_buf[sl], host + off, len);
+                    e = cudaMemcpyAsync(dev + off, c->stage_buf[sl], len, cudaMemcpyHostToDevice, c->stream);
                 }
-                if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[t], c->stream);
-                in_flight = true;
-            } else {
-                e = cudaMemcpyAsync(c->stage_buf[t], dev + off, len, cudaMemcpyDeviceToHost, c->stream);
-                if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[t], c->stream);
-                if (e == cudaSuccess) e = cudaEventSynchronize(c->stage_ev[t]);
-                if (e == cudaSuccess) stage_copy(host + off, c->stage_buf[t], len);
+                if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[sl], c->stream);
             }
-            if (e != cudaSuccess) failed.store((int)e);
+        } else {
+            auto fetch = [&](size_t k) {                                       // enqueue the download of chunk k into its buffer
+                size_t o, l;
+                chunk(k, &o, &l);
+                if (!l) return cudaSuccess;
+                cudaError_t r = cudaMemcpyAsync(c->stage_buf[slot(k)], dev + o, l, cudaMemcpyDeviceToHost, c->stream);
+                return r == cudaSuccess ? cudaEventRecord(c->stage_ev[slot(k)], c->stream) : r;
+            };
+            e = fetch(0);
+            for (size_t k = 0; e == cudaSuccess && !failed.load(std::memory_order_relaxed); ++k) {
+                chunk(k, &off, &len);
+                if (!len) break;
+                e = fetch(k + 1);                                              // the next chunk travels while this one is copied out
+                if (e == cudaSuccess) e = cudaEventSynchronize(c->stage_ev[slot(k)]);
+                if (e == cudaSuccess) stage_copy(host + off, c->stage_buf[slot(k)], len);
+            }
         }
+        if (e != cudaSuccess) failed.store((int)e);
     };
+    (void)nchunks;
     std::thread workers[kMaxStageLanes - 1];
     for (int t = 1; t < kStageLanes; ++t) workers[t - 1] = std::thread(lane, t);
     lane(0);
