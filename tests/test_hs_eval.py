@@ -234,3 +234,46 @@ def test_c_oracle_equals_reference_source_on_fresh_inputs(oracle, dt):
             assert same(r, o), tag
         g = (oracle.srotg if dt == F32 else oracle.drotg)(margs[0], margs[1])
         assert same(list(R.rotg(margs[0], margs[1], ty=dt)), list(g)), margs
+
+
+@needs_ref
+@pytest.mark.parametrize("dt", [F32, F64])
+def test_c_oracle_equals_reference_source_on_arbitrary_bit_patterns(oracle, dt):
+    """elements drawn from ALL bit patterns (NaN payloads, infinities, denormals, signed zeros), n from 0, increments -3..3"""
+    R = H.Reference()
+    rng = np.random.default_rng(2026 if dt == F32 else 2027)
+    U = np.uint32 if dt == F32 else np.uint64
+
+    def same(a, b):
+        a, b = np.atleast_1d(np.asarray(a, dtype=dt)), np.atleast_1d(np.asarray(b, dtype=dt))
+        nan = np.isnan(a)
+        return a.shape == b.shape and np.array_equal(nan, np.isnan(b)) and np.array_equal(a.view(U)[~nan], b.view(U)[~nan])
+
+    def vec(n):
+        kind = int(rng.integers(3))
+        if kind == 0:
+            return rng.integers(0, 2 ** 32 if dt == F32 else 2 ** 63, n, dtype=np.uint64).astype(U).view(dt).copy()
+        if kind == 1:
+            with np.errstate(over="ignore"):
+                return (rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n)).astype(dt)
+        return rng.choice(np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 1e-40, 3e38, 2.0 ** 60, 2.0 ** -70]), n).astype(dt)
+
+    for _ in range(120):
+        n = int(rng.integers(0, 14))
+        ix, iy = int(rng.integers(-3, 4)), int(rng.integers(-3, 4))
+        x, y = vec(span(max(n, 1), ix, int(rng.integers(0, 2)))), vec(span(max(n, 1), iy, int(rng.integers(0, 2))))
+        a = vec(1)[0]
+        c, s = vec(2)
+        tag = (n, ix, iy)
+        with np.errstate(all="ignore"):
+            assert same(R.dot(n, x, ix, y, iy), oracle.dot(n, x, ix, y, iy)), tag
+            assert same(R.asum(n, x, ix), oracle.asum(n, x, ix)) and same(R.nrm2(n, x, ix), oracle.nrm2(n, x, ix)), tag
+            assert R.iamax(n, x, ix) == oracle.iamax(n, x, ix), tag
+            assert same(R.scal(n, a, x, ix), oracle.scal(n, a, x, ix)) and same(R.copy(n, x, ix, y, iy), oracle.copy(n, x, ix, y, iy)), tag
+            assert same(R.axpy(n, a, x, ix, y, iy), oracle.axpy(n, a, x, ix, y, iy)), tag
+            for r, o in zip(R.swap(n, x, ix, y, iy), oracle.swap(n, x, ix, y, iy)):
+                assert same(r, o), tag
+            for r, o in zip(R.rot(n, x, ix, y, iy, c, s), oracle.rot(n, x, ix, y, iy, c, s)):
+                assert same(r, o), tag
+            if dt == F32:
+                assert same(R.sdsdot(n, a, x, ix, y, iy), oracle.sdsdot(n, a, x, ix, y, iy)), tag
