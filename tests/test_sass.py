@@ -105,3 +105,16 @@ def test_default_kernels_do_not_spill():
     hits = [n for n in usage if "reduce_unit_kernelINS_7DsdotOpELi8ELi2ELi1ELb0ELi0E" in n]
     assert len(hits) == 1 and re.search(r"STACK:0\b", usage[hits[0]])
     assert seen == 26
+
+
+def test_shifted_load_kernels_read_aligned_packs_and_shuffle(sass):
+    """lbk_kernels.cuh, shift_pack: 16-byte loads of x plus lane shuffles -- down for a shift of at most half a pack, up beyond"""
+    _, kernels = sass
+    shifted = {k: v for k, v in kernels.items() if re.search(r"_unit_kernelI.*ELb0ELi[123]E", k)}
+    assert len(shifted) >= 38
+    for name, ins in shifted.items():
+        assert any(re.match(r"LDG\.E.*\.128", i) for i in ins), name
+        shift = int(re.search(r"ELb0ELi([123])E", name).group(1))
+        vec = int(re.search(r"ELi(\d)ELi\dELi\dELb0", name).group(1))
+        want = "SHFL.DOWN" if 2 * shift <= vec else "SHFL.UP"
+        assert any(i.startswith(want) for i in ins), (name, want)
