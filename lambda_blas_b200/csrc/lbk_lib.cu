@@ -558,7 +558,19 @@ extern "C" int lbk_shutdown(lbk_ctx *c)
     std::lock_guard<std::mutex> lk(g_life);
     if (c->closed) return LBK_OK;
     for (lbk_ctx *s : c->subs) { DevGuard g(s->device); if (s->stream) cudaStreamSynchronize(s->stream); s->closed = true; }
-    if (c->stream) { DevGuard g(c->device); cudaStreamSynchronize(c->stream); }
+    if (c->stream) {
+        DevGuard g(c->device);
+        if (c->capturing) {                    // shut down in the middle of a capture: drop what was recorded
+            cudaGraph_t rec = nullptr;
+            cudaStreamEndCapture(c->stream, &rec);
+            if (rec) cudaGraphDestroy(rec);
+            cudaGetLastError();
+            c->capturing = false;
+            for (void *p : c->deferred_free) cudaFreeAsync(p, c->stream);
+            c->deferred_free.clear();
+        }
+        cudaStreamSynchronize(c->stream);
+    }
     c->team.reset();
     c->closed = true;
     if (live_handles(c) == 0) destroy_tree(c);      // otherwise the last lbk_vec_free / lbk_event_destroy does it

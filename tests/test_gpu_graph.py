@@ -134,3 +134,19 @@ def test_multi_device_contexts_do_not_capture(blas):
         assert e.value.status == 6
     finally:
         m.close()
+
+
+def test_closing_a_context_in_the_middle_of_a_capture(blas):
+    from lambda_blas_b200 import inplace as ip
+    c = blas.Context(0)
+    x = c.alloc(4096).fill(2.0)
+    blas._ffi.check(blas._ffi.lib().lbk_capture_begin(c.handle), c.handle)
+    ip.sscal_(4096, 3.0, x, 1)
+    c.close()                                  # drops the recording; nothing ran
+    c2 = blas.Context(0)                       # the device is fine afterwards
+    y = c2.alloc(4096).fill(1.5)
+    ip.sscal_(4096, 2.0, y, 1)
+    assert y.to_host()[7] == 3.0
+    c2.close()
+    del x
+    gc.collect()
