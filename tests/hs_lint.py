@@ -426,6 +426,13 @@ MEMBERS = {
     "Data.Vector.Storable.Mutable": "IOVector MVector STVector new unsafeNew replicate length unsafeWith read write unsafeRead unsafeWrite slice".split(),
     "Control.DeepSeq": "NFData rnf deepseq force ($!!)".split(),
     "GHC.Generics": ["Generic"],
+    # what hs/test/DeviceMain.hs imports whole, as the reference's test/Main.hs does
+    "Test.Tasty": "TestTree TestName defaultMain testGroup localOption".split(),
+    "Test.Tasty.QuickCheck": "testProperty Gen Property forAll choose elements suchThat ioProperty frequency vectorOf oneof listOf property (==>) (===) QuickCheckTests".split(),
+    # the reference's own modules: src/Numerical/BLAS/Single.hs:41-61 (export list), test/Gen.hs
+    "Numerical.BLAS.Single": ("asum sasum dasum nrm2 snrm2 dnrm2 dot sdot ddot sdsdot scal sscal dscal rot srot drot rotg srotg drotg rotm srotm drotm "
+                              "rotmg srotmg drotmg axpy saxpy daxpy copy scopy dcopy swap sswap dswap iamax isamax idamax").split(),
+    "Gen": "genNiceFloat genNiceDouble genNVector genFloat genDouble genEveryday genNegative".split(),
 }
 
 
@@ -571,12 +578,12 @@ def applications(e, visit):
         return
     if not isinstance(e, tuple) or not e:
         return
-    if e[0] == "app":
+    if e[0] == "app" or (e[0] == "binop" and e[1] == "$"):           # f a b  and  f a $ b  are both applications of f
         n, f = 0, e
-        while f[0] == "app":
-            applications(f[2], visit)
+        while f[0] == "app" or (f[0] == "binop" and f[1] == "$"):
+            applications(f[2] if f[0] == "app" else f[3], visit)
             n += 1
-            f = f[1]
+            f = f[1] if f[0] == "app" else f[2]
         if f[0] == "var":
             visit(f[1], n)
         else:

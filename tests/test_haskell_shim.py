@@ -11,7 +11,8 @@ from oracle import hs_eval as H
 from tests import hs_lint as L
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SHIM = sorted(glob.glob(os.path.join(ROOT, "hs", "Numerical", "BLAS", "*.hs")) + glob.glob(os.path.join(ROOT, "hs", "Numerical", "BLAS", "Device", "*.hs")))
+SHIM = sorted(glob.glob(os.path.join(ROOT, "hs", "Numerical", "BLAS", "*.hs")) + glob.glob(os.path.join(ROOT, "hs", "Numerical", "BLAS", "Device", "*.hs"))) + \
+    sorted(glob.glob(os.path.join(ROOT, "hs", "test", "*.hs")))
 REF = "/root/reference"
 # constructors and fields behind `GivensRot(..)`, `ModGivensRot(..)` (src/Numerical/BLAS/Types.hs:8,15-20 of the reference)
 REFERENCE_TYPES = {"GivensRot": ["GIVENSROT"],
@@ -46,7 +47,37 @@ def test_the_parser_rejects_broken_sources(src, why):
 
 
 def test_shim_modules_exist():
-    assert [os.path.basename(f) for f in SHIM] == ["Device.hs", "Types.hs"]
+    assert [os.path.basename(f) for f in SHIM] == ["Device.hs", "Types.hs", "DeviceMain.hs"]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference is only present in the build container")
+def test_member_lists_of_the_references_modules_are_its_export_lists():
+    """hs_lint.MEMBERS states what `import Numerical.BLAS.Single` / `import Gen` bring into scope: hold that to the reference"""
+    p, _, _ = L.parse_file(REF + "/src/Numerical/BLAS/Single.hs")
+    assert sorted(n for n, _ in p.exports) == sorted(L.MEMBERS["Numerical.BLAS.Single"])
+    g, gd, _ = L.parse_file(REF + "/test/Gen.hs")
+    defined = set(L.decl_names(gd))
+    assert set(L.MEMBERS["Gen"]) <= defined, set(L.MEMBERS["Gen"]) - defined
+
+
+def test_device_suite_applies_the_device_routines_to_as_many_arguments_as_they_take():
+    """hs/test/DeviceMain.hs calls Numerical.BLAS.Device qualified as D: every D.f is applied to nothing (passed on) or to exactly
+    the number of arguments of f's signature in Device.hs"""
+    dev, _, _ = L.parse_file(os.path.join(ROOT, "hs", "Numerical", "BLAS", "Device.hs"))
+    p, decls, _ = L.parse_file(os.path.join(ROOT, "hs", "test", "DeviceMain.hs"))
+    bad, seen = [], set()
+
+    def visit(name, nargs):
+        if name.startswith("D."):
+            f = name[2:]
+            seen.add(f)
+            if f in dev.sigs and nargs not in (0, dev.sigs[f]):
+                bad.append((name, nargs, dev.sigs[f]))
+    for d in decls:
+        L.applications(d[3] if d[0] == "fun" else d[2], visit)
+        L.applications(d[4] if d[0] == "fun" else d[3], visit)
+    assert not bad, bad
+    assert {"toDevice", "fromDevice", "dot", "iamax", "scal", "copy", "swap", "rot", "axpy", "withContext"} <= seen, seen
 
 
 def module_scope(path):
