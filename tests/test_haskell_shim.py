@@ -183,3 +183,16 @@ def test_export_lists_name_things_that_exist(path):
     # every top-level function has a type signature (the reference builds with -Wall -Werror, lambda-blas.cabal:48)
     unsigned = [d[1] for d in decls if d[0] == "fun" and d[1] not in p.sigs]
     assert not unsigned, unsigned
+
+
+@pytest.mark.skipif(not os.path.isdir(REF) or not __import__("shutil").which("patch"), reason="needs /root/reference and patch(1)")
+def test_patches_apply_to_the_reference_as_it_lies_there(tmp_path):
+    """hs/patches/*.patch are what INTEGRATION.md tells a maintainer to apply: they must apply cleanly (no fuzz, no offset)"""
+    import shutil
+    import subprocess
+    (tmp_path / "src" / "Numerical" / "BLAS").mkdir(parents=True)
+    shutil.copy(REF + "/lambda-blas.cabal", tmp_path / "lambda-blas.cabal")
+    shutil.copy(REF + "/src/Numerical/BLAS/Types.hs", tmp_path / "src" / "Numerical" / "BLAS" / "Types.hs")
+    for name in ("lambda-blas.cabal.patch", "Types.hs.patch"):
+        r = subprocess.run(["patch", "-p1", "--dry-run", "-i", os.path.join(ROOT, "hs", "patches", name)], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 0 and "fuzz" not in r.stdout and "offset" not in r.stdout, (name, r.stdout, r.stderr)
